@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py -- Mpix/s advected on BASELINE.json's config[1]:
+2048x2048 synthetic radar frames, motion field + 12-leadtime semi-Lagrangian
+extrapolation.
+
+    python bench.py --gpus N --steps K --warmup W          (ours, CUDA)
+    python bench.py --impl reference ...                   (CPU oracle port, host cores)
+
+One "step" = one pass of the hot path over one batch of synthetic input:
+  [rank 0] motion field from the last frames (dense Lucas-Kanade)         (when built)
+  [N > 1]  NCCL broadcast of the motion field (the only collective)
+  [all]    12-leadtime semi-Lagrangian extrapolation of this rank's field
+Metric: Mpix/s advected = (N * T * m * n) / step time, max over ranks (weak scaling:
+per-GPU work is fixed, one field per GPU, as ensemble members shard in nowcasts.steps).
+
+value  : inputs resident in HBM, device time by CUDA events, L2 flushed between steps.
+e2e    : the same step through the public NumPy API with pinned HOST buffers, H2D and
+         D2H copies inside the timed region.
+roofline: the semi-Lagrangian trajectory kernel (sl_multistep_kernel), algorithmic
+         bytes per launch / CUDA-event time of that launch, vs MEASURED_PEAKS.json.
+cpu_baseline: the CPU oracle (port of the reference path) on the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+M = N_ = 2048
+T_LEAD = 12
+METRIC = "Mpix/s advected (2048^2 frame, 12 leadtimes)"
+UNIT = "Mpix/s"
+
+
+def have_lk():
+    try:
+        from pysteps_b200.motion import lucaskanade  # noqa: F401
+        return True
+    except ImportError:
+        return False
+
+
+def workload_name(lk):
+    return ("lk_dense+semilagrangian_T12_2048x2048" if lk else "semilagrangian_T12_2048x2048")
+
+
+def make_inputs(seed, lk):
+    """float32 fields (the synthetic data are float32-exact; float32 arrays keep the
+    reference's float64 arithmetic but halve field storage)."""
+    from pysteps_b200 import _synthetic as syn
+    frames = syn.rain_frames(M, N_, 2, seed).astype(np.float32)
+    V = syn.velocity_field(M, N_, seed).astype(np.float32)
+    return frames, V
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for k, nm in enumerate(names)
+                   if any(len(s) > 2 + k and s[2 + k].lower() == "active" for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------- CPU legs
+def cpu_step(frames, V, lk):
+    """The oracle port of one step on host cores."""
+    from oracle import semilagrangian as ora
+    if lk:
+        from oracle import lucaskanade as ora_lk
+        V = ora_lk.dense_lucaskanade(frames.astype(np.float64))
+    return ora.extrapolate(frames[-1], V, T_LEAD)
+
+
+def cpu_baseline(frames, V, lk, reps=1):
+    import oracle
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        cpu_step(frames, V, lk)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {"value": T_LEAD * M * N_ / best / 1e6, "unit": UNIT, "cores": oracle.num_threads(),
+            "kind": "port",
+            "sample": f"{reps} full step(s) of {workload_name(lk)} (oracle C/NumPy port, "
+                      f"OpenMP {oracle.num_threads()} threads), best of {reps}; {best:.2f} s"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    lk = have_lk_oracle()
+    frames, V = make_inputs(0, lk)
+    import oracle
+    for _ in range(args.warmup):
+        cpu_step(frames[:, :256, :256], V[:, :256, :256], lk)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_step(frames, V, lk)
+    dt = time.perf_counter() - t0
+    val = args.steps * T_LEAD * M * N_ / dt / 1e6
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(lk), "frame": [M, N_], "leadtimes": T_LEAD},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": oracle.num_threads(),
+                             "kind": "port",
+                             "sample": f"{args.steps} full step(s), oracle port of the reference "
+                                       f"path, OpenMP {oracle.num_threads()} threads"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def have_lk_oracle():
+    try:
+        from oracle import lucaskanade  # noqa: F401
+        return have_lk()
+    except ImportError:
+        return False
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import pysteps_b200
+    from pysteps_b200 import _lib
+    extrap = pysteps_b200.extrapolation.get_method("semilagrangian")
+    lk = have_lk()
+    motion = None
+    if lk:
+        from pysteps_b200 import motion as b200_motion
+        motion = b200_motion.get_method("lk")
+
+    frames_h, V_h = make_inputs(rank, lk)
+    # pinned host buffers for the e2e leg
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()  # noqa: E731
+    frames_h = pin(frames_h)
+    V_h = pin(V_h)
+    frames_d = torch.from_numpy(frames_h).cuda()
+    V_d = torch.from_numpy(V_h).cuda()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def step_device():
+        """inputs resident in HBM; results stay in HBM."""
+        if lk:
+            if rank == 0:
+                Vd = motion(frames_d)
+            else:
+                Vd = torch.empty((2, M, N_), dtype=torch.float64, device="cuda")
+        else:
+            Vd = V_d
+        if world > 1:
+            dist.broadcast(Vd, src=0)
+        return extrap(frames_d[-1], Vd, T_LEAD)
+
+    def step_host():
+        """public NumPy API: H2D of inputs and D2H of the result inside."""
+        if lk:
+            Vh = motion(frames_h) if rank == 0 else None
+            if world > 1:
+                Vd = torch.from_numpy(Vh).cuda() if rank == 0 else \
+                    torch.empty((2, M, N_), dtype=torch.float64, device="cuda")
+                dist.broadcast(Vd, src=0)
+                return extrap(frames_h[-1], Vd, T_LEAD).cpu().numpy()
+        else:
+            Vh = V_h
+        return extrap(frames_h[-1], Vh, T_LEAD)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ------------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    launches0 = _lib.load().b200_launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    with ClockSampler(local) as clocks, _lib.Trace() as trace:
+        for s, e in ev:
+            flush.fill_(1)  # L2 flush between timed iterations (outside the events)
+            barrier()
+            s.record()
+            step_device()
+            e.record()
+        barrier()
+    launches = _lib.load().b200_launch_count() - launches0
+    dev_ms = sum(s.elapsed_time(e) for s, e in ev)
+    tr = trace.summary()
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    value = world * args.steps * T_LEAD * M * N_ / (dev_ms * 1e-3) / 1e6
+
+    # ---- end-to-end timing (host buffers) --------------------------------------------
+    for _ in range(max(1, args.warmup // 2)):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = step_host()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_val = world * args.steps * T_LEAD * M * N_ / e2e_s / 1e6
+    h2d = frames_h[-1].nbytes + (frames_h.nbytes if lk else V_h.nbytes)
+    d2h = out.nbytes + (2 * M * N_ * 8 if lk else 0)
+
+    if rank == 0:
+        # ---- roofline of the trajectory kernel (this run's launches) -----------------
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650"
+        k_ms = tr.get("b200_sl_extrapolate", [])
+        k_avg = sum(k_ms) / len(k_ms) if k_ms else float("nan")
+        vbytes = 8 if lk else 4  # LK returns float64 fields, synthetic V is float32
+        alg_bytes = M * N_ * (2 * vbytes + 4 + 4 * T_LEAD)
+        achieved = alg_bytes / (k_avg * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "sl_traffic.json")))["bytes_per_launch"]
+        except Exception:
+            pass
+        roofline = {"kernel": "sl_multistep_kernel", "bound": "hbm", "achieved": achieved,
+                    "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                    "peak_source": peak_src, "kernel_ms": k_avg,
+                    "algorithmic_bytes_per_launch": alg_bytes}
+        stage_ms = {k: sum(v) / args.steps for k, v in tr.items()}
+        cpu = cpu_baseline(frames_h, V_h, have_lk_oracle()) if not args.no_cpu else None
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64 trajectory arithmetic, f32 field storage", "data": "synthetic",
+                "config": {"workload": workload_name(lk), "frame": [M, N_], "leadtimes": T_LEAD,
+                           "fields_per_gpu": 1, "l2": "flushed between timed steps (256 MB fill)",
+                           "parallelism": f"1 field per GPU x{world}, NCCL broadcast of the motion field"},
+                "clocks": clocks.summary(),
+                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / args.steps},
+                "gpu_launches": int(launches),
+                "roofline": roofline, "cpu_baseline": cpu, "stage_ms_per_step": stage_ms}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

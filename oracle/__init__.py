@@ -1,0 +1,39 @@
+"""CPU oracle for the pysteps advection hot path -- TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs
+may import this package.  The product package ``pysteps_b200`` never does; it
+fails loudly when its CUDA library is missing instead of falling back here.
+
+``oracle.lib()`` returns the ctypes handle of ``liboracle.so`` (plain C,
+strict IEEE float64), building it with ``make`` on first use.
+"""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith(".c")]
+    stale = (not os.path.exists(so)) or any(
+        os.path.getmtime(s) > os.path.getmtime(so) for s in srcs
+    )
+    if force or stale:
+        cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+        subprocess.check_call(["make", "-s", "-B", "-C", _HERE, f"CC={cc}"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = ctypes.CDLL(build())
+        _LIB.ora_num_threads.restype = ctypes.c_int
+    return _LIB
+
+
+def num_threads():
+    return int(lib().ora_num_threads())

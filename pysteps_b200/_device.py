@@ -1,0 +1,78 @@
+"""Device-memory plumbing.  PyTorch is used ONLY as a container for device /
+pinned-host memory and as the owner of the CUDA stream; all arithmetic runs in
+the kernels of ``libpysteps_b200.so``."""
+import threading
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_init_lock = threading.Lock()
+_initialised = False
+
+
+def require_cuda():
+    """Fail loudly when no GPU is usable -- there is no CPU path in this package."""
+    global _initialised
+    if _initialised:
+        return
+    with _init_lock:
+        if _initialised:
+            return
+        if not torch.cuda.is_available():
+            raise RuntimeError("pysteps_b200 needs a CUDA device (B200, sm_100a); none is "
+                               "available and there is no CPU fallback.")
+        torch.cuda.init()
+        lib = _lib.load()
+        torch.zeros(1, device="cuda")  # make sure the primary context exists
+        sm = _lib.c_int(0)
+        mj = _lib.c_int(0)
+        mn = _lib.c_int(0)
+        _lib.check(lib.b200_device_info(sm, mj, mn, None, 0))
+        _initialised = True
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def dtype_code(dt):
+    if dt == torch.float32 or dt == np.float32:
+        return _lib.F32
+    if dt == torch.float64 or dt == np.float64:
+        return _lib.F64
+    raise TypeError(f"unsupported dtype {dt}")
+
+
+def is_device_tensor(x):
+    return isinstance(x, torch.Tensor) and x.is_cuda
+
+
+def to_device(a, dtype=None):
+    """numpy array / torch tensor -> contiguous CUDA tensor (async H2D on the current stream;
+    full PCIe speed when the host buffer is pinned)."""
+    if isinstance(a, torch.Tensor):
+        t = a
+    else:
+        a = np.asarray(a)
+        if not a.flags.c_contiguous or not a.flags.writeable:
+            a = np.ascontiguousarray(a) if a.flags.writeable else np.array(a, order="C")
+        t = torch.from_numpy(a)
+    if not t.is_cuda:
+        t = t.to("cuda", non_blocking=True)
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def to_host(t):
+    """CUDA tensor -> numpy array backed by pinned memory (async D2H + one sync)."""
+    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    host.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return host.numpy()
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()

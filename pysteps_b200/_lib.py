@@ -1,0 +1,124 @@
+"""ctypes binding of ``libpysteps_b200.so`` (the C ABI declared in
+``include/pysteps_b200.h``).
+
+There is NO fallback: if the shared library is missing or a call fails, the
+product path raises.  Build it with ``python -c "import __graft_entry__ as g;
+g.build()"`` or ``make -C pysteps_b200/csrc``.
+"""
+import ctypes
+import os
+import re
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpysteps_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "pysteps_b200.h")
+
+F32, F64 = 0, 1
+MODE_CONSTANT, MODE_NEAREST = 0, 1
+LAYOUT_PLANAR, LAYOUT_INTERLEAVED = 0, 1
+
+_lib = None
+_lock = threading.Lock()
+
+c_void_p, c_int, c_i64, c_double = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double
+c_dp = ctypes.POINTER(ctypes.c_double)
+
+# name -> (restype, argtypes); must list every function declared in the header
+_SIGNATURES = {
+    "b200_version": (c_int, []),
+    "b200_last_error": (ctypes.c_char_p, []),
+    "b200_launch_count": (ctypes.c_longlong, []),
+    "b200_device_info": (c_int, [ctypes.POINTER(c_int)] * 3 + [ctypes.c_char_p, c_int]),
+    "b200_sl_extrapolate": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_dp, c_int, c_double,
+                                    c_int, c_double, c_int, c_int, c_int, c_int, c_int, c_int,
+                                    c_void_p, c_void_p, c_void_p]),
+    "b200_sl_interleave_velocity": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "b200_sl_extrapolate_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_dp, c_int,
+                                         c_double, c_int, c_double, c_int, c_int, c_int, c_int,
+                                         c_int, c_void_p, c_void_p]),
+    "b200_field_stats": (c_int, [c_void_p, c_int, c_i64, c_void_p, c_void_p]),
+    "b200_convert": (c_int, [c_void_p, c_int, c_void_p, c_int, c_i64, c_void_p]),
+}
+
+
+def header_symbols():
+    """Names of all functions declared in include/pysteps_b200.h."""
+    with open(HEADER_PATH) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    return sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", text)))
+
+
+def load():
+    """Load the CUDA library; raise RuntimeError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    f"pysteps_b200: CUDA library not built ({LIB_PATH} missing). "
+                    "Run `make -C pysteps_b200/csrc` (needs nvcc, sm_100a). "
+                    "There is no CPU fallback.")
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in _SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().b200_last_error()
+        raise RuntimeError(f"pysteps_b200 CUDA call failed (code {rc}): "
+                           f"{msg.decode(errors='replace') if msg else ''}")
+
+
+# --- optional tracing: CUDA events around every C-ABI call (bench.py / profiling) ---------
+_trace = None
+
+
+class Trace:
+    """Records (name, start_event, end_event) for each traced C-ABI call on the current
+    torch stream.  ``summary()`` synchronises and returns {name: [ms, ...]}."""
+
+    def __init__(self):
+        self.records = []
+
+    def __enter__(self):
+        global _trace
+        self._prev = _trace
+        _trace = self
+        return self
+
+    def __exit__(self, *exc):
+        global _trace
+        _trace = self._prev
+
+    def summary(self):
+        import torch
+        torch.cuda.synchronize()
+        out = {}
+        for name, s, e in self.records:
+            out.setdefault(name, []).append(s.elapsed_time(e))
+        return out
+
+
+def call(name, *args):
+    """Invoke a C-ABI function by name, raising on failure; traced when a Trace is active."""
+    fn = getattr(load(), name)
+    tr = _trace
+    if tr is None:
+        check(fn(*args))
+        return
+    import torch
+    s = torch.cuda.Event(enable_timing=True)
+    e = torch.cuda.Event(enable_timing=True)
+    s.record()
+    rc = fn(*args)
+    e.record()
+    tr.records.append((name, s, e))
+    check(rc)

