@@ -24,37 +24,68 @@ constexpr int SL_BX = 32, SL_BY = 8;
 enum { SL_INIT_FRESH = 0, SL_INIT_PREV = 1, SL_INIT_RESUME = 2 };
 
 struct SLParams {
-    const void *Vi;         // (m,n) interleaved (vx,vy), field dtype
-    const void *precip;     // (m,n) or null
+    const void *Vi;         // (m,n) double2 (vx,vy)
+    const void *precip;     // (m,n) float64 or null
     const double *xy;       // (2,m,n) or null -> pixel grid
     const double *disp_in;  // (2,m,n) or null
     const double *vinc_in;  // (2,m,n), RESUME only
     double *disp_out;       // (2,m,n) or null
     double *vinc_out;       // (2,m,n) or null
     void *out;              // (T,m,n) planes of this chunk
-    int m, n, T, n_iter, ti_offset, init_mode, mode, has_prev;
-    double vts, cval;
-    double td[SL_MAX_T];
+    int m, n, T, n_iter, ti_offset, init_mode, mode, has_prev, vel_f32;
+    double vts, td0, cval;
+    double scale[SL_MAX_T];  // td / vel_timestep per leadtime
 };
 
-template <typename F> struct Vec2;
-template <> struct Vec2<float> { using type = float2; };
-template <> struct Vec2<double> { using type = double2; };
+// ---- exact float64 building blocks ---------------------------------------------------
+// The XU pipe (conversions, FRND, MUFU) is the scarce unit for this kernel, so the hot
+// path avoids it: fields are pre-widened to float64 once per call, floor() comes from a
+// magic-constant add on the FP64 pipe, and no division is issued per leadtime.
 
-// one axis of scipy's order-1 footprint in mode="nearest": taps floor(c),
-// floor(c)+1 each clamped to [0, L-1]; weights w0 = 1 - t, w1 = 1 - w0.
-__device__ __forceinline__ void axis_nearest(double c, int L, int &i0, int &i1, double &w0,
-                                             double &w1) {
-    const double f = floor(c);
+constexpr double SL_MAGIC = 6755399441055744.0;  // 2^52 + 2^51
+
+// floor(c) and (int)floor(c) for -2^31 < c < 2^31 without FRND/F2I
+__device__ __forceinline__ void floor_magic(double c, double &f, int &i) {
+    const double t = __dadd_rn(c, SL_MAGIC);  // nearest integer (ties to even) in the low bits
+    i = __double2loint(t);
+    f = __dsub_rn(t, SL_MAGIC);
+    if (f > c) {
+        f = __dsub_rn(f, 1.0);
+        i -= 1;
+    }
+}
+
+struct Axis {
+    int i0, i1;      // tap indices, mode "nearest" (clamped to [0, L-1])
+    int f0;          // (int)floor(c), unclamped, valid when `inside`
+    double w0, w1;   // 1 - t, 1 - w0
+    bool inside;     // 0 <= c <= L-1  (mode "constant" validity)
+};
+
+// one axis of scipy's order-1 footprint: taps floor(c), floor(c)+1; weights w0 = 1 - t,
+// w1 = 1 - w0 with t = c - floor(c).
+__device__ __forceinline__ Axis make_axis(double c, int L) {
+    Axis a;
+    double f;
+    int i;
+    if (c > -2.0 && c < (double)L + 1.0) {
+        floor_magic(c, f, i);
+    } else {
+        // rare (trajectory far outside the domain, or NaN): generic path.
+        // (npy_intp)floor(c) on x86-64: out-of-range / non-finite -> INT64_MIN (both taps 0)
+        f = floor(c);
+        double fc = (fabs(f) < 9223372036854775808.0) ? f : -1.0;
+        fc = fmin(fmax(fc, -1.0), (double)L);
+        i = (int)fc;
+    }
     const double t = __dsub_rn(c, f);
-    w0 = __dsub_rn(1.0, t);
-    w1 = __dsub_rn(1.0, w0);
-    // (npy_intp)floor(c) on x86-64: out-of-range / non-finite -> INT64_MIN (both taps 0)
-    double fc = (fabs(f) < 9223372036854775808.0) ? f : -1.0;
-    fc = fmin(fmax(fc, -1.0), (double)L);
-    const int i = (int)fc;
-    i0 = min(max(i, 0), L - 1);
-    i1 = min(max(i + 1, 0), L - 1);
+    a.w0 = __dsub_rn(1.0, t);
+    a.w1 = __dsub_rn(1.0, a.w0);
+    a.f0 = i;
+    a.i0 = min(max(i, 0), L - 1);
+    a.i1 = min(max(i + 1, 0), L - 1);
+    a.inside = (c >= 0.0) && (c <= (double)(L - 1));
+    return a;
 }
 
 // sum_{taps} ((a * wy) * wx), left to right from 0.0 (scipy accumulation order)
@@ -67,22 +98,77 @@ __device__ __forceinline__ double bilin(double a00, double a01, double a10, doub
     return t;
 }
 
-// interpolate_motion (semilagrangian.py:181-198) for one pixel
-template <typename F>
-__device__ __forceinline__ void sample_velocity(const typename Vec2<F>::type *__restrict__ Vi,
-                                                int m, int n, double cy, double cx, double scale,
-                                                int n_iter, double &vx, double &vy) {
-    int y0, y1, x0, x1;
+// ---- slow (generic) path: any coordinate, per-tap index clamping --------------------
+__device__ __noinline__ void slow_velocity(const double2 *__restrict__ Vi, int m, int n, double cy,
+                                           double cx, double &vx, double &vy) {
+    const Axis ay = make_axis(cy, m), ax = make_axis(cx, n);
+    const double2 *r0 = Vi + (size_t)ay.i0 * n;
+    const double2 *r1 = Vi + (size_t)ay.i1 * n;
+    const double2 a00 = __ldg(r0 + ax.i0), a01 = __ldg(r0 + ax.i1);
+    const double2 a10 = __ldg(r1 + ax.i0), a11 = __ldg(r1 + ax.i1);
+    vx = bilin(a00.x, a01.x, a10.x, a11.x, ay.w0, ay.w1, ax.w0, ax.w1);
+    vy = bilin(a00.y, a01.y, a10.y, a11.y, ay.w0, ay.w1, ax.w0, ax.w1);
+}
+
+// map_coordinates(precip, order=1, mode, cval) for one pixel (:221-232), generic path
+__device__ __noinline__ double slow_precip(const double *__restrict__ P, int m, int n, double cy,
+                                           double cx, int mode, double cval) {
+    const Axis ay = make_axis(cy, m), ax = make_axis(cx, n);
+    int y0 = ay.i0, y1 = ay.i1, x0 = ax.i0, x1 = ax.i1;
+    if (mode == B200_MODE_CONSTANT) {
+        if (!(ay.inside && ax.inside)) return cval;
+        // the tap one past the end (only when c == L-1) is mirrored and still read
+        y0 = ay.f0; x0 = ax.f0;
+        y1 = (y0 + 1 < m) ? y0 + 1 : (m > 1 ? m - 2 : 0);
+        x1 = (x0 + 1 < n) ? x0 + 1 : (n > 1 ? n - 2 : 0);
+    }
+    const double *r0 = P + (size_t)y0 * n;
+    const double *r1 = P + (size_t)y1 * n;
+    return bilin(__ldg(r0 + x0), __ldg(r0 + x1), __ldg(r1 + x0), __ldg(r1 + x1), ay.w0, ay.w1,
+                 ax.w0, ax.w1);
+}
+
+// ---- fast path: footprint strictly inside the array ------------------------------------
+// floor via a round-DOWN add of 2^52+2^51: the sum's low word IS (int)floor(c) and its high
+// word is 0x43380000 exactly when 0 <= floor(c) < 2^31, so validity, floor and the integer
+// index cost two FP64-pipe adds and integer compares -- no FRND/F2I/I2F (XU pipe).
+struct Foot {
+    int base;  // y0 * n + x0
     double wy0, wy1, wx0, wx1;
-    axis_nearest(cy, m, y0, y1, wy0, wy1);
-    axis_nearest(cx, n, x0, x1, wx0, wx1);
-    const typename Vec2<F>::type *r0 = Vi + (size_t)y0 * n;
-    const typename Vec2<F>::type *r1 = Vi + (size_t)y1 * n;
-    const auto a00 = __ldg(r0 + x0), a01 = __ldg(r0 + x1);
-    const auto a10 = __ldg(r1 + x0), a11 = __ldg(r1 + x1);
-    vx = bilin((double)a00.x, (double)a01.x, (double)a10.x, (double)a11.x, wy0, wy1, wx0, wx1);
-    vy = bilin((double)a00.y, (double)a01.y, (double)a10.y, (double)a11.y, wy0, wy1, wx0, wx1);
-    if (sizeof(F) == 4) {
+    bool interior;  // taps (y0, y0+1) x (x0, x0+1) all in range: modes coincide, no clamping
+};
+
+__device__ __forceinline__ Foot footprint(double cy, double cx, int n, int ymax, int xmax) {
+    Foot f;
+    const double sy = __dadd_rd(cy, SL_MAGIC), sx = __dadd_rd(cx, SL_MAGIC);
+    const int iy = __double2loint(sy), ix = __double2loint(sx);
+    f.interior = (__double2hiint(sy) == 0x43380000) & (__double2hiint(sx) == 0x43380000) &
+                 (iy <= ymax) & (ix <= xmax) & (iy >= 0) & (ix >= 0);
+    const double ty = __dsub_rn(cy, __dsub_rn(sy, SL_MAGIC));
+    const double tx = __dsub_rn(cx, __dsub_rn(sx, SL_MAGIC));
+    f.wy0 = __dsub_rn(1.0, ty); f.wy1 = __dsub_rn(1.0, f.wy0);
+    f.wx0 = __dsub_rn(1.0, tx); f.wx1 = __dsub_rn(1.0, f.wx0);
+    f.base = iy * n + ix;
+    return f;
+}
+
+// interpolate_motion (semilagrangian.py:181-198) for one pixel; returns the footprint so
+// the precip warp at the same coordinates can reuse it
+__device__ __forceinline__ Foot sample_velocity(const double2 *__restrict__ Vi, int m, int n,
+                                                int ymax, int xmax, double cy, double cx,
+                                                double scale, int n_iter, bool vel_f32,
+                                                double &vx, double &vy) {
+    const Foot f = footprint(cy, cx, n, ymax, xmax);
+    if (f.interior) {
+        const double2 *q = Vi + f.base;
+        const double2 a00 = __ldg(q), a01 = __ldg(q + 1);
+        const double2 a10 = __ldg(q + n), a11 = __ldg(q + n + 1);
+        vx = bilin(a00.x, a01.x, a10.x, a11.x, f.wy0, f.wy1, f.wx0, f.wx1);
+        vy = bilin(a00.y, a01.y, a10.y, a11.y, f.wy0, f.wy1, f.wx0, f.wx1);
+    } else {
+        slow_velocity(Vi, m, n, cy, cx, vx, vy);
+    }
+    if (vel_f32) {
         // float32 velocity: map_coordinates returns the input dtype, so the reference
         // stores the sampled increment rounded to float32 (:192-193)
         vx = (double)__double2float_rn(vx);
@@ -94,52 +180,33 @@ __device__ __forceinline__ void sample_velocity(const typename Vec2<F>::type *__
     }
     vx = __dmul_rn(vx, scale);  // :198
     vy = __dmul_rn(vy, scale);
-}
-
-// map_coordinates(precip, order=1, mode, cval) for one pixel (:221-232)
-template <typename F>
-__device__ __forceinline__ double sample_precip(const F *__restrict__ P, int m, int n, double cy,
-                                                double cx, int mode, double cval) {
-    int y0, y1, x0, x1;
-    double wy0, wy1, wx0, wx1;
-    if (mode == B200_MODE_CONSTANT) {
-        if (!(cy >= 0.0 && cy <= (double)(m - 1) && cx >= 0.0 && cx <= (double)(n - 1)))
-            return cval;
-        const double fy = floor(cy), fx = floor(cx);
-        const double ty = __dsub_rn(cy, fy), tx = __dsub_rn(cx, fx);
-        wy0 = __dsub_rn(1.0, ty); wy1 = __dsub_rn(1.0, wy0);
-        wx0 = __dsub_rn(1.0, tx); wx1 = __dsub_rn(1.0, wx0);
-        y0 = (int)fy; x0 = (int)fx;
-        // the tap one past the end (only when c == L-1) is mirrored and still read
-        y1 = (y0 + 1 < m) ? y0 + 1 : (m > 1 ? m - 2 : 0);
-        x1 = (x0 + 1 < n) ? x0 + 1 : (n > 1 ? n - 2 : 0);
-    } else {
-        axis_nearest(cy, m, y0, y1, wy0, wy1);
-        axis_nearest(cx, n, x0, x1, wx0, wx1);
-    }
-    const F *r0 = P + (size_t)y0 * n;
-    const F *r1 = P + (size_t)y1 * n;
-    return bilin((double)__ldg(r0 + x0), (double)__ldg(r0 + x1), (double)__ldg(r1 + x0),
-                 (double)__ldg(r1 + x1), wy0, wy1, wx0, wx1);
+    return f;
 }
 
 template <typename F> __device__ __forceinline__ F from_double(double v);
 template <> __device__ __forceinline__ float from_double<float>(double v) { return __double2float_rn(v); }
 template <> __device__ __forceinline__ double from_double<double>(double v) { return v; }
 
-template <typename FV, typename F>
+// NITER1: n_iter == 1 (the default and what every nowcast method uses) compiled without
+// the inner loop / division branches.
+template <typename F, bool NITER1>
 __global__ void __launch_bounds__(SL_BX *SL_BY)
 sl_multistep_kernel(const __grid_constant__ SLParams p) {
-    using V2 = typename Vec2<FV>::type;
     const int x = blockIdx.x * SL_BX + threadIdx.x;
     const int y = blockIdx.y * SL_BY + threadIdx.y;
     if (x >= p.n || y >= p.m) return;
     const int m = p.m, n = p.n;
+    const int ymax = m - 2, xmax = n - 2;  // largest interior floor index (negative: none)
     const size_t N = (size_t)m * n;
-    const size_t idx = (size_t)y * n + x;
-    const V2 *__restrict__ Vi = (const V2 *)p.Vi;
-    const F *__restrict__ P = (const F *)p.precip;
-    F *__restrict__ out = (F *)p.out;
+    const int idx = y * n + x;
+    const double2 *__restrict__ Vi = (const double2 *)p.Vi;
+    const double *__restrict__ P = (const double *)p.precip;
+    F *__restrict__ out = (F *)p.out + idx;
+    const bool vel_f32 = p.vel_f32 != 0;
+    const int n_iter = NITER1 ? 1 : p.n_iter;
+    const int mode = p.mode;
+    const double cval = p.cval;
+    const int T = p.T;
 
     double gx, gy;  // xy_coords of this pixel (:174-179)
     if (p.xy) {
@@ -154,43 +221,58 @@ sl_multistep_kernel(const __grid_constant__ SLParams p) {
     if (p.init_mode == SL_INIT_FRESH) {
         // :201-203  displacement = 0 ; velocity_inc = V * tdiff[0] / vel_timestep
         dx = 0.0; dy = 0.0;
-        const V2 v = Vi[idx];
-        ux = __ddiv_rn(__dmul_rn((double)v.x, p.td[0]), p.vts);
-        uy = __ddiv_rn(__dmul_rn((double)v.y, p.td[0]), p.vts);
+        const double2 v = Vi[idx];
+        ux = __ddiv_rn(__dmul_rn(v.x, p.td0), p.vts);
+        uy = __ddiv_rn(__dmul_rn(v.y, p.td0), p.vts);
     } else if (p.init_mode == SL_INIT_PREV) {
         // :205-207
         dx = p.disp_in[idx]; dy = p.disp_in[N + idx];
-        sample_velocity<FV>(Vi, m, n, __dadd_rn(gy, dy), __dadd_rn(gx, dx),
-                           __ddiv_rn(p.td[0], p.vts), p.n_iter, ux, uy);
+        sample_velocity(Vi, m, n, ymax, xmax, __dadd_rn(gy, dy), __dadd_rn(gx, dx), p.scale[0],
+                        n_iter, vel_f32, ux, uy);
     } else {
         dx = p.disp_in[idx]; dy = p.disp_in[N + idx];
         ux = p.vinc_in[idx]; uy = p.vinc_in[N + idx];
     }
 
-    for (int ti = 0; ti < p.T; ti++) {
-        const double scale = __ddiv_rn(p.td[ti], p.vts);  // td / vel_timestep (:198)
-        if (p.n_iter > 0) {
-            for (int k = 0; k < p.n_iter; k++) {  // :211-214
-                const double hx = __dsub_rn(dx, __ddiv_rn(ux, 2.0));
-                const double hy = __dsub_rn(dy, __ddiv_rn(uy, 2.0));
-                sample_velocity<FV>(Vi, m, n, __dadd_rn(gy, hy), __dadd_rn(gx, hx), scale,
-                                   p.n_iter, ux, uy);
+    for (int ti = 0; ti < T; ti++) {
+        const double scale = p.scale[ti];  // td / vel_timestep (:198), divided on the host
+        Foot f;
+        f.interior = false;
+        bool have_foot = false;  // f describes xy + displacement
+        if (n_iter > 0) {
+            for (int k = 0; k < n_iter; k++) {  // :211-214
+                // velocity_inc / 2.0 == velocity_inc * 0.5 exactly
+                const double hx = __dsub_rn(dx, __dmul_rn(ux, 0.5));
+                const double hy = __dsub_rn(dy, __dmul_rn(uy, 0.5));
+                sample_velocity(Vi, m, n, ymax, xmax, __dadd_rn(gy, hy), __dadd_rn(gx, hx), scale,
+                                n_iter, vel_f32, ux, uy);
                 dx = __dsub_rn(dx, ux);
                 dy = __dsub_rn(dy, uy);
-                sample_velocity<FV>(Vi, m, n, __dadd_rn(gy, dy), __dadd_rn(gx, dx), scale,
-                                   p.n_iter, ux, uy);
+                f = sample_velocity(Vi, m, n, ymax, xmax, __dadd_rn(gy, dy), __dadd_rn(gx, dx),
+                                    scale, n_iter, vel_f32, ux, uy);
             }
+            // the precip warp samples at xy + displacement: the coordinates (hence footprint
+            // and weights) of the last velocity gather
+            have_foot = true;
         } else {  // :215-219
             if (ti + p.ti_offset > 0 || p.has_prev)
-                sample_velocity<FV>(Vi, m, n, __dadd_rn(gy, dy), __dadd_rn(gx, dx), scale,
-                                   p.n_iter, ux, uy);
+                sample_velocity(Vi, m, n, ymax, xmax, __dadd_rn(gy, dy), __dadd_rn(gx, dx), scale,
+                                n_iter, vel_f32, ux, uy);
             dx = __dsub_rn(dx, ux);
             dy = __dsub_rn(dy, uy);
         }
         if (P) {
-            const double v = sample_precip<F>(P, m, n, __dadd_rn(gy, dy), __dadd_rn(gx, dx),
-                                              p.mode, p.cval);
-            out[(size_t)ti * N + idx] = from_double<F>(v);
+            const double cy = __dadd_rn(gy, dy), cx = __dadd_rn(gx, dx);
+            if (!have_foot) f = footprint(cy, cx, n, ymax, xmax);
+            double v;
+            if (f.interior) {
+                const double *q = P + f.base;
+                v = bilin(__ldg(q), __ldg(q + 1), __ldg(q + n), __ldg(q + n + 1), f.wy0, f.wy1,
+                          f.wx0, f.wx1);
+            } else {
+                v = slow_precip(P, m, n, cy, cx, mode, cval);
+            }
+            out[(size_t)ti * N] = from_double<F>(v);
         }
     }
     if (p.disp_out) {
@@ -203,13 +285,38 @@ sl_multistep_kernel(const __grid_constant__ SLParams p) {
     }
 }
 
-// planar (2,m,n) -> interleaved (m,n){x,y}; one pass, 16 B per thread-iteration
+// (2,m,n) planar or (m,n,2) interleaved velocity of dtype F -> (m,n) double2
 template <typename F>
 __global__ void __launch_bounds__(256)
-interleave_kernel(const F *__restrict__ V, typename Vec2<F>::type *__restrict__ Vi, size_t N) {
+widen_velocity_kernel(const F *__restrict__ V, double2 *__restrict__ Vi, size_t N, int interleaved) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
-        typename Vec2<F>::type v;
+        double2 v;
+        if (interleaved) {
+            v.x = (double)__ldg(V + 2 * i);
+            v.y = (double)__ldg(V + 2 * i + 1);
+        } else {
+            v.x = (double)__ldg(V + i);
+            v.y = (double)__ldg(V + N + i);
+        }
+        Vi[i] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+widen_field_kernel(const float *__restrict__ a, double *__restrict__ o, size_t N) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride)
+        o[i] = (double)__ldg(a + i);
+}
+
+// planar (2,m,n) -> interleaved (m,n,2), same dtype
+template <typename F, typename F2>
+__global__ void __launch_bounds__(256)
+interleave_kernel(const F *__restrict__ V, F2 *__restrict__ Vi, size_t N) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+        F2 v;
         v.x = __ldg(V + i);
         v.y = __ldg(V + N + i);
         Vi[i] = v;
@@ -220,15 +327,23 @@ template <typename FV, typename F>
 int sl_run(const void *precip, const void *velocity, const double *xy, const double *disp_prev,
            const double *tdiff, int T, double vts, int n_iter, double outval, int mode,
            int layout, int m, int n, void *out, double *disp_out, cudaStream_t stream) {
-    using V2 = typename Vec2<FV>::type;
     const size_t N = (size_t)m * n;
-    b200::Scratch vi, st_disp, st_vinc;
+    b200::Scratch vi, pw, st_disp, st_vinc;
+    const int sblocks = (int)std::min<size_t>((N + 255) / 256, (size_t)b200::num_sms() * 16);
+    // widen the fields to float64 once (exact), so the trajectory loop issues no conversions
     const void *vi_ptr = velocity;
-    if (layout == B200_LAYOUT_PLANAR) {
-        B200_CUDA(vi.alloc(N * sizeof(V2), stream));
+    if (!(sizeof(FV) == 8 && layout == B200_LAYOUT_INTERLEAVED)) {
+        B200_CUDA(vi.alloc(N * sizeof(double2), stream));
         vi_ptr = vi.p;
-        const int blocks = (int)std::min<size_t>((N + 255) / 256, (size_t)b200::num_sms() * 16);
-        interleave_kernel<FV><<<blocks, 256, 0, stream>>>((const FV *)velocity, (V2 *)vi.p, N);
+        widen_velocity_kernel<FV><<<sblocks, 256, 0, stream>>>(
+            (const FV *)velocity, (double2 *)vi.p, N, layout == B200_LAYOUT_INTERLEAVED);
+        B200_LAUNCH_CHECK();
+    }
+    const void *p_ptr = precip;
+    if (precip && sizeof(F) == 4) {
+        B200_CUDA(pw.alloc(N * sizeof(double), stream));
+        p_ptr = pw.p;
+        widen_field_kernel<<<sblocks, 256, 0, stream>>>((const float *)precip, (double *)pw.p, N);
         B200_LAUNCH_CHECK();
     }
     const int nchunks = (T + SL_MAX_T - 1) / SL_MAX_T;
@@ -242,17 +357,19 @@ int sl_run(const void *precip, const void *velocity, const double *xy, const dou
         SLParams p;
         memset(&p, 0, sizeof(p));
         p.Vi = vi_ptr;
-        p.precip = precip;
+        p.precip = p_ptr;
         p.xy = xy;
         p.m = m; p.n = n;
         p.n_iter = n_iter;
         p.mode = mode;
         p.vts = vts;
+        p.td0 = tdiff[0];
         p.cval = outval;
         p.has_prev = disp_prev != nullptr;
+        p.vel_f32 = sizeof(FV) == 4;
         p.ti_offset = c * SL_MAX_T;
         p.T = std::min(SL_MAX_T, T - p.ti_offset);
-        for (int i = 0; i < p.T; i++) p.td[i] = tdiff[p.ti_offset + i];
+        for (int i = 0; i < p.T; i++) p.scale[i] = tdiff[p.ti_offset + i] / vts;
         if (c == 0) {
             p.init_mode = disp_prev ? SL_INIT_PREV : SL_INIT_FRESH;
             p.disp_in = disp_prev;
@@ -265,7 +382,10 @@ int sl_run(const void *precip, const void *velocity, const double *xy, const dou
         p.disp_out = last ? disp_out : (double *)st_disp.p;
         p.vinc_out = last ? nullptr : (double *)st_vinc.p;
         p.out = precip ? (void *)((F *)out + (size_t)p.ti_offset * N) : nullptr;
-        sl_multistep_kernel<FV, F><<<grid, block, 0, stream>>>(p);
+        if (n_iter == 1)
+            sl_multistep_kernel<F, true><<<grid, block, 0, stream>>>(p);
+        else
+            sl_multistep_kernel<F, false><<<grid, block, 0, stream>>>(p);
         B200_LAUNCH_CHECK();
     }
     return 0;
@@ -283,7 +403,7 @@ extern "C" int b200_sl_extrapolate(const void *precip, const void *velocity,
                  "unknown velocity layout");
     B200_REQUIRE(velocity != nullptr, "velocity is NULL");
     B200_REQUIRE(tdiff != nullptr && T >= 1, "need at least one timestep");
-    B200_REQUIRE(m >= 1 && n >= 1, "empty grid");
+    B200_REQUIRE(m >= 1 && n >= 1 && (int64_t)m * n < ((int64_t)1 << 30), "grid must have 1 .. 2^30 pixels");
     B200_REQUIRE(n_iter >= 0, "n_iter must be >= 0");
     B200_REQUIRE(mode == B200_MODE_CONSTANT || mode == B200_MODE_NEAREST, "unsupported mode");
     B200_REQUIRE((precip == nullptr) == (out == nullptr), "precip and out must both be given or both NULL");
@@ -352,9 +472,9 @@ extern "C" int b200_sl_interleave_velocity(const void *velocity, int velocity_dt
     const int blocks = (int)std::min<size_t>((N + 255) / 256, (size_t)b200::num_sms() * 16);
     cudaStream_t s = (cudaStream_t)stream;
     if (velocity_dtype == B200_F32)
-        interleave_kernel<float><<<blocks, 256, 0, s>>>((const float *)velocity, (float2 *)out, N);
+        interleave_kernel<float, float2><<<blocks, 256, 0, s>>>((const float *)velocity, (float2 *)out, N);
     else if (velocity_dtype == B200_F64)
-        interleave_kernel<double><<<blocks, 256, 0, s>>>((const double *)velocity, (double2 *)out, N);
+        interleave_kernel<double, double2><<<blocks, 256, 0, s>>>((const double *)velocity, (double2 *)out, N);
     else {
         b200::set_error("unknown velocity dtype %d", velocity_dtype);
         return B200_EINVAL;
