@@ -103,6 +103,97 @@ int b200_field_stats(const void *a, int field_dtype, int64_t count, double *stat
 /* dtype conversion on device (float64 <-> float32), count elements */
 int b200_convert(const void *src, int src_dtype, void *dst, int dst_dtype,
                  int64_t count, void *stream);
+/* dst[0..count) = value (float64) */
+int b200_fill_f64(double *dst, int64_t count, double value, void *stream);
+
+
+/* ------------------------------------------------------------------------
+ * Dense Lucas-Kanade motion estimation
+ * replaces the array work of pysteps/motion/lucaskanade.py:38-279 and the helpers
+ * it calls.  pysteps delegates most of it to opencv-python / scipy; each entry
+ * point names the reference call it stands for.  All pointers are device
+ * pointers; images are (m,n) row-major.  "n_dev" arguments are optional device
+ * pointers to an element count produced by an earlier stage (NULL: use the
+ * capacity argument), so the chain runs without host round trips.
+ * ---------------------------------------------------------------------- */
+
+/* np.ma.masked_invalid + MaskedArray.min()/max()  (motion/lucaskanade.py:213-219):
+ * mask_out = user_mask | !isfinite(img); stats[0..2] = min, max, count of unmasked. */
+int b200_mask_invalid(const double *img, const uint8_t *user_mask, int m, int n,
+                      uint8_t *mask_out, double *stats, void *stream);
+
+/* pysteps/utils/images.py:27-86 morph_opening (cv2.morphologyEx MORPH_OPEN with the
+ * 3x3 cross): pixels > *thr_dev removed by the opening are set to *min_dev (device scalars,
+ * e.g. the stats of b200_mask_invalid). size must be 3. */
+int b200_morph_opening(const double *img, const uint8_t *mask, int m, int n, int size,
+                       const double *thr_dev, const double *min_dev, double *out, void *stream);
+
+/* stats (12 doubles): min / max / count over unmasked pixels of all rows [0..2], of rows
+ * >= 1 [3..5], of rows >= 2 [6..8]; [11] = number of pixels whose dilate x dilate buffered
+ * mask (cv2.dilate, feature/shitomasi.py:131-139) is clear.  The row sets reproduce the
+ * integer-indexing quirk of shitomasi.py:139 (see csrc/lk_dense.cu). */
+int b200_masked_minmax(const double *img, const uint8_t *mask, int m, int n, int dilate,
+                       double *stats, void *stream);
+
+/* "scale between 0 and 255" + astype(uint8).  mode 0: tracking/lucaskanade.py:144-160;
+ * mode 1: feature/shitomasi.py:131-151 (buffer_mask = dilate) with valid = buffered mask
+ * clear.  stats = output of b200_masked_minmax, masked pixels take *fill_dev. */
+int b200_quantise_u8(const double *img, const uint8_t *mask, int m, int n, int mode, int dilate,
+                     const double *stats, const double *fill_dev, uint8_t *out, uint8_t *valid,
+                     void *stream);
+
+/* cv::pyrDown (uint8, BORDER_REFLECT_101) and the int16 Scharr pair image of
+ * cv::calcOpticalFlowPyrLK's pyramid (dst holds (Ix, Iy) interleaved). */
+int b200_pyr_down_u8(const uint8_t *src, int h, int w, uint8_t *dst, void *stream);
+int b200_scharr_i16(const uint8_t *src, int h, int w, int16_t *dst, void *stream);
+
+/* cv::cornerMinEigenVal(q, blockSize=5, ksize=3) -> float32 (m,n), bit-identical to
+ * opencv-python 4.13.0 (AVX-512 build). */
+int b200_min_eig(const uint8_t *q, int m, int n, float *eig, void *stream);
+
+/* cv::goodFeaturesToTrack selection on a minimum-eigenvalue map
+ * (feature/shitomasi.py:153-162): out_xy (max_corners,2) float32 (x,y), *out_count.
+ * Synchronises the stream once (the sort network is sized by the candidate count). */
+int b200_good_features(const float *eig, const uint8_t *valid, int m, int n, int max_corners,
+                       double quality_level, double min_distance, float *out_xy,
+                       int *out_count, void *stream);
+
+/* Pyramid geometry of cv::buildOpticalFlowPyramid (HOST pointers, 8 entries each). */
+int b200_lk_pyramid_layout(int h, int w, int win_w, int win_h, int max_level, int *levels_out,
+                           int64_t *offsets, int *hs, int *ws, int64_t *total_pixels);
+/* Gaussian pyramid (levels contiguous) and, if deriv != NULL, its Scharr pyramid. */
+int b200_lk_build_pyramid(const uint8_t *img, int h, int w, int win_w, int win_h, int max_level,
+                          uint8_t *pyr, int16_t *deriv, void *stream);
+/* cv::calcOpticalFlowPyrLK (tracking/lucaskanade.py:171), flags = 0: next_pts (npts,2)
+ * float32, status (npts) uint8; bit-identical to opencv-python 4.13.0. */
+int b200_lk_track(const uint8_t *pyrI, const uint8_t *pyrJ, const int16_t *derivI, int h, int w,
+                  int win_w, int win_h, int max_level, int max_count, double epsilon,
+                  double min_eig_thr, const float *prev_pts, int npts, const int *npts_dev,
+                  float *next_pts, uint8_t *status, void *stream);
+/* keep status == 1 rows (tracking/lucaskanade.py:174-181) and append xy = p0,
+ * uv = p1 - p0 (float32 arithmetic, widened) to a float64 pool at *pool_count. */
+int b200_lk_compact_tracks(const float *p0, const float *p1, const uint8_t *status,
+                           const int *npts_dev, int npts_cap, double *pool_xy, double *pool_uv,
+                           int *pool_count, int pool_cap, void *stream);
+
+/* pysteps/utils/cleansing.py:124-249 detect_outliers(uv, thr, xy, k), multivariate local
+ * branch: out[i] = 1 where the Mahalanobis distance to the k nearest vectors exceeds thr. */
+int b200_detect_outliers(const double *uv, const double *xy, const int *n_dev, int n_cap,
+                         double thr, int k, uint8_t *out, void *stream);
+/* rows with drop == 0, order preserved */
+int b200_compact_rows(const double *xy, const double *uv, const uint8_t *drop, const int *n_dev,
+                      int n_cap, double *out_xy, double *out_uv, int *out_count, void *stream);
+/* pysteps/utils/cleansing.py:21-121 decluster(xy, uv, scale, min_samples): per-cell medians,
+ * cells in np.unique(axis=0) order. */
+int b200_decluster(const double *xy, const double *uv, const int *n_dev, int n_cap, double scale,
+                   int min_samples, double *out_xy, double *out_uv, int *out_count, void *stream);
+
+/* pysteps/utils/interpolate.py:26-114 idwinterp2d: k-nearest inverse-distance weighting of
+ * (npts, nvar) values onto the (ny, nx) grid -> out (nvar, ny, nx). k <= 32. */
+int b200_idw_fill(const double *xy, const double *vals, const int *npts_dev, int npts_cap,
+                  int nvar, int k, double power, double dist_offset, double mean_res,
+                  const double *xgrid, int nx, const double *ygrid, int ny, double *out,
+                  void *stream);
 
 #ifdef __cplusplus
 }

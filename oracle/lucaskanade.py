@@ -216,12 +216,9 @@ def morph_opening(input_image, thr, n):
     return input_image
 
 
-def detection(input_image, max_corners=1000, max_num_features=None, quality_level=0.01,
-              min_distance=10, block_size=5, buffer_mask=5, use_harris=False, k=0.04,
-              verbose=False, **kwargs):
-    """pysteps/feature/shitomasi.py:26-171."""
-    if use_harris or block_size != 5:
-        raise NotImplementedError("oracle restates the default detector only")
+def detection_image(input_image, buffer_mask=5):
+    """The uint8 image and the validity mask that shitomasi.detection hands to
+    cv2.goodFeaturesToTrack (pysteps/feature/shitomasi.py:119-152)."""
     input_image = input_image.copy()
     if input_image.ndim != 2:
         raise ValueError("input_image must be a two-dimensional array")
@@ -231,13 +228,35 @@ def detection(input_image, max_corners=1000, max_num_features=None, quality_leve
     mask = np.ma.getmaskarray(input_image).astype("uint8")
     if buffer_mask > 0:
         mask = dilate_rect(mask, int(buffer_mask))
+        # NOTE (reference quirk, shitomasi.py:139): `mask` is uint8, so this is INTEGER
+        # indexing -- it masks rows 0 and/or 1, not the buffered pixels.  Kept as is.
         input_image[mask] = np.ma.masked
     input_image = _quantise_u8(input_image)
     mask = ~mask & 1
+    return input_image, mask
+
+
+def detection(input_image, max_corners=1000, max_num_features=None, quality_level=0.01,
+              min_distance=10, block_size=5, buffer_mask=5, use_harris=False, k=0.04,
+              verbose=False, **kwargs):
+    """pysteps/feature/shitomasi.py:26-171."""
+    if use_harris or block_size != 5:
+        raise NotImplementedError("oracle restates the default detector only")
+    input_image, mask = detection_image(input_image, buffer_mask)
     points = good_features_to_track(
         input_image, mask, max_num_features if max_num_features is not None else max_corners,
         quality_level, min_distance)
     return points
+
+
+def tracking_image(img):
+    """The uint8 image track_features hands to cv2.calcOpticalFlowPyrLK
+    (pysteps/tracking/lucaskanade.py:134-160)."""
+    img = img.copy()
+    if not isinstance(img, MaskedArray):
+        img = np.ma.masked_invalid(img)
+    np.ma.set_fill_value(img, img.min())
+    return _quantise_u8(img)
 
 
 def track_features(prvs_image, next_image, points, winsize=(50, 50), nr_levels=3,

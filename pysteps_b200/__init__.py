@@ -11,4 +11,5 @@ There is no CPU fallback: without the built library and a GPU, calls raise.
 __version__ = "0.1.0"
 
 from . import extrapolation  # noqa: F401
+from . import motion  # noqa: F401
 from .interface import register  # noqa: F401

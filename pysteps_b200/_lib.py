@@ -37,6 +37,36 @@ _SIGNATURES = {
     "b200_sl_extrapolate_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_dp, c_int,
                                          c_double, c_int, c_double, c_int, c_int, c_int, c_int,
                                          c_int, c_void_p, c_void_p]),
+    "b200_mask_invalid": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "b200_morph_opening": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+                                   c_void_p, c_void_p]),
+    "b200_masked_minmax": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "b200_quantise_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_void_p]),
+    "b200_fill_f64": (c_int, [c_void_p, c_i64, c_double, c_void_p]),
+    "b200_pyr_down_u8": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "b200_scharr_i16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "b200_min_eig": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "b200_good_features": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_double,
+                                   c_void_p, c_void_p, c_void_p]),
+    "b200_lk_pyramid_layout": (c_int, [c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_int),
+                                       ctypes.POINTER(c_i64), ctypes.POINTER(c_int),
+                                       ctypes.POINTER(c_int), ctypes.POINTER(c_i64)]),
+    "b200_lk_build_pyramid": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                      c_void_p]),
+    "b200_lk_track": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                              c_double, c_double, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                              c_void_p]),
+    "b200_lk_compact_tracks": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                       c_void_p, c_int, c_void_p]),
+    "b200_detect_outliers": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_double, c_int, c_void_p,
+                                     c_void_p]),
+    "b200_compact_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                  c_void_p, c_void_p]),
+    "b200_decluster": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_double, c_int, c_void_p, c_void_p,
+                               c_void_p, c_void_p]),
+    "b200_idw_fill": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_double,
+                              c_double, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "b200_field_stats": (c_int, [c_void_p, c_int, c_i64, c_void_p, c_void_p]),
     "b200_convert": (c_int, [c_void_p, c_int, c_void_p, c_int, c_i64, c_void_p]),
 }

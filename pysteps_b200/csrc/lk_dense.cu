@@ -1,0 +1,430 @@
+// lk_dense.cu -- the dense per-pixel stages of pysteps' Lucas-Kanade path (sm_100a):
+// masking / min-max reductions, 3x3 cross opening, uint8 quantisation, Gaussian pyramid,
+// Scharr derivative images and the Shi-Tomasi minimum-eigenvalue map.
+//
+// Reference call sites (pysteps is Python; the arithmetic is in opencv-python 4.13.0):
+//   pysteps/motion/lucaskanade.py:207-224      masked_invalid, fill value, morph_opening
+//   pysteps/utils/images.py:27-86              morph_opening (cv2.morphologyEx, 3x3 cross)
+//   pysteps/feature/shitomasi.py:131-162       mask dilation, uint8 scaling, goodFeaturesToTrack
+//   pysteps/tracking/lucaskanade.py:144-171    uint8 scaling, calcOpticalFlowPyrLK
+// All of these are HBM/L2-streaming stencils over m x n pixels: one thread per pixel,
+// 32-wide rows per warp for coalescing, halos served by L1 (reuse factor 9-25 in a tile).
+// Integer stages are exact; the float32 stages reproduce OpenCV's operation order
+// (explicit fmaf where the AVX-512 build fuses, plain mul/add elsewhere; --fmad=false).
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int TX = 32, TY = 8;
+
+__device__ __forceinline__ int reflect101(int i, int L) {
+    if (L == 1) return 0;
+    while (i < 0 || i >= L) {
+        if (i < 0) i = -i;
+        if (i >= L) i = 2 * L - 2 - i;
+    }
+    return i;
+}
+
+// ---------------------------------------------------------------- block min/max reduce
+struct MM {
+    double mn, mx;
+    unsigned long long cnt;
+};
+
+__device__ __forceinline__ MM mm_merge(MM a, const MM &b) {
+    a.mn = fmin(a.mn, b.mn);
+    a.mx = fmax(a.mx, b.mx);
+    a.cnt += b.cnt;
+    return a;
+}
+
+__device__ __forceinline__ MM mm_warp(MM v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        MM t;
+        t.mn = __shfl_xor_sync(0xffffffffu, v.mn, o);
+        t.mx = __shfl_xor_sync(0xffffffffu, v.mx, o);
+        t.cnt = __shfl_xor_sync(0xffffffffu, v.cnt, o);
+        v = mm_merge(v, t);
+    }
+    return v;
+}
+
+__device__ __forceinline__ MM mm_block(MM v, MM *sm) {
+    v = mm_warp(v);
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int w = tid >> 5, l = tid & 31;
+    const int nw = (blockDim.x * blockDim.y + 31) >> 5;
+    __syncthreads();
+    if (l == 0) sm[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        MM t;
+        t.mn = CUDART_INF; t.mx = -CUDART_INF; t.cnt = 0;
+        if (l < nw) t = sm[l];
+        v = mm_warp(t);
+    }
+    return v;
+}
+
+// stats layout written by the final kernel: [min, max, count] (+3 per set)
+__global__ void __launch_bounds__(256) mm_final_kernel(const MM *__restrict__ part, int nparts, int nsets,
+                                                       double *__restrict__ stats) {
+    __shared__ MM sm[32];
+    for (int s = 0; s < nsets; s++) {
+        MM v;
+        v.mn = CUDART_INF; v.mx = -CUDART_INF; v.cnt = 0;
+        for (int i = threadIdx.x; i < nparts; i += blockDim.x) v = mm_merge(v, part[(size_t)s * nparts + i]);
+        v = mm_block(v, sm);
+        if (threadIdx.x == 0) {
+            // numpy's masked min()/max() of an all-masked array is `masked`; report NaN
+            stats[3 * s + 0] = v.cnt ? v.mn : CUDART_NAN;
+            stats[3 * s + 1] = v.cnt ? v.mx : CUDART_NAN;
+            stats[3 * s + 2] = (double)v.cnt;
+        }
+        __syncthreads();
+    }
+}
+
+// mask = user_mask | !isfinite(img) (np.ma.masked_invalid); min/max over unmasked
+__global__ void __launch_bounds__(TX *TY)
+mask_invalid_kernel(const double *__restrict__ img, const uint8_t *__restrict__ user_mask, int m, int n,
+                    uint8_t *__restrict__ mask, MM *__restrict__ part) {
+    __shared__ MM sm[32];
+    const int x = blockIdx.x * TX + threadIdx.x, y = blockIdx.y * TY + threadIdx.y;
+    MM v;
+    v.mn = CUDART_INF; v.mx = -CUDART_INF; v.cnt = 0;
+    if (x < n && y < m) {
+        const size_t i = (size_t)y * n + x;
+        const double a = img[i];
+        const bool msk = (user_mask && user_mask[i]) || !isfinite(a);
+        mask[i] = msk ? 1 : 0;
+        if (!msk) { v.mn = a; v.mx = a; v.cnt = 1; }
+    }
+    v = mm_block(v, sm);
+    if (threadIdx.x == 0 && threadIdx.y == 0) part[blockIdx.y * gridDim.x + blockIdx.x] = v;
+}
+
+// utils/images.py:66-81 : bin = filled > thr ; open with the 3x3 cross ; pixels removed by the
+// opening are set to the minimum.  erode ignores out-of-image taps, so does dilate.
+__global__ void __launch_bounds__(TX *TY)
+morph_open_kernel(const double *__restrict__ img, const uint8_t *__restrict__ mask, int m, int n,
+                  const double *__restrict__ thr_dev, const double *__restrict__ min_dev,
+                  double *__restrict__ out) {
+    const int x = blockIdx.x * TX + threadIdx.x, y = blockIdx.y * TY + threadIdx.y;
+    if (x >= n || y >= m) return;
+    const double thr = *thr_dev, minval = *min_dev;
+    auto bin = [&](int yy, int xx) -> int {  // -1 outside the image
+        if (yy < 0 || yy >= m || xx < 0 || xx >= n) return -1;
+        const size_t i = (size_t)yy * n + xx;
+        return (!mask[i] && img[i] > thr) ? 1 : 0;
+    };
+    auto eroded = [&](int yy, int xx) -> int {  // -1 outside
+        const int c = bin(yy, xx);
+        if (c < 0) return -1;
+        // out-of-image neighbours do not erode (border = +max)
+        return (c != 0) & (bin(yy - 1, xx) != 0) & (bin(yy + 1, xx) != 0) & (bin(yy, xx - 1) != 0) &
+               (bin(yy, xx + 1) != 0);
+    };
+    const size_t i = (size_t)y * n + x;
+    const double v = img[i];
+    const int b = bin(y, x);
+    double o = v;
+    if (b == 1) {
+        const bool opened = (eroded(y, x) == 1) | (eroded(y - 1, x) == 1) | (eroded(y + 1, x) == 1) |
+                            (eroded(y, x - 1) == 1) | (eroded(y, x + 1) == 1);
+        if (!opened) o = minval;
+    }
+    out[i] = o;
+}
+
+// min/max/count over unmasked pixels of all rows (set 0), of rows >= 1 (set 1) and of rows >= 2
+// (set 2), plus (set 3, count only) the number of pixels whose k x k dilated mask is clear.
+// The row sets exist because feature/shitomasi.py:139 indexes the image with the uint8 mask
+// (`input_image[mask] = masked`): NumPy treats it as INTEGER indexing, which masks row 0 when
+// the buffered mask contains a 0 and row 1 when it contains a 1 -- not the buffered pixels.
+__global__ void __launch_bounds__(TX *TY)
+masked_minmax_kernel(const double *__restrict__ img, const uint8_t *__restrict__ mask, int m, int n,
+                     int dil, MM *__restrict__ part, int nparts) {
+    __shared__ MM sm[32];
+    const int x = blockIdx.x * TX + threadIdx.x, y = blockIdx.y * TY + threadIdx.y;
+    MM a[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { a[k].mn = CUDART_INF; a[k].mx = -CUDART_INF; a[k].cnt = 0; }
+    if (x < n && y < m) {
+        const size_t i = (size_t)y * n + x;
+        const double v = img[i];
+        if (!mask[i]) {
+            a[0].mn = a[0].mx = v; a[0].cnt = 1;
+            if (y >= 1) a[1] = a[0];
+            if (y >= 2) a[2] = a[0];
+        }
+        bool d = mask[i] != 0;
+        if (dil > 0) {
+            const int r = dil / 2;
+            for (int dy = -r; dy <= dil - 1 - r; dy++)
+                for (int dx = -r; dx <= dil - 1 - r; dx++) {
+                    const int yy = y + dy, xx = x + dx;
+                    if (yy >= 0 && yy < m && xx >= 0 && xx < n) d |= mask[(size_t)yy * n + xx] != 0;
+                }
+        }
+        if (!d) a[3].cnt = 1;
+    }
+    const int bi = blockIdx.y * gridDim.x + blockIdx.x;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const MM r = mm_block(a[k], sm);
+        if (threadIdx.x == 0 && threadIdx.y == 0) part[(size_t)k * nparts + bi] = r;
+    }
+}
+
+// (x - im_min) / (im_max - im_min) * 255 -> astype(uint8): truncation toward zero, and the
+// x86-64 behaviour of NumPy for out-of-range values (through int32, low byte kept)
+__device__ __forceinline__ uint8_t cast_u8(double v) {
+    if (!(v > -2147483649.0 && v < 2147483648.0)) return 0;  // cvttsd2si -> INT_MIN -> low byte 0
+    return (uint8_t)((int)v & 0xff);
+}
+
+// mode 0 (tracking/lucaskanade.py:144-160): masked pixels take the fill value, min/max over
+// the unmasked pixels.  mode 1 (feature/shitomasi.py:131-151): additionally row 0 / row 1 are
+// masked as described above, min/max over what is left, and `valid` = buffered mask clear.
+__global__ void __launch_bounds__(TX *TY)
+quantise_kernel(const double *__restrict__ img, const uint8_t *__restrict__ mask, int m, int n, int mode,
+                int dil, const double *__restrict__ stats, const double *__restrict__ fill_dev,
+                uint8_t *__restrict__ out, uint8_t *__restrict__ valid) {
+    const int x = blockIdx.x * TX + threadIdx.x, y = blockIdx.y * TY + threadIdx.y;
+    if (x >= n || y >= m) return;
+    const size_t i = (size_t)y * n + x;
+    bool msk = mask[i] != 0;
+    int set = 0;
+    if (mode == 1) {
+        bool dmask = msk;
+        if (dil > 0) {
+            const int r = dil / 2;
+            for (int dy = -r; dy <= dil - 1 - r; dy++)
+                for (int dx = -r; dx <= dil - 1 - r; dx++) {
+                    const int yy = y + dy, xx = x + dx;
+                    if (yy >= 0 && yy < m && xx >= 0 && xx < n) dmask |= mask[(size_t)yy * n + xx] != 0;
+                }
+        }
+        if (valid) valid[i] = dmask ? 0 : 1;
+        const bool any_clear = stats[11] > 0.0;                       // buffered mask contains a 0
+        const bool any_masked = stats[2] < (double)m * (double)n;     // ... contains a 1
+        if (dil > 0) {
+            const int rows = (any_clear ? 1 : 0) + (any_masked ? 1 : 0);
+            set = rows;  // rows masked from the top: 0, 1 or 2 (row 1 alone only if nothing is clear)
+            if ((y == 0 && any_clear) || (y == 1 && any_masked)) msk = true;
+            if (!any_clear && any_masked) { set = 2; if (y == 0) msk = true; }
+        }
+    } else if (valid) {
+        valid[i] = msk ? 0 : 1;
+    }
+    const double im_min = stats[3 * set + 0], im_max = stats[3 * set + 1];
+    const double v = msk ? *fill_dev : img[i];
+    double q;
+    if (__dsub_rn(im_max, im_min) > 1e-8)
+        q = __dmul_rn(__ddiv_rn(__dsub_rn(v, im_min), __dsub_rn(im_max, im_min)), 255.0);
+    else
+        q = __dsub_rn(v, im_min);
+    out[i] = cast_u8(q);
+}
+
+// cv::pyrDown on uint8: separable [1 4 6 4 1], BORDER_REFLECT_101, (sum + 128) >> 8
+__global__ void __launch_bounds__(TX *TY)
+pyrdown_kernel(const uint8_t *__restrict__ src, int h, int w, uint8_t *__restrict__ dst, int dh, int dw) {
+    const int x = blockIdx.x * TX + threadIdx.x, y = blockIdx.y * TY + threadIdx.y;
+    if (x >= dw || y >= dh) return;
+    const int wt[5] = {1, 4, 6, 4, 1};
+    int xs[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) xs[k] = reflect101(2 * x + k - 2, w);
+    int acc = 0;
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+        const uint8_t *r = src + (size_t)reflect101(2 * y + j - 2, h) * w;
+        int row = 0;
+#pragma unroll
+        for (int k = 0; k < 5; k++) row += wt[k] * r[xs[k]];
+        acc += wt[j] * row;
+    }
+    dst[(size_t)y * dw + x] = (uint8_t)((acc + 128) >> 8);
+}
+
+// calcScharrDeriv: smooth [3 10 3], diff [-1 0 1], BORDER_REFLECT_101, int16 (Ix, Iy)
+__global__ void __launch_bounds__(TX *TY)
+scharr_kernel(const uint8_t *__restrict__ src, int h, int w, short2 *__restrict__ dst) {
+    const int x = blockIdx.x * TX + threadIdx.x, y = blockIdx.y * TY + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const uint8_t *r0 = src + (size_t)reflect101(y - 1, h) * w;
+    const uint8_t *r1 = src + (size_t)y * w;
+    const uint8_t *r2 = src + (size_t)reflect101(y + 1, h) * w;
+    const int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w);
+    const int t0m = (r0[xm] + r2[xm]) * 3 + r1[xm] * 10;
+    const int t0p = (r0[xp] + r2[xp]) * 3 + r1[xp] * 10;
+    const int t1m = r2[xm] - r0[xm], t1c = r2[x] - r0[x], t1p = r2[xp] - r0[xp];
+    dst[(size_t)y * w + x] = make_short2((short)(t0p - t0m), (short)((t1m + t1p) * 3 + t1c * 10));
+}
+
+// ---------------------------------------------------------------- Shi-Tomasi eigenvalue map
+// cv::cornerMinEigenVal(u8, blockSize 5, ksize 3) as the 4.13.0 AVX-512 build evaluates it
+// (pinned bit for bit, oracle/lk_oracle.c ora_min_eig_u8).
+struct Cov { float xx, xy, yy; };
+
+__device__ __forceinline__ Cov cov_at(const uint8_t *__restrict__ q, int h, int w, int y, int x, int tail0) {
+    const float s = (float)(1.0 / 5100.0), s2 = (float)(2.0 / 5100.0);
+    const int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w);
+    float g[3], v[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const uint8_t *r = q + (size_t)reflect101(y + k - 1, h) * w;
+        const float c0 = (float)r[xm], c1 = (float)r[x], c2 = (float)r[xp];
+        g[k] = __fsub_rn(c2, c0);
+        v[k] = (x < tail0) ? __fmaf_rn(c2, s, __fmaf_rn(c1, s2, __fmul_rn(c0, s)))
+                           : __fadd_rn(__fadd_rn(__fmul_rn(c0, s), __fmul_rn(c1, s2)), __fmul_rn(c2, s));
+    }
+    const float dx = __fmaf_rn(s, __fadd_rn(g[0], g[2]), __fmul_rn(s2, g[1]));
+    const float dy = __fsub_rn(v[2], v[0]);
+    Cov c;
+    c.xx = __fmul_rn(dx, dx);
+    c.xy = __fmul_rn(dx, dy);
+    c.yy = __fmul_rn(dy, dy);
+    return c;
+}
+
+// per pixel: the three 5-tap row sums of the covariance products, in double, left to right
+__global__ void __launch_bounds__(TX *TY)
+cov_rowsum_kernel(const uint8_t *__restrict__ q, int h, int w, double *__restrict__ rs) {
+    const int x = blockIdx.x * TX + threadIdx.x, y = blockIdx.y * TY + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const int tail0 = (w / 32) * 32;
+    double sxx = 0.0, sxy = 0.0, syy = 0.0;
+#pragma unroll
+    for (int d = -2; d <= 2; d++) {
+        const Cov c = cov_at(q, h, w, y, reflect101(x + d, w), tail0);
+        if (d == -2) { sxx = (double)c.xx; sxy = (double)c.xy; syy = (double)c.yy; }
+        else { sxx = __dadd_rn(sxx, (double)c.xx); sxy = __dadd_rn(sxy, (double)c.xy); syy = __dadd_rn(syy, (double)c.yy); }
+    }
+    const size_t N = (size_t)h * w, i = (size_t)y * w + x;
+    rs[i] = sxx;
+    rs[N + i] = sxy;
+    rs[2 * N + i] = syy;
+}
+
+// per column: OpenCV's running column sum (double) down the rows, then the eigenvalue.
+// The recurrence is history dependent (add entering row, emit, subtract leaving row), so a
+// column is one sequential chain; columns are independent and coalesced across the warp.
+__global__ void __launch_bounds__(128)
+box_eig_kernel(const double *__restrict__ rs, int h, int w, float *__restrict__ eig) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= w) return;
+    const size_t N = (size_t)h * w;
+    double S0 = 0.0, S1 = 0.0, S2 = 0.0;
+    for (int k = -2; k < 2; k++) {
+        const size_t i = (size_t)reflect101(k, h) * w + x;
+        S0 = __dadd_rn(S0, rs[i]);
+        S1 = __dadd_rn(S1, rs[N + i]);
+        S2 = __dadd_rn(S2, rs[2 * N + i]);
+    }
+    for (int y = 0; y < h; y++) {
+        const size_t ip = (size_t)reflect101(y + 2, h) * w + x;
+        const size_t im = (size_t)reflect101(y - 2, h) * w + x;
+        const double a0 = __dadd_rn(S0, rs[ip]), a1 = __dadd_rn(S1, rs[N + ip]), a2 = __dadd_rn(S2, rs[2 * N + ip]);
+        S0 = __dsub_rn(a0, rs[im]);
+        S1 = __dsub_rn(a1, rs[N + im]);
+        S2 = __dsub_rn(a2, rs[2 * N + im]);
+        const float a = __fmul_rn(__double2float_rn(a0), 0.5f);
+        const float b = __double2float_rn(a1);
+        const float c = __fmul_rn(__double2float_rn(a2), 0.5f);
+        const float t = __fsub_rn(a, c);
+        const float r = __fsqrt_rn(__fadd_rn(__fmul_rn(t, t), __fmul_rn(b, b)));
+        eig[(size_t)y * w + x] = __fsub_rn(__fadd_rn(a, c), r);
+    }
+}
+
+static dim3 grid2d(int m, int n) { return dim3(b200::ceil_div(n, TX), b200::ceil_div(m, TY)); }
+
+}  // namespace
+
+extern "C" int b200_mask_invalid(const double *img, const uint8_t *user_mask, int m, int n,
+                                 uint8_t *mask_out, double *stats, void *stream) {
+    B200_REQUIRE(img && mask_out && stats && m >= 1 && n >= 1, "bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    const dim3 g = grid2d(m, n);
+    const int nparts = g.x * g.y;
+    b200::Scratch part;
+    B200_CUDA(part.alloc(sizeof(MM) * nparts, s));
+    mask_invalid_kernel<<<g, dim3(TX, TY), 0, s>>>(img, user_mask, m, n, mask_out, (MM *)part.p);
+    B200_LAUNCH_CHECK();
+    mm_final_kernel<<<1, 256, 0, s>>>((const MM *)part.p, nparts, 1, stats);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int b200_morph_opening(const double *img, const uint8_t *mask, int m, int n, int size,
+                                  const double *thr_dev, const double *min_dev, double *out,
+                                  void *stream) {
+    B200_REQUIRE(img && mask && out && thr_dev && min_dev && m >= 1 && n >= 1, "bad arguments");
+    if (size != 3) {
+        b200::set_error("morph_opening: only the 3x3 structuring element is implemented");
+        return B200_ENOTSUP;
+    }
+    morph_open_kernel<<<grid2d(m, n), dim3(TX, TY), 0, (cudaStream_t)stream>>>(img, mask, m, n, thr_dev, min_dev, out);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int b200_masked_minmax(const double *img, const uint8_t *mask, int m, int n, int dilate,
+                                  double *stats, void *stream) {
+    B200_REQUIRE(img && mask && stats && m >= 1 && n >= 1 && dilate >= 0 && dilate <= 31, "bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    const dim3 g = grid2d(m, n);
+    const int nparts = g.x * g.y;
+    b200::Scratch part;
+    B200_CUDA(part.alloc(sizeof(MM) * nparts * 4, s));
+    masked_minmax_kernel<<<g, dim3(TX, TY), 0, s>>>(img, mask, m, n, dilate, (MM *)part.p, nparts);
+    B200_LAUNCH_CHECK();
+    mm_final_kernel<<<1, 256, 0, s>>>((const MM *)part.p, nparts, 4, stats);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int b200_quantise_u8(const double *img, const uint8_t *mask, int m, int n, int mode,
+                                int dilate, const double *stats, const double *fill_dev,
+                                uint8_t *out, uint8_t *valid, void *stream) {
+    B200_REQUIRE(img && mask && stats && fill_dev && out && m >= 1 && n >= 1 && dilate >= 0 &&
+                     dilate <= 31 && (mode == 0 || mode == 1), "bad arguments");
+    quantise_kernel<<<grid2d(m, n), dim3(TX, TY), 0, (cudaStream_t)stream>>>(img, mask, m, n, mode, dilate,
+                                                                            stats, fill_dev, out, valid);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int b200_pyr_down_u8(const uint8_t *src, int h, int w, uint8_t *dst, void *stream) {
+    B200_REQUIRE(src && dst && h >= 1 && w >= 1, "bad arguments");
+    const int dh = (h + 1) / 2, dw = (w + 1) / 2;
+    pyrdown_kernel<<<grid2d(dh, dw), dim3(TX, TY), 0, (cudaStream_t)stream>>>(src, h, w, dst, dh, dw);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int b200_scharr_i16(const uint8_t *src, int h, int w, int16_t *dst, void *stream) {
+    B200_REQUIRE(src && dst && h >= 1 && w >= 1, "bad arguments");
+    scharr_kernel<<<grid2d(h, w), dim3(TX, TY), 0, (cudaStream_t)stream>>>(src, h, w, (short2 *)dst);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int b200_min_eig(const uint8_t *q, int m, int n, float *eig, void *stream) {
+    B200_REQUIRE(q && eig && m >= 1 && n >= 1, "bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    b200::Scratch rs;
+    B200_CUDA(rs.alloc(sizeof(double) * 3 * (size_t)m * n, s));
+    cov_rowsum_kernel<<<grid2d(m, n), dim3(TX, TY), 0, s>>>(q, m, n, (double *)rs.p);
+    B200_LAUNCH_CHECK();
+    box_eig_kernel<<<b200::ceil_div(n, 32), 32, 0, s>>>((const double *)rs.p, m, n, eig);
+    B200_LAUNCH_CHECK();
+    return 0;
+}

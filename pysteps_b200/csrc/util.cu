@@ -108,7 +108,21 @@ __global__ void __launch_bounds__(256) convert_kernel(const S *__restrict__ src,
         dst[i] = (D)src[i];
 }
 
+__global__ void __launch_bounds__(256) fill_kernel(double *__restrict__ dst, int64_t count, double v) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) dst[i] = v;
+}
+
 }  // namespace
+
+extern "C" int b200_fill_f64(double *dst, int64_t count, double value, void *stream) {
+    B200_REQUIRE(dst != nullptr && count >= 0, "bad arguments");
+    const int blocks = (int)std::max<int64_t>(
+        1, std::min<int64_t>(b200::ceil_div64(count, 256), (int64_t)b200::num_sms() * 16));
+    fill_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dst, count, value);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int b200_field_stats(const void *a, int field_dtype, int64_t count, double *stats,
                                 void *stream) {

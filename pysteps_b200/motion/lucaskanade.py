@@ -1,0 +1,292 @@
+"""B200 dense Lucas-Kanade motion estimation -- drop-in for
+``pysteps.motion.lucaskanade.dense_lucaskanade``
+(pysteps/motion/lucaskanade.py:38-279).
+
+The reference orchestrates OpenCV / SciPy calls from Python; here the same
+orchestration (argument handling, early-outs, return shapes) stays in Python and
+every array operation is a CUDA kernel of ``libpysteps_b200.so``:
+
+  reference call                                   | kernel(s), csrc/
+  -------------------------------------------------+---------------------------------
+  np.ma.masked_invalid / .min() (:213-219)         | lk_dense.cu  mask_invalid
+  utils.images.morph_opening (:222-224)            | lk_dense.cu  morph_open
+  feature.shitomasi.detection (:227)               | lk_dense.cu  masked_minmax, quantise,
+    cv2.dilate / goodFeaturesToTrack               |   cov_rowsum, box_eig; lk_features.cu
+  tracking.lucaskanade.track_features (:234)       | lk_dense.cu  quantise, pyrdown, scharr;
+    cv2.calcOpticalFlowPyrLK                       |   lk_track.cu lk_track, compact_tracks
+  utils.cleansing.detect_outliers (:252)           | sparse.cu    outliers, compact_rows
+  utils.cleansing.decluster (:265)                 | sparse.cu    decluster
+  utils.interpolate.idwinterp2d (:274)             | idw.cu       idw
+
+Sparse vectors stay on the device between stages; the host reads back only element
+counts (to size the next launch / take the reference's early-outs).
+"""
+import ctypes
+import time
+
+import numpy as np
+import torch
+from numpy.ma.core import MaskedArray
+
+from .. import _device, _lib
+
+
+def _call(name, *args):
+    _lib.call(name, *args)
+
+
+def _s():
+    return _device.stream_ptr()
+
+
+class _Frame:
+    """Device state of one input frame after masking and morphological opening."""
+    __slots__ = ("img", "mask", "stats0", "opened", "stats", "q_track")
+
+
+def _prepare_frame(img_d, user_mask_d, m, n, size_opening):
+    """masked_invalid + fill value + morph_opening (lucaskanade.py:213-224) and the uint8
+    image track_features would build from it (tracking/lucaskanade.py:144-160)."""
+    f = _Frame()
+    f.img = img_d
+    f.mask = torch.empty((m, n), dtype=torch.uint8, device="cuda")
+    f.stats0 = torch.empty(3, dtype=torch.float64, device="cuda")
+    _call("b200_mask_invalid", img_d.data_ptr(), _device.ptr(user_mask_d), m, n, f.mask.data_ptr(),
+          f.stats0.data_ptr(), _s())
+    if size_opening > 0:
+        f.opened = torch.empty((m, n), dtype=torch.float64, device="cuda")
+        # thr = prvs_img.min(); removed pixels take np.nanmin(prvs_img): both stats0[0]
+        _call("b200_morph_opening", img_d.data_ptr(), f.mask.data_ptr(), m, n, int(size_opening),
+              f.stats0.data_ptr(), f.stats0.data_ptr(), f.opened.data_ptr(), _s())
+    else:
+        f.opened = img_d
+    f.stats = None
+    f.q_track = None
+    return f
+
+
+def _frame_stats(f, m, n, buffer_mask):
+    if f.stats is None:
+        f.stats = torch.empty(12, dtype=torch.float64, device="cuda")
+        _call("b200_masked_minmax", f.opened.data_ptr(), f.mask.data_ptr(), m, n, int(buffer_mask),
+              f.stats.data_ptr(), _s())
+    return f.stats
+
+
+def _track_image(f, m, n, buffer_mask):
+    if f.q_track is None:
+        st = _frame_stats(f, m, n, buffer_mask)
+        f.q_track = torch.empty((m, n), dtype=torch.uint8, device="cuda")
+        _call("b200_quantise_u8", f.opened.data_ptr(), f.mask.data_ptr(), m, n, 0, 0, st.data_ptr(),
+              st.data_ptr(), f.q_track.data_ptr(), None, _s())
+    return f.q_track
+
+
+def _pyramid_layout(m, n, win, max_level):
+    lv = ctypes.c_int(0)
+    off = (ctypes.c_int64 * 8)()
+    hs = (ctypes.c_int * 8)()
+    ws = (ctypes.c_int * 8)()
+    tot = ctypes.c_int64(0)
+    _lib.check(_lib.load().b200_lk_pyramid_layout(m, n, int(win[0]), int(win[1]), int(max_level),
+                                                  ctypes.byref(lv), off, hs, ws, ctypes.byref(tot)))
+    return lv.value, int(tot.value)
+
+
+def dense_lucaskanade(input_images, lk_kwargs=None, fd_method="shitomasi", fd_kwargs=None,
+                      interp_method="idwinterp2d", interp_kwargs=None, dense=True,
+                      nr_std_outlier=3, k_outlier=30, size_opening=3, decl_scale=20,
+                      verbose=False):
+    """Same contract as the reference (see its docstring, lucaskanade.py:54-180).
+
+    input_images: ndarray / MaskedArray (T,m,n) -> NumPy results; CUDA torch tensor
+    (NaN = no data) -> results stay on the device.  Only the default feature detector
+    ("shitomasi") and interpolator ("idwinterp2d") are implemented; anything else raises
+    NotImplementedError (there is no CPU fallback).
+    """
+    # decorators.check_input_frames(2): decorators.py:121-146
+    if input_images.ndim != 3:
+        raise ValueError(
+            "input_images dimension mismatch.\n"
+            f"input_images.shape: {str(tuple(input_images.shape))}\n"
+            "(t, x, y ) dimensions expected"
+        )
+    if fd_method != "shitomasi":
+        raise NotImplementedError(f"pysteps_b200 LK: fd_method={fd_method!r} is not implemented")
+    if interp_method != "idwinterp2d":
+        raise NotImplementedError(f"pysteps_b200 LK: interp_method={interp_method!r} is not implemented")
+    if size_opening not in (0, 3):
+        raise NotImplementedError("pysteps_b200 LK: size_opening must be 0 or 3")
+
+    _device.require_cuda()
+    on_device = _device.is_device_tensor(input_images)
+
+    if verbose:
+        print("Computing the motion field with the Lucas-Kanade method.")
+        t0 = time.time()
+
+    fd_kwargs = dict() if fd_kwargs is None else dict(fd_kwargs)
+    lk_kwargs = dict() if lk_kwargs is None else dict(lk_kwargs)
+    interp_kwargs = dict() if interp_kwargs is None else dict(interp_kwargs)
+
+    # feature.shitomasi.detection defaults (shitomasi.py:26-38)
+    max_corners = fd_kwargs.get("max_corners", 1000)
+    if fd_kwargs.get("max_num_features", None) is not None:
+        max_corners = fd_kwargs["max_num_features"]
+    quality_level = fd_kwargs.get("quality_level", 0.01)
+    min_distance = fd_kwargs.get("min_distance", 10)
+    block_size = fd_kwargs.get("block_size", 5)
+    buffer_mask = int(fd_kwargs.get("buffer_mask", 5))
+    if block_size != 5 or fd_kwargs.get("use_harris", False):
+        raise NotImplementedError("pysteps_b200 LK: only block_size=5, use_harris=False")
+    if int(max_corners) <= 0:
+        raise NotImplementedError("pysteps_b200 LK: max_corners must be positive")
+    max_corners = int(max_corners)
+    # tracking.lucaskanade.track_features defaults (tracking/lucaskanade.py:35-45)
+    winsize = tuple(lk_kwargs.get("winsize", (50, 50)))
+    nr_levels = int(lk_kwargs.get("nr_levels", 3))
+    criteria = tuple(lk_kwargs.get("criteria", (3, 10, 0)))
+    if lk_kwargs.get("flags", 0) != 0:
+        raise NotImplementedError("pysteps_b200 LK: flags must be 0")
+    min_eig_thr = float(lk_kwargs.get("min_eig_thr", 1e-4))
+    ctype, max_count, eps = criteria
+    max_count = min(max(int(max_count), 0), 100) if (int(ctype) & 1) else 30
+    eps = min(max(float(eps), 0.0), 10.0) if (int(ctype) & 2) else 0.01
+
+    nr_fields = int(input_images.shape[0])
+    m, n = int(input_images.shape[1]), int(input_images.shape[2])
+
+    # ---- upload (the reference copies its input, :182) ------------------------------------
+    user_mask_d = None
+    if isinstance(input_images, MaskedArray):
+        user_mask_d = _device.to_device(np.ascontiguousarray(np.ma.getmaskarray(input_images),
+                                                             dtype=np.uint8))
+        frames_d = _device.to_device(np.ascontiguousarray(input_images.data), torch.float64)
+    else:
+        frames_d = _device.to_device(input_images, torch.float64)
+
+    frames = [_prepare_frame(frames_d[t], None if user_mask_d is None else user_mask_d[t], m, n,
+                             size_opening) for t in range(nr_fields)]
+
+    pool_cap = max_corners * max(nr_fields - 1, 1)
+    pool_xy = torch.empty((pool_cap, 2), dtype=torch.float64, device="cuda")
+    pool_uv = torch.empty((pool_cap, 2), dtype=torch.float64, device="cuda")
+    counts = torch.zeros(4, dtype=torch.int32, device="cuda")  # pool, kept, declustered, corners
+    lv, total = _pyramid_layout(m, n, winsize, nr_levels)
+    pyr = {}
+
+    def pyramid(t, with_deriv):
+        """Gaussian pyramid of frame t's uint8 image (+ Scharr pyramid when it is the previous
+        frame of a pair); a middle frame is built once and reused by both of its pairs."""
+        args = (m, n, int(winsize[0]), int(winsize[1]), nr_levels)
+        if t not in pyr:
+            P = torch.empty(total, dtype=torch.uint8, device="cuda")
+            D = torch.empty(2 * total, dtype=torch.int16, device="cuda") if with_deriv else None
+            _call("b200_lk_build_pyramid", _track_image(frames[t], m, n, buffer_mask).data_ptr(), *args,
+                  P.data_ptr(), _device.ptr(D), _s())
+            pyr[t] = [P, D]
+        elif with_deriv and pyr[t][1] is None:
+            pyr[t][1] = torch.empty(2 * total, dtype=torch.int16, device="cuda")
+            _call("b200_lk_build_pyramid", None, *args, pyr[t][0].data_ptr(), pyr[t][1].data_ptr(), _s())
+        return pyr[t]
+
+    for t in range(nr_fields - 1):
+        f = frames[t]
+        st = _frame_stats(f, m, n, buffer_mask)
+        # ---- feature detection on the previous frame (:227) -------------------------------
+        q_det = torch.empty((m, n), dtype=torch.uint8, device="cuda")
+        valid = torch.empty((m, n), dtype=torch.uint8, device="cuda")
+        _call("b200_quantise_u8", f.opened.data_ptr(), f.mask.data_ptr(), m, n, 1, buffer_mask,
+              st.data_ptr(), st.data_ptr(), q_det.data_ptr(), valid.data_ptr(), _s())
+        eig = torch.empty((m, n), dtype=torch.float32, device="cuda")
+        _call("b200_min_eig", q_det.data_ptr(), m, n, eig.data_ptr(), _s())
+        corners = torch.empty((max_corners, 2), dtype=torch.float32, device="cuda")
+        ncorner = counts[3:4]
+        _call("b200_good_features", eig.data_ptr(), valid.data_ptr(), m, n, max_corners,
+              float(quality_level), float(min_distance), corners.data_ptr(), ncorner.data_ptr(), _s())
+        # ---- sparse tracking previous -> next (:234) --------------------------------------
+        pI = pyramid(t, True)
+        pJ = pyramid(t + 1, False)
+        nxt = torch.empty((max_corners, 2), dtype=torch.float32, device="cuda")
+        status = torch.empty(max_corners, dtype=torch.uint8, device="cuda")
+        _call("b200_lk_track", pI[0].data_ptr(), pJ[0].data_ptr(), pI[1].data_ptr(), m, n,
+              int(winsize[0]), int(winsize[1]), nr_levels, max_count, eps, min_eig_thr,
+              corners.data_ptr(), max_corners, ncorner.data_ptr(), nxt.data_ptr(), status.data_ptr(),
+              _s())
+        _call("b200_lk_compact_tracks", corners.data_ptr(), nxt.data_ptr(), status.data_ptr(),
+              ncorner.data_ptr(), max_corners, pool_xy.data_ptr(), pool_uv.data_ptr(),
+              counts[0:1].data_ptr(), pool_cap, _s())
+        del pyr[t]
+
+    def zeros_or_empty():
+        if dense:
+            z = torch.zeros((2, m, n), dtype=torch.float64, device="cuda")
+            return z if on_device else np.zeros((2, m, n))
+        e = np.empty(shape=(0, 2))
+        return (torch.from_numpy(e).cuda(), torch.from_numpy(e).cuda()) if on_device else (e, e.copy())
+
+    if nr_fields < 2:
+        return zeros_or_empty()
+
+    # ---- outliers (:252-254) on the pooled vectors --------------------------------------
+    flags = torch.empty(pool_cap, dtype=torch.uint8, device="cuda")
+    kept_xy = torch.empty((pool_cap, 2), dtype=torch.float64, device="cuda")
+    kept_uv = torch.empty((pool_cap, 2), dtype=torch.float64, device="cuda")
+    if k_outlier is None:
+        raise NotImplementedError("pysteps_b200 LK: k_outlier=None (global outlier test) is not implemented")
+    _call("b200_detect_outliers", pool_uv.data_ptr(), pool_xy.data_ptr(), counts[0:1].data_ptr(),
+          pool_cap, float(nr_std_outlier), int(k_outlier), flags.data_ptr(), _s())
+    _call("b200_compact_rows", pool_xy.data_ptr(), pool_uv.data_ptr(), flags.data_ptr(),
+          counts[0:1].data_ptr(), pool_cap, kept_xy.data_ptr(), kept_uv.data_ptr(),
+          counts[1:2].data_ptr(), _s())
+    dec_xy, dec_uv = kept_xy, kept_uv
+    if dense and decl_scale > 1:
+        dec_xy = torch.empty((pool_cap, 2), dtype=torch.float64, device="cuda")
+        dec_uv = torch.empty((pool_cap, 2), dtype=torch.float64, device="cuda")
+        _call("b200_decluster", kept_xy.data_ptr(), kept_uv.data_ptr(), counts[1:2].data_ptr(), pool_cap,
+              float(decl_scale), 1, dec_xy.data_ptr(), dec_uv.data_ptr(), counts[2:3].data_ptr(), _s())
+    else:
+        counts[2:3].copy_(counts[1:2])
+    n_pool, n_kept, n_dec, _ = counts.cpu().tolist()  # the one host read-back of the sparse stage
+
+    if n_pool == 0:  # :245-249
+        return zeros_or_empty()
+    if verbose:
+        print("--- LK found %i sparse vectors ---" % n_kept)
+    if not dense:  # :260-261
+        xy, uv = kept_xy[:n_kept], kept_uv[:n_kept]
+        return (xy, uv) if on_device else (xy.cpu().numpy(), uv.cpu().numpy())
+    if n_dec == 0:  # :268-269
+        return zeros_or_empty()
+
+    # ---- interpolation (:272-274) behind decorators.prepare_interpolator ----------------
+    power = float(interp_kwargs.get("power", 0.5))
+    k = interp_kwargs.get("k", 20)
+    dist_offset = float(interp_kwargs.get("dist_offset", 0.5))
+    if k is None:
+        raise NotImplementedError("pysteps_b200 LK: idwinterp2d with k=None is not implemented")
+    out = torch.empty((2, m, n), dtype=torch.float64, device="cuda")
+    xy_h = dec_xy[:n_dec].cpu().numpy()
+    uv_h = dec_uv[:n_dec].cpu().numpy()
+    if np.any(~np.isfinite(uv_h)):
+        raise ValueError("argument 'values' contains non-finite values")
+    if np.any(~np.isfinite(xy_h)):
+        raise ValueError("argument 'xy_coord' contains non-finite values")
+    if n_dec == 1:  # decorators.py:200-204
+        for c in range(2):
+            _call("b200_fill_f64", out[c].data_ptr(), m * n, float(1.0 * uv_h[0, c]), _s())
+    elif uv_h.max() == uv_h.min():  # decorators.py:207-208
+        _call("b200_fill_f64", out.data_ptr(), 2 * m * n, float(1.0 * uv_h.ravel()[0]), _s())
+    else:
+        if n < 2 or m < 2:
+            raise ValueError("Shape of array too small to calculate a numerical gradient, "
+                             "at least (edge_order + 1) elements are required.")
+        xgrid = torch.arange(n, dtype=torch.float64, device="cuda")
+        ygrid = torch.arange(m, dtype=torch.float64, device="cuda")
+        _call("b200_idw_fill", dec_xy.data_ptr(), dec_uv.data_ptr(), None, n_dec, 2, int(min(int(k), n_dec)),
+              power, dist_offset, 1.0, xgrid.data_ptr(), n, ygrid.data_ptr(), m, out.data_ptr(), _s())
+
+    if verbose:
+        torch.cuda.current_stream().synchronize()
+        print("--- total time: %.2f seconds ---" % (time.time() - t0))
+    return out if on_device else _device.to_host(out)
