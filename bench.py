@@ -53,12 +53,14 @@ def workload_name(lk):
 
 
 def make_inputs(seed, lk):
-    """float32 fields (the synthetic data are float32-exact; float32 arrays keep the
-    reference's float64 arithmetic but halve field storage)."""
+    """frames: float64 (2,m,n) for the motion estimator (as pysteps importers deliver them);
+    precip: the last frame as float32 (the synthetic data are float32-exact; a float32 array
+    keeps the reference's float64 arithmetic and halves the output volume);
+    V: synthetic float32 advection field, used only when the LK stage is not built."""
     from pysteps_b200 import _synthetic as syn
-    frames = syn.rain_frames(M, N_, 2, seed).astype(np.float32)
+    frames = syn.rain_frames(M, N_, 2, seed)
     V = syn.velocity_field(M, N_, seed).astype(np.float32)
-    return frames, V
+    return frames, frames[-1].astype(np.float32), V
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -106,21 +108,21 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU legs
-def cpu_step(frames, V, lk):
+def cpu_step(frames, precip, V, lk):
     """The oracle port of one step on host cores."""
     from oracle import semilagrangian as ora
     if lk:
         from oracle import lucaskanade as ora_lk
-        V = ora_lk.dense_lucaskanade(frames.astype(np.float64))
-    return ora.extrapolate(frames[-1], V, T_LEAD)
+        V = ora_lk.dense_lucaskanade(frames)
+    return ora.extrapolate(precip, V, T_LEAD)
 
 
-def cpu_baseline(frames, V, lk, reps=1):
+def cpu_baseline(frames, precip, V, lk, reps=1):
     import oracle
     best = None
     for _ in range(reps):
         t0 = time.perf_counter()
-        cpu_step(frames, V, lk)
+        cpu_step(frames, precip, V, lk)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     return {"value": T_LEAD * M * N_ / best / 1e6, "unit": UNIT, "cores": oracle.num_threads(),
@@ -134,13 +136,14 @@ def run_reference(args):
     if rank != 0:
         return 0
     lk = have_lk_oracle()
-    frames, V = make_inputs(0, lk)
+    frames, precip, V = make_inputs(0, lk)
     import oracle
     for _ in range(args.warmup):
-        cpu_step(frames[:, :256, :256], V[:, :256, :256], lk)
+        cpu_step(np.ascontiguousarray(frames[:, :256, :256]), np.ascontiguousarray(precip[:256, :256]),
+                 np.ascontiguousarray(V[:, :256, :256]), lk)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_step(frames, V, lk)
+        cpu_step(frames, precip, V, lk)
     dt = time.perf_counter() - t0
     val = args.steps * T_LEAD * M * N_ / dt / 1e6
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
@@ -187,12 +190,14 @@ def run_ours(args):
         from pysteps_b200 import motion as b200_motion
         motion = b200_motion.get_method("lk")
 
-    frames_h, V_h = make_inputs(rank, lk)
+    frames_h, precip_h, V_h = make_inputs(rank, lk)
     # pinned host buffers for the e2e leg
     pin = lambda a: torch.from_numpy(a).pin_memory().numpy()  # noqa: E731
     frames_h = pin(frames_h)
+    precip_h = pin(precip_h)
     V_h = pin(V_h)
     frames_d = torch.from_numpy(frames_h).cuda()
+    precip_d = torch.from_numpy(precip_h).cuda()
     V_d = torch.from_numpy(V_h).cuda()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
@@ -207,20 +212,20 @@ def run_ours(args):
             Vd = V_d
         if world > 1:
             dist.broadcast(Vd, src=0)
-        return extrap(frames_d[-1], Vd, T_LEAD)
+        return extrap(precip_d, Vd, T_LEAD)
 
     def step_host():
         """public NumPy API: H2D of inputs and D2H of the result inside."""
         if lk:
-            Vh = motion(frames_h) if rank == 0 else None
+            Vh = motion(frames_h) if rank == 0 else None  # NumPy (2,m,n) float64, as pysteps returns
             if world > 1:
                 Vd = torch.from_numpy(Vh).cuda() if rank == 0 else \
                     torch.empty((2, M, N_), dtype=torch.float64, device="cuda")
                 dist.broadcast(Vd, src=0)
-                return extrap(frames_h[-1], Vd, T_LEAD).cpu().numpy()
+                Vh = Vd.cpu().numpy()
         else:
             Vh = V_h
-        return extrap(frames_h[-1], Vh, T_LEAD)
+        return extrap(precip_h, Vh, T_LEAD)
 
     def barrier():
         if world > 1:
@@ -265,7 +270,8 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     e2e_val = world * args.steps * T_LEAD * M * N_ / e2e_s / 1e6
-    h2d = frames_h[-1].nbytes + (frames_h.nbytes if lk else V_h.nbytes)
+    # LK: frames up, field down, field up again for the extrapolator (plugin API is NumPy)
+    h2d = precip_h.nbytes + (frames_h.nbytes + 2 * M * N_ * 8 if lk else V_h.nbytes)
     d2h = out.nbytes + (2 * M * N_ * 8 if lk else 0)
 
     if rank == 0:
@@ -292,11 +298,12 @@ def run_ours(args):
                     "peak_source": peak_src, "kernel_ms": k_avg,
                     "algorithmic_bytes_per_launch": alg_bytes}
         stage_ms = {k: sum(v) / args.steps for k, v in tr.items()}
-        cpu = cpu_baseline(frames_h, V_h, have_lk_oracle()) if not args.no_cpu else None
+        cpu = cpu_baseline(frames_h, precip_h, V_h, have_lk_oracle()) if not args.no_cpu else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64 trajectory arithmetic, f32 field storage", "data": "synthetic",
+                "dtype": "f64 (trajectories, motion field, IDW); f32 precip in/out; u8/i16/f32 "
+                         "OpenCV-exact LK stages", "data": "synthetic",
                 "config": {"workload": workload_name(lk), "frame": [M, N_], "leadtimes": T_LEAD,
                            "fields_per_gpu": 1, "l2": "flushed between timed steps (256 MB fill)",
                            "parallelism": f"1 field per GPU x{world}, NCCL broadcast of the motion field"},
