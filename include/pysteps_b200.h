@@ -131,9 +131,10 @@ int b200_morph_opening(const double *img, const uint8_t *mask, int m, int n, int
 /* stats (12 doubles): min / max / count over unmasked pixels of all rows [0..2], of rows
  * >= 1 [3..5], of rows >= 2 [6..8]; [11] = number of pixels whose dilate x dilate buffered
  * mask (cv2.dilate, feature/shitomasi.py:131-139) is clear.  The row sets reproduce the
- * integer-indexing quirk of shitomasi.py:139 (see csrc/lk_dense.cu). */
+ * integer-indexing quirk of shitomasi.py:139 (see csrc/lk_dense.cu).  stats0 (optional) is
+ * the output of b200_mask_invalid: when it shows no masked pixel the dilation is skipped. */
 int b200_masked_minmax(const double *img, const uint8_t *mask, int m, int n, int dilate,
-                       double *stats, void *stream);
+                       const double *stats0, double *stats, void *stream);
 
 /* "scale between 0 and 255" + astype(uint8).  mode 0: tracking/lucaskanade.py:144-160;
  * mode 1: feature/shitomasi.py:131-151 (buffer_mask = dilate) with valid = buffered mask

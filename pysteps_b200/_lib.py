@@ -40,7 +40,8 @@ _SIGNATURES = {
     "b200_mask_invalid": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "b200_morph_opening": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p]),
-    "b200_masked_minmax": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "b200_masked_minmax": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+                                   c_void_p]),
     "b200_quantise_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p]),
     "b200_fill_f64": (c_int, [c_void_p, c_i64, c_double, c_void_p]),

@@ -15,7 +15,7 @@
 
 namespace {
 
-constexpr int IDW_TX = 32, IDW_TY = 8;            // pixel tile of one CTA
+constexpr int IDW_TX = 16, IDW_TY = 16;           // pixel tile of one CTA (8 warps of 8x4 pixels)
 constexpr int IDW_THREADS = IDW_TX * IDW_TY;
 constexpr int IDW_CHUNK = 2048;                    // source vectors examined per round
 constexpr int IDW_BINS = 256;                      // distance histogram of the tile centre
@@ -62,21 +62,67 @@ __device__ __forceinline__ double np_sum(const double (&w)[K], int k) {
 // p of the tile has its k nearest within Rk + r of p, hence within Rk + 2r of c.  Vectors
 // outside that disc cannot be among any pixel's k nearest and are dropped -- the result is
 // identical to the exhaustive search, with ~k..3k candidates per tile instead of all.
-// Candidates are compacted IN INDEX ORDER, so equal distances still resolve to the lower
-// index exactly as in the exhaustive scan.
-template <int K>
+// The candidates are bucketed by centre distance (counting sort on the histogram that gave
+// Rk), so each pixel meets its near vectors first and later ones fail the `< worst` test
+// without touching the sorted list.  Order of examination is irrelevant for the result:
+// the list is ordered by (squared distance, index), i.e. equal distances resolve to the
+// lower index exactly as cKDTree-free exhaustive scanning in index order would.
+// Sorted list of the k best (squared distance, index) pairs of one pixel.
+// EXACT = true: k == K, the list lives in registers (every index is a compile-time constant)
+// and an insertion is branch free: K independent "key < entry" predicates, then each slot
+// takes its left neighbour, the key, or keeps its value.  Squared distances are >= 0, so
+// their bit patterns order like the doubles; (bits, index) is compared as one integer key.
+// EXACT = false (k < K: fewer vectors than neighbours, or an unusual k): same algorithm with
+// a runtime length; the arrays may live in local memory -- a rare, small-problem path.
+template <int K, bool EXACT>
+__device__ __forceinline__ void topk_scan(const double2 *__restrict__ spt, const int *__restrict__ sidx,
+                                          int ncand, double qx, double qy, int k,
+                                          unsigned long long (&bd)[K], int (&bi)[K]) {
+    for (int t = 0; t < ncand; t++) {
+        const double2 s = spt[t];
+        const double dx = __dsub_rn(s.x, qx), dy = __dsub_rn(s.y, qy);
+        const unsigned long long d2 =
+            (unsigned long long)__double_as_longlong(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+        const int last = EXACT ? K - 1 : k - 1;
+        unsigned long long wd = bd[K - 1];
+        int wi = bi[K - 1];
+        if (!EXACT) {
+#pragma unroll
+            for (int q = 0; q < K; q++)
+                if (q == last) { wd = bd[q]; wi = bi[q]; }
+        }
+        const int id = sidx[t];
+        if (d2 < wd || (d2 == wd && id < wi)) {
+            bool lt[K];
+#pragma unroll
+            for (int q = 0; q < K; q++) lt[q] = d2 < bd[q] || (d2 == bd[q] && id < bi[q]);
+#pragma unroll
+            for (int q = K - 1; q >= 1; q--) {
+                if (EXACT || q <= last) {
+                    const unsigned long long nd = lt[q - 1] ? bd[q - 1] : (lt[q] ? d2 : bd[q]);
+                    const int ni = lt[q - 1] ? bi[q - 1] : (lt[q] ? id : bi[q]);
+                    bd[q] = nd; bi[q] = ni;
+                }
+            }
+            if (lt[0]) { bd[0] = d2; bi[0] = id; }
+        }
+    }
+}
+
+template <int K, bool EXACT>
 __global__ void __launch_bounds__(IDW_THREADS) idw_kernel(const IDWParams p) {
     __shared__ double2 spt[IDW_CHUNK];
     __shared__ int sidx[IDW_CHUNK];
-    __shared__ int hist[IDW_BINS];
-    __shared__ int warp_cnt[IDW_THREADS / 32];
-    __shared__ double s_R2;
-    __shared__ int s_n;
+    __shared__ int hist[IDW_BINS];   // counts, then exclusive offsets
+    __shared__ int fill[IDW_BINS];
+    __shared__ int s_bmax, s_total;
     const int npts = p.npts_dev ? min(*p.npts_dev, p.npts_cap) : p.npts_cap;
     const int k = min(min(p.k, npts), K);
-    const int tid = threadIdx.y * IDW_TX + threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int j = blockIdx.x * IDW_TX + threadIdx.x;  // column
-    const int i = blockIdx.y * IDW_TY + threadIdx.y;  // row
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    // a warp covers a compact 8x4 pixel patch: its lanes agree on most insert decisions
+    const int j = blockIdx.x * IDW_TX + (wid & 1) * 8 + (lane & 7);   // column
+    const int i = blockIdx.y * IDW_TY + (wid >> 1) * 4 + (lane >> 3);  // row
+    const double2 *__restrict__ pts = reinterpret_cast<const double2 *>(p.xy);
     const bool active = j < p.nx && i < p.ny;
     const double qx = p.gx[min(j, p.nx - 1)], qy = p.gy[min(i, p.ny - 1)];
 
@@ -88,99 +134,92 @@ __global__ void __launch_bounds__(IDW_THREADS) idw_kernel(const IDWParams p) {
     // grids are monotonic (np.arange in dense_lucaskanade); the tile extent bounds the radius
     const double rt = sqrt(0.25 * (xb - xa) * (xb - xa) + 0.25 * (yb - ya) * (yb - ya));
     const double binw = fmax(rt, 1e-300) * 0.5;
-    for (int b = tid; b < IDW_BINS; b += IDW_THREADS) hist[b] = 0;
+    const double inv_binw = 1.0 / binw;
+    for (int b = tid; b < IDW_BINS; b += IDW_THREADS) { hist[b] = 0; fill[b] = 0; }
     __syncthreads();
-    for (int t = tid; t < npts; t += IDW_THREADS) {
-        const double dx = p.xy[2 * t] - cx, dy = p.xy[2 * t + 1] - cy;
-        const double d = sqrt(dx * dx + dy * dy) / binw;
-        const int b = d < (double)(IDW_BINS - 1) ? (int)d : IDW_BINS - 1;
-        atomicAdd(&hist[b], 1);
-    }
+    auto bin_of = [&](int t) -> int {
+        const double2 s = pts[t];
+        const double dx = s.x - cx, dy = s.y - cy;
+        // conservative: a vector is never put in a bin below its true distance (1e-9 slack)
+        const double d = sqrt(dx * dx + dy * dy) * inv_binw * (1.0 + 1e-9);
+        return d < (double)(IDW_BINS - 1) ? (int)d : IDW_BINS - 1;
+    };
+    for (int t = tid; t < npts; t += IDW_THREADS) atomicAdd(&hist[bin_of(t)], 1);
     __syncthreads();
-    if (tid == 0) {
-        int acc = 0, b = 0;
-        for (; b < IDW_BINS; b++) {
-            acc += hist[b];
-            if (acc >= k) break;
+    if (tid < 32) {
+        // exclusive prefix over the bins (8 per lane), bin of the k-th vector, search bound
+        int c[IDW_BINS / 32], sum = 0;
+#pragma unroll
+        for (int q = 0; q < IDW_BINS / 32; q++) { c[q] = hist[lane * (IDW_BINS / 32) + q]; sum += c[q]; }
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
         }
-        // overflow bin: no bound (every vector is a candidate)
-        double R = (b >= IDW_BINS - 1) ? CUDART_INF : ((double)(b + 1) * binw + 2.0 * rt) * (1.0 + 1e-9);
-        s_R2 = R * R;
+        int run = incl - sum, bk = IDW_BINS;  // first bin whose inclusive count reaches k
+#pragma unroll
+        for (int q = 0; q < IDW_BINS / 32; q++) {
+            hist[lane * (IDW_BINS / 32) + q] = run;
+            run += c[q];
+            if (run >= k && bk == IDW_BINS) bk = lane * (IDW_BINS / 32) + q;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) bk = min(bk, __shfl_xor_sync(0xffffffffu, bk, o));
+        if (lane == 0) {
+            int bmax = IDW_BINS - 1;  // overflow bin reached: every vector is a candidate
+            if (bk < IDW_BINS - 1) {
+                const double R = ((double)(bk + 1) * binw + 2.0 * rt) * (1.0 + 1e-9);
+                const double bb = R * inv_binw * (1.0 + 1e-9);
+                bmax = bb < (double)(IDW_BINS - 1) ? (int)bb : IDW_BINS - 1;
+            }
+            s_bmax = bmax;
+        }
     }
     __syncthreads();
-    const double R2 = s_R2;
+    const int bmax = s_bmax;
+    if (tid == 0) s_total = (bmax == IDW_BINS - 1) ? npts : hist[bmax + 1];
+    __syncthreads();
+    const int total = s_total;
 
-    double bd[K];
+    unsigned long long bd[K];  // squared distances as ordered bit patterns
     int bi[K];
 #pragma unroll
-    for (int q = 0; q < K; q++) { bd[q] = CUDART_INF; bi[q] = 0; }
-    double worst = CUDART_INF;  // bd[k-1], refreshed only when the list changes
+    for (int q = 0; q < K; q++) { bd[q] = 0x7ff0000000000000ull; bi[q] = 0x7fffffff; }  // +inf
 
-    for (int base = 0; base < npts; base += IDW_CHUNK) {
-        const int cnt = min(IDW_CHUNK, npts - base);
-        // ---- ordered compaction of the candidates of this chunk ------------------------
+    // sorted: all candidates fit in shared memory (one round, counting sort by centre-distance
+    // bin); otherwise plain exhaustive rounds over chunks of all vectors
+    const bool sorted = total <= IDW_CHUNK;
+    const int nrounds = sorted ? 1 : (npts + IDW_CHUNK - 1) / IDW_CHUNK;
+    for (int r = 0; r < nrounds; r++) {
+        int cnt;
         __syncthreads();
-        if (tid == 0) s_n = 0;
-        __syncthreads();
-        for (int t0 = 0; t0 < cnt; t0 += IDW_THREADS) {
-            const int t = t0 + tid;
-            double2 s = make_double2(0.0, 0.0);
-            bool keep = false;
-            if (t < cnt) {
-                s = make_double2(p.xy[2 * (base + t)], p.xy[2 * (base + t) + 1]);
-                const double dx = s.x - cx, dy = s.y - cy;
-                keep = !(dx * dx + dy * dy > R2);
+        if (sorted) {
+            for (int t = tid; t < npts; t += IDW_THREADS) {
+                const int b = bin_of(t);
+                if (b <= bmax) {
+                    const int o = hist[b] + atomicAdd(&fill[b], 1);
+                    spt[o] = pts[t];
+                    sidx[o] = t;
+                }
             }
-            const unsigned bal = __ballot_sync(0xffffffffu, keep);
-            if (lane == 0) warp_cnt[wid] = __popc(bal);
-            __syncthreads();
-            int before = s_n, total = 0;
-#pragma unroll
-            for (int w = 0; w < IDW_THREADS / 32; w++) {
-                if (w < wid) before += warp_cnt[w];
-                total += warp_cnt[w];
-            }
-            if (keep) {
-                const int o = before + __popc(bal & ((1u << lane) - 1u));
-                spt[o] = s;
-                sidx[o] = base + t;
-            }
-            __syncthreads();
-            if (tid == 0) s_n += total;
-            __syncthreads();
-        }
-        const int ncand = s_n;
-        if (!active) continue;
-        // ---- exhaustive top-k over the candidates ------------------------------------
-        for (int t = 0; t < ncand; t++) {
-            const double2 s = spt[t];
-            const double dx = __dsub_rn(s.x, qx), dy = __dsub_rn(s.y, qy);
-            const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-            if (d2 < worst) {
-                // replace the worst, then bubble towards the front (strict <: earlier index
-                // stays first on equal distances)
-                const int id = sidx[t];
-#pragma unroll
-                for (int q = K - 1; q >= 0; q--)
-                    if (q == k - 1) { bd[q] = d2; bi[q] = id; }
-#pragma unroll
-                for (int q = K - 1; q >= 1; q--)
-                    if (q <= k - 1 && bd[q] < bd[q - 1]) {
-                        const double td = bd[q]; bd[q] = bd[q - 1]; bd[q - 1] = td;
-                        const int ti = bi[q]; bi[q] = bi[q - 1]; bi[q - 1] = ti;
-                    }
-                // K is a compile-time bound, k <= K is the runtime list length
-#pragma unroll
-                for (int q = 0; q < K; q++)
-                    if (q == k - 1) worst = bd[q];
+            cnt = total;
+        } else {
+            const int base = r * IDW_CHUNK;
+            cnt = min(IDW_CHUNK, npts - base);
+            for (int t = tid; t < cnt; t += IDW_THREADS) {
+                spt[t] = pts[base + t];
+                sidx[t] = base + t;
             }
         }
+        __syncthreads();
+        if (active) topk_scan<K, EXACT>(spt, sidx, cnt, qx, qy, k, bd, bi);
     }
     if (!active || k < 1) return;
     double w[K];
 #pragma unroll
     for (int q = 0; q < K; q++) {
-        double d = sqrt(bd[q]);                 // exact Euclidean distance (IEEE sqrt)
+        double d = sqrt(__longlong_as_double((long long)bd[q]));  // exact Euclidean distance
         d = __ddiv_rn(d, p.mean_res);           // interpolate.py:98
         d = __dadd_rn(d, p.offset);             // :101
         const double pw = (p.power == 0.5) ? sqrt(d) : pow(d, p.power);
@@ -216,11 +255,13 @@ extern "C" int b200_idw_fill(const double *xy, const double *vals, const int *np
     p.gx = xgrid; p.gy = ygrid; p.nx = nx; p.ny = ny;
     p.power = power; p.offset = dist_offset; p.mean_res = mean_res; p.out = out;
     dim3 grid(b200::ceil_div(nx, IDW_TX), b200::ceil_div(ny, IDW_TY));
-    dim3 block(IDW_TX, IDW_TY);
+    dim3 block(IDW_THREADS);
     cudaStream_t s = (cudaStream_t)stream;
-    if (k <= 8) idw_kernel<8><<<grid, block, 0, s>>>(p);
-    else if (k <= 20) idw_kernel<20><<<grid, block, 0, s>>>(p);
-    else idw_kernel<32><<<grid, block, 0, s>>>(p);
+    // the host knows npts only as a capacity when npts_dev is given; EXACT needs k == K <= npts
+    const bool exact_ok = (npts_dev == nullptr) && npts_cap >= k;
+    if (k == 20 && exact_ok) idw_kernel<20, true><<<grid, block, 0, s>>>(p);
+    else if (k == 8 && exact_ok) idw_kernel<8, true><<<grid, block, 0, s>>>(p);
+    else idw_kernel<32, false><<<grid, block, 0, s>>>(p);
     B200_LAUNCH_CHECK();
     return 0;
 }

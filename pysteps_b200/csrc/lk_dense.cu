@@ -94,18 +94,21 @@ __global__ void __launch_bounds__(TX *TY)
 mask_invalid_kernel(const double *__restrict__ img, const uint8_t *__restrict__ user_mask, int m, int n,
                     uint8_t *__restrict__ mask, MM *__restrict__ part) {
     __shared__ MM sm[32];
-    const int x = blockIdx.x * TX + threadIdx.x, y = blockIdx.y * TY + threadIdx.y;
     MM v;
     v.mn = CUDART_INF; v.mx = -CUDART_INF; v.cnt = 0;
-    if (x < n && y < m) {
-        const size_t i = (size_t)y * n + x;
-        const double a = img[i];
-        const bool msk = (user_mask && user_mask[i]) || !isfinite(a);
-        mask[i] = msk ? 1 : 0;
-        if (!msk) { v.mn = a; v.mx = a; v.cnt = 1; }
+    const int tiles_x = (n + TX - 1) / TX, tiles = tiles_x * ((m + TY - 1) / TY);
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x) {  // persistent CTAs over pixel tiles
+        const int x = (t % tiles_x) * TX + threadIdx.x, y = (t / tiles_x) * TY + threadIdx.y;
+        if (x < n && y < m) {
+            const size_t i = (size_t)y * n + x;
+            const double a = img[i];
+            const bool msk = (user_mask && user_mask[i]) || !isfinite(a);
+            mask[i] = msk ? 1 : 0;
+            if (!msk) { v.mn = fmin(v.mn, a); v.mx = fmax(v.mx, a); v.cnt++; }
+        }
     }
     v = mm_block(v, sm);
-    if (threadIdx.x == 0 && threadIdx.y == 0) part[blockIdx.y * gridDim.x + blockIdx.x] = v;
+    if (threadIdx.x == 0 && threadIdx.y == 0) part[blockIdx.x] = v;
 }
 
 // utils/images.py:66-81 : bin = filled > thr ; open with the 3x3 cross ; pixels removed by the
@@ -148,22 +151,26 @@ morph_open_kernel(const double *__restrict__ img, const uint8_t *__restrict__ ma
 // the buffered mask contains a 0 and row 1 when it contains a 1 -- not the buffered pixels.
 __global__ void __launch_bounds__(TX *TY)
 masked_minmax_kernel(const double *__restrict__ img, const uint8_t *__restrict__ mask, int m, int n,
-                     int dil, MM *__restrict__ part, int nparts) {
+                     int dil, const double *__restrict__ stats0, MM *__restrict__ part, int nparts) {
     __shared__ MM sm[32];
-    const int x = blockIdx.x * TX + threadIdx.x, y = blockIdx.y * TY + threadIdx.y;
     MM a[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) { a[k].mn = CUDART_INF; a[k].mx = -CUDART_INF; a[k].cnt = 0; }
-    if (x < n && y < m) {
+    // nothing masked (stats of b200_mask_invalid): the buffered mask is clear everywhere
+    const bool any_masked = !stats0 || stats0[2] < (double)m * (double)n;
+    const int tiles_x = (n + TX - 1) / TX, tiles = tiles_x * ((m + TY - 1) / TY);
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int x = (t % tiles_x) * TX + threadIdx.x, y = (t / tiles_x) * TY + threadIdx.y;
+        if (x >= n || y >= m) continue;
         const size_t i = (size_t)y * n + x;
         const double v = img[i];
-        if (!mask[i]) {
-            a[0].mn = a[0].mx = v; a[0].cnt = 1;
-            if (y >= 1) a[1] = a[0];
-            if (y >= 2) a[2] = a[0];
-        }
         bool d = mask[i] != 0;
-        if (dil > 0) {
+        if (!d) {
+            a[0].mn = fmin(a[0].mn, v); a[0].mx = fmax(a[0].mx, v); a[0].cnt++;
+            if (y >= 1) { a[1].mn = fmin(a[1].mn, v); a[1].mx = fmax(a[1].mx, v); a[1].cnt++; }
+            if (y >= 2) { a[2].mn = fmin(a[2].mn, v); a[2].mx = fmax(a[2].mx, v); a[2].cnt++; }
+        }
+        if (dil > 0 && any_masked) {
             const int r = dil / 2;
             for (int dy = -r; dy <= dil - 1 - r; dy++)
                 for (int dx = -r; dx <= dil - 1 - r; dx++) {
@@ -171,13 +178,12 @@ masked_minmax_kernel(const double *__restrict__ img, const uint8_t *__restrict__
                     if (yy >= 0 && yy < m && xx >= 0 && xx < n) d |= mask[(size_t)yy * n + xx] != 0;
                 }
         }
-        if (!d) a[3].cnt = 1;
+        if (!d) a[3].cnt++;
     }
-    const int bi = blockIdx.y * gridDim.x + blockIdx.x;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const MM r = mm_block(a[k], sm);
-        if (threadIdx.x == 0 && threadIdx.y == 0) part[(size_t)k * nparts + bi] = r;
+        if (threadIdx.x == 0 && threadIdx.y == 0) part[(size_t)k * nparts + blockIdx.x] = r;
     }
 }
 
@@ -316,31 +322,66 @@ cov_rowsum_kernel(const uint8_t *__restrict__ q, int h, int w, double *__restric
 // per column: OpenCV's running column sum (double) down the rows, then the eigenvalue.
 // The recurrence is history dependent (add entering row, emit, subtract leaving row), so a
 // column is one sequential chain; columns are independent and coalesced across the warp.
-__global__ void __launch_bounds__(128)
+// The row leaving at step y is the row that entered at step y-4 (a 4-deep delay line in
+// registers), so each step needs only the entering row; those loads do not depend on the
+// chain and are issued BOX_U steps ahead to cover DRAM latency with few resident warps.
+constexpr int BOX_U = 8;
+
+__global__ void __launch_bounds__(32)
 box_eig_kernel(const double *__restrict__ rs, int h, int w, float *__restrict__ eig) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= w) return;
     const size_t N = (size_t)h * w;
-    double S0 = 0.0, S1 = 0.0, S2 = 0.0;
-    for (int k = -2; k < 2; k++) {
-        const size_t i = (size_t)reflect101(k, h) * w + x;
-        S0 = __dadd_rn(S0, rs[i]);
-        S1 = __dadd_rn(S1, rs[N + i]);
-        S2 = __dadd_rn(S2, rs[2 * N + i]);
+    // rows -2, -1, 0, 1 (reflected): the initial sum and the first four leaving rows
+    double ring[4][3];
+    double S[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const size_t i = (size_t)reflect101(k - 2, h) * w + x;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            ring[k][c] = rs[c * N + i];
+            S[c] = __dadd_rn(S[c], ring[k][c]);
+        }
     }
-    for (int y = 0; y < h; y++) {
-        const size_t ip = (size_t)reflect101(y + 2, h) * w + x;
-        const size_t im = (size_t)reflect101(y - 2, h) * w + x;
-        const double a0 = __dadd_rn(S0, rs[ip]), a1 = __dadd_rn(S1, rs[N + ip]), a2 = __dadd_rn(S2, rs[2 * N + ip]);
-        S0 = __dsub_rn(a0, rs[im]);
-        S1 = __dsub_rn(a1, rs[N + im]);
-        S2 = __dsub_rn(a2, rs[2 * N + im]);
-        const float a = __fmul_rn(__double2float_rn(a0), 0.5f);
-        const float b = __double2float_rn(a1);
-        const float c = __fmul_rn(__double2float_rn(a2), 0.5f);
-        const float t = __fsub_rn(a, c);
-        const float r = __fsqrt_rn(__fadd_rn(__fmul_rn(t, t), __fmul_rn(b, b)));
-        eig[(size_t)y * w + x] = __fsub_rn(__fadd_rn(a, c), r);
+    double cur[BOX_U][3];
+#pragma unroll
+    for (int u = 0; u < BOX_U; u++) {
+        const size_t i = (size_t)reflect101(u + 2, h) * w + x;
+#pragma unroll
+        for (int c = 0; c < 3; c++) cur[u][c] = rs[c * N + i];
+    }
+    for (int y0 = 0; y0 < h; y0 += BOX_U) {
+        double nxt[BOX_U][3];
+#pragma unroll
+        for (int u = 0; u < BOX_U; u++) {
+            const size_t i = (size_t)reflect101(y0 + BOX_U + u + 2, h) * w + x;
+#pragma unroll
+            for (int c = 0; c < 3; c++) nxt[u][c] = rs[c * N + i];
+        }
+#pragma unroll
+        for (int u = 0; u < BOX_U; u++) {
+            const int y = y0 + u;
+            if (y < h) {
+                double a[3];
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    a[c] = __dadd_rn(S[c], cur[u][c]);
+                    S[c] = __dsub_rn(a[c], ring[u & 3][c]);  // y0 is a multiple of 4
+                    ring[u & 3][c] = cur[u][c];
+                }
+                const float fa = __fmul_rn(__double2float_rn(a[0]), 0.5f);
+                const float fb = __double2float_rn(a[1]);
+                const float fc = __fmul_rn(__double2float_rn(a[2]), 0.5f);
+                const float t = __fsub_rn(fa, fc);
+                const float r = __fsqrt_rn(__fadd_rn(__fmul_rn(t, t), __fmul_rn(fb, fb)));
+                eig[(size_t)y * w + x] = __fsub_rn(__fadd_rn(fa, fc), r);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < BOX_U; u++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) cur[u][c] = nxt[u][c];
     }
 }
 
@@ -352,11 +393,10 @@ extern "C" int b200_mask_invalid(const double *img, const uint8_t *user_mask, in
                                  uint8_t *mask_out, double *stats, void *stream) {
     B200_REQUIRE(img && mask_out && stats && m >= 1 && n >= 1, "bad arguments");
     cudaStream_t s = (cudaStream_t)stream;
-    const dim3 g = grid2d(m, n);
-    const int nparts = g.x * g.y;
+    const int nparts = b200::num_sms() * 4;  // persistent CTAs: a multiple of the SM count
     b200::Scratch part;
     B200_CUDA(part.alloc(sizeof(MM) * nparts, s));
-    mask_invalid_kernel<<<g, dim3(TX, TY), 0, s>>>(img, user_mask, m, n, mask_out, (MM *)part.p);
+    mask_invalid_kernel<<<nparts, dim3(TX, TY), 0, s>>>(img, user_mask, m, n, mask_out, (MM *)part.p);
     B200_LAUNCH_CHECK();
     mm_final_kernel<<<1, 256, 0, s>>>((const MM *)part.p, nparts, 1, stats);
     B200_LAUNCH_CHECK();
@@ -377,14 +417,13 @@ extern "C" int b200_morph_opening(const double *img, const uint8_t *mask, int m,
 }
 
 extern "C" int b200_masked_minmax(const double *img, const uint8_t *mask, int m, int n, int dilate,
-                                  double *stats, void *stream) {
+                                  const double *stats0, double *stats, void *stream) {
     B200_REQUIRE(img && mask && stats && m >= 1 && n >= 1 && dilate >= 0 && dilate <= 31, "bad arguments");
     cudaStream_t s = (cudaStream_t)stream;
-    const dim3 g = grid2d(m, n);
-    const int nparts = g.x * g.y;
+    const int nparts = b200::num_sms() * 4;
     b200::Scratch part;
     B200_CUDA(part.alloc(sizeof(MM) * nparts * 4, s));
-    masked_minmax_kernel<<<g, dim3(TX, TY), 0, s>>>(img, mask, m, n, dilate, (MM *)part.p, nparts);
+    masked_minmax_kernel<<<nparts, dim3(TX, TY), 0, s>>>(img, mask, m, n, dilate, stats0, (MM *)part.p, nparts);
     B200_LAUNCH_CHECK();
     mm_final_kernel<<<1, 256, 0, s>>>((const MM *)part.p, nparts, 4, stats);
     B200_LAUNCH_CHECK();

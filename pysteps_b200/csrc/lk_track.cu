@@ -67,8 +67,15 @@ __global__ void __launch_bounds__(LK_THREADS) lk_track_kernel(const LKParams p) 
     short *Iw = (short *)smem_raw;         // patch of I, 5 fractional bits
     short *Dx = Iw + npx;                  // interpolated Scharr derivatives
     short *Dy = Dx + npx;
-    short *Df = Dy + npx;                  // J - I mismatch of the current iteration
-    float *red = (float *)(Df + npx);       // 16 floats: chain results (4*npx shorts: 8-byte aligned)
+    // per-iteration mismatch products, already widened to float32 in the order the chains
+    // consume them: PX/PY[(y * nchunk + c) * 4 + q] = int32 pair sum of pixels (8c+q, 8c+q+4),
+    // TX/TY[y * ntail + t] = single-pixel products of the scalar tail
+    const int npair = wh * nchunk * 4, ntl = wh * ntail;
+    float *PX = (float *)(Dy + npx + (npx & 1));
+    float *PY = PX + npair;
+    float *TXp = PY + npair;
+    float *TYp = TXp + ntl;
+    float *red = TYp + ntl;                // 16 floats: chain results
     __shared__ float s_b[2];
 
     const float half_x = (ww - 1) * 0.5f, half_y = (wh - 1) * 0.5f;
@@ -126,6 +133,7 @@ __global__ void __launch_bounds__(LK_THREADS) lk_track_kernel(const LKParams p) 
             if (tid < 12) {
                 const int l = tid & 3;
                 for (int y = 0; y < wh; y++)
+#pragma unroll 4
                     for (int x = l; x < simd_w; x += 4) {
                         const float fx = (float)Dx[y * ww + x], fy = (float)Dy[y * ww + x];
                         const float pr = acc == 0 ? fx * fx : (acc == 1 ? fx * fy : fy * fy);
@@ -166,15 +174,27 @@ __global__ void __launch_bounds__(LK_THREADS) lk_track_kernel(const LKParams p) 
                 break;
             }
             make_weights(nx - (float)jx, ny - (float)jy, w00, w01, w10, w11);
-            // ---- mismatch J - I (data parallel) -----------------------------------------
+            // ---- mismatch J - I and its products with the derivatives (data parallel) --------
             __syncthreads();
-            for (int i = tid; i < npx; i += LK_THREADS) {
-                const int y = i / ww, x = i - y * ww;
+            auto mismatch = [&](int y, int x) -> int {
                 const int r0 = reflect101(jy + y, h), r1 = reflect101(jy + y + 1, h);
                 const int c0 = reflect101(jx + x, w), c1 = reflect101(jx + x + 1, w);
                 const int jv = descale(J[(size_t)r0 * w + c0] * w00 + J[(size_t)r0 * w + c1] * w01 +
                                        J[(size_t)r1 * w + c0] * w10 + J[(size_t)r1 * w + c1] * w11, W_BITS - 5);
-                Df[i] = (short)(jv - Iw[i]);
+                return jv - (int)Iw[y * ww + x];
+            };
+            for (int i = tid; i < npair; i += LK_THREADS) {
+                const int q = i & 3, c = (i >> 2) % nchunk, y = (i >> 2) / nchunk;
+                const int x0 = 8 * c + q, i0 = y * ww + x0;
+                const int d0 = mismatch(y, x0), d1 = mismatch(y, x0 + 4);
+                PX[i] = (float)(d0 * (int)Dx[i0] + d1 * (int)Dx[i0 + 4]);
+                PY[i] = (float)(d0 * (int)Dy[i0] + d1 * (int)Dy[i0 + 4]);
+            }
+            for (int i = tid; i < ntl; i += LK_THREADS) {
+                const int y = i / ntail, x = simd_w + (i - y * ntail);
+                const int d0 = mismatch(y, x);
+                TXp[i] = (float)(d0 * (int)Dx[y * ww + x]);
+                TYp[i] = (float)(d0 * (int)Dy[y * ww + x]);
             }
             __syncthreads();
             // ---- mismatch vector: 8 lane chains over pixel pairs (q, q+4) + 2 tail chains --
@@ -182,18 +202,15 @@ __global__ void __launch_bounds__(LK_THREADS) lk_track_kernel(const LKParams p) 
                 float q = 0.f;
                 if (tid < 8) {
                     // qb0 = [x(0,4) y(0,4) x(1,5) y(1,5)], qb1 = [x(2,6) y(2,6) x(3,7) y(3,7)]
-                    const int pair = (tid >> 2) * 2 + ((tid & 3) >> 1), comp = tid & 1;
-                    const short *G = comp ? Dy : Dx;
-                    for (int y = 0; y < wh; y++)
-                        for (int c = 0; c < nchunk; c++) {
-                            const int i0 = y * ww + 8 * c + pair;
-                            const int s = (int)Df[i0] * (int)G[i0] + (int)Df[i0 + 4] * (int)G[i0 + 4];
-                            q += (float)s;
-                        }
+                    const int pair = (tid >> 2) * 2 + ((tid & 3) >> 1);
+                    const float *P = (tid & 1) ? PY : PX;
+                    const int nsteps = wh * nchunk;
+#pragma unroll 8
+                    for (int s = 0; s < nsteps; s++) q += P[4 * s + pair];
                 } else {
-                    const short *G = (tid == 9) ? Dy : Dx;
-                    for (int y = 0; y < wh; y++)
-                        for (int x = simd_w; x < ww; x++) q += (float)((int)Df[y * ww + x] * (int)G[y * ww + x]);
+                    const float *P = (tid == 9) ? TYp : TXp;
+#pragma unroll 4
+                    for (int s = 0; s < ntl; s++) q += P[s];
                 }
                 red[tid] = q;
             }
@@ -354,7 +371,9 @@ extern "C" int b200_lk_track(const uint8_t *pyrI, const uint8_t *pyrJ, const int
     p.npts = npts; p.npts_dev = npts_dev;
     p.next_pts = next_pts; p.status = status;
     const int npx = win_w * win_h;
-    const size_t smem = sizeof(short) * 4 * (size_t)npx + 16 * sizeof(float);
+    const int nchunk = win_w / 8, ntail = win_w - nchunk * 8;
+    const size_t smem = sizeof(short) * (3 * (size_t)npx + (npx & 1)) +
+                        sizeof(float) * (2 * (size_t)win_h * nchunk * 4 + 2 * (size_t)win_h * ntail + 16);
     B200_CUDA(cudaFuncSetAttribute(lk_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     lk_track_kernel<<<npts, LK_THREADS, smem, (cudaStream_t)stream>>>(p);
     B200_LAUNCH_CHECK();

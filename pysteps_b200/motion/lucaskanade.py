@@ -69,7 +69,7 @@ def _frame_stats(f, m, n, buffer_mask):
     if f.stats is None:
         f.stats = torch.empty(12, dtype=torch.float64, device="cuda")
         _call("b200_masked_minmax", f.opened.data_ptr(), f.mask.data_ptr(), m, n, int(buffer_mask),
-              f.stats.data_ptr(), _s())
+              f.stats0.data_ptr(), f.stats.data_ptr(), _s())
     return f.stats
 
 

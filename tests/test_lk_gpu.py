@@ -56,7 +56,7 @@ class Stages:
                self.st0.data_ptr(), self.st0.data_ptr(), self.opened.data_ptr(), s)
         self.st = torch.empty(12, dtype=torch.float64, device="cuda")
         L.call("b200_masked_minmax", self.opened.data_ptr(), self.mask.data_ptr(), m, n, buffer_mask,
-               self.st.data_ptr(), s)
+               self.st0.data_ptr(), self.st.data_ptr(), s)
         self.q_track = torch.empty((m, n), dtype=torch.uint8, device="cuda")
         L.call("b200_quantise_u8", self.opened.data_ptr(), self.mask.data_ptr(), m, n, 0, 0,
                self.st.data_ptr(), self.st.data_ptr(), self.q_track.data_ptr(), None, s)
