@@ -196,6 +196,28 @@ int b200_idw_fill(const double *xy, const double *vals, const int *npts_dev, int
                   const double *xgrid, int nx, const double *ygrid, int ny, double *out,
                   void *stream);
 
+/* ------------------------------------------------------------------------
+ * Variational Echo Tracking -- replaces the native extension of the reference,
+ * pysteps/motion/_vet.pyx.  The CG optimiser (scipy.optimize.minimize, vet.py:593-600)
+ * stays on the host and calls b200_vet_cost once per cost / gradient evaluation.
+ * Note the reference's axis naming: axis 0 of the images is "x", axis 1 is "y"
+ * (_vet.pyx:129-130); sector_disp is (2, xs, ys), images are (nx, ny), mask is int8.
+ * ---------------------------------------------------------------------- */
+
+/* _vet.pyx:238-621 _cost_function.  gradient == 0: out[0] = residuals, out[1] =
+ * smoothness penalty.  gradient != 0: out (2, xs, ys) = grad_residuals + grad_smooth.
+ * smooth_gain is a C float in the reference (:242) and is one here. */
+int b200_vet_cost(const double *sector_disp, const double *templ, const double *input,
+                  const int8_t *mask, int xs, int ys, int nx, int ny, float smooth_gain,
+                  int gradient, double *out, void *stream);
+/* _vet.pyx:66-232 _warp (vet.morph, vet.py:93-153): out, out_mask (int8) and, if grad is
+ * not NULL, the gradient (2, nx, ny). */
+int b200_vet_warp(const double *image, const int8_t *mask, const double *displacement, int nx,
+                  int ny, double *out, int8_t *out_mask, double *grad, void *stream);
+/* scipy.ndimage.zoom(a (c,h,w), (1, oh/h, ow/w), order=1, mode="nearest") (vet.py:621-630) */
+int b200_zoom_bilinear(const double *a, int c, int h, int w, int oh, int ow, double *out,
+                       void *stream);
+
 #ifdef __cplusplus
 }
 #endif
