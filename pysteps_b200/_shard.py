@@ -1,0 +1,33 @@
+"""Multi-GPU plumbing of the advection path: one process per GPU (torch.distributed),
+independent fields sharded round-robin over ranks, ONE broadcast of the motion field
+(ensemble members of nowcasts.steps each have their own precipitation
+field and displacement; nothing else is exchanged)."""
+import torch
+import torch.distributed as dist
+
+
+def member_indices(n_members, world_size, rank):
+    """Members owned by `rank`: i with i % world_size == rank (3 per GPU for 24 members on 8)."""
+    return list(range(rank, n_members, world_size))
+
+
+def broadcast_field(field, src=0, shape=None, dtype=torch.float64, device=None):
+    """Broadcast the (2,m,n) motion field computed on `src` to every rank.  Ranks other than
+    `src` may pass None (a buffer of `shape` is allocated).  No-op without a process group."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return field
+    if field is None:
+        if shape is None:
+            raise ValueError("shape is required on ranks that do not hold the field")
+        field = torch.empty(shape, dtype=dtype, device=device)
+    dist.broadcast(field, src=src)
+    return field
+
+
+def max_over_ranks(value, device=None):
+    """Max of a Python float over ranks (device timing is reported as the slowest rank)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
