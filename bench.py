@@ -182,7 +182,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     import pysteps_b200
-    from pysteps_b200 import _lib
+    from pysteps_b200 import _lib, _shard
     extrap = pysteps_b200.extrapolation.get_method("semilagrangian")
     lk = have_lk()
     motion = None
@@ -210,8 +210,7 @@ def run_ours(args):
                 Vd = torch.empty((2, M, N_), dtype=torch.float64, device="cuda")
         else:
             Vd = V_d
-        if world > 1:
-            dist.broadcast(Vd, src=0)
+        Vd = _shard.broadcast_field(Vd, src=0)  # the only collective (NCCL over NVLink)
         return extrap(precip_d, Vd, T_LEAD)
 
     def step_host():
@@ -250,10 +249,7 @@ def run_ours(args):
     launches = _lib.load().b200_launch_count() - launches0
     dev_ms = sum(s.elapsed_time(e) for s, e in ev)
     tr = trace.summary()
-    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms = float(t.item())
+    dev_ms = _shard.max_over_ranks(dev_ms, device="cuda")
     value = world * args.steps * T_LEAD * M * N_ / (dev_ms * 1e-3) / 1e6
 
     # ---- end-to-end timing (host buffers) --------------------------------------------
@@ -265,10 +261,7 @@ def run_ours(args):
         out = step_host()
     barrier()
     e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
+    e2e_s = _shard.max_over_ranks(e2e_s, device="cuda")
     e2e_val = world * args.steps * T_LEAD * M * N_ / e2e_s / 1e6
     # LK: frames up, field down, field up again for the extrapolator (plugin API is NumPy)
     h2d = precip_h.nbytes + (frames_h.nbytes + 2 * M * N_ * 8 if lk else V_h.nbytes)
