@@ -323,65 +323,73 @@ cov_rowsum_kernel(const uint8_t *__restrict__ q, int h, int w, double *__restric
 // The recurrence is history dependent (add entering row, emit, subtract leaving row), so a
 // column is one sequential chain; columns are independent and coalesced across the warp.
 // The row leaving at step y is the row that entered at step y-4 (a 4-deep delay line in
-// registers), so each step needs only the entering row; those loads do not depend on the
-// chain and are issued BOX_U steps ahead to cover DRAM latency with few resident warps.
-constexpr int BOX_U = 8;
+// registers), so each step needs only the entering row.  Those loads do not depend on the
+// chain: they are streamed BOX_R rows ahead into a shared-memory ring with cp.async
+// (LDGSTS), one commit group per row, so a single resident warp per SM still covers the
+// DRAM latency and the loop runs at the speed of its two dependent FP64 adds.
+constexpr int BOX_R = 48;  // rows in flight per warp: 48 * 3 planes * 32 columns * 8 B = 36 KB
+
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
 
 __global__ void __launch_bounds__(32)
 box_eig_kernel(const double *__restrict__ rs, int h, int w, float *__restrict__ eig) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= w) return;
+    __shared__ double ring_s[BOX_R][3][32];
+    const int lane = threadIdx.x;
+    const int x = blockIdx.x * 32 + lane;
+    const int xc = min(x, w - 1);  // out-of-range lanes shadow the last column
     const size_t N = (size_t)h * w;
     // rows -2, -1, 0, 1 (reflected): the initial sum and the first four leaving rows
-    double ring[4][3];
+    double delay[4][3];
     double S[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const size_t i = (size_t)reflect101(k - 2, h) * w + x;
+        const size_t i = (size_t)reflect101(k - 2, h) * w + xc;
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            ring[k][c] = rs[c * N + i];
-            S[c] = __dadd_rn(S[c], ring[k][c]);
+            delay[k][c] = rs[c * N + i];
+            S[c] = __dadd_rn(S[c], delay[k][c]);
         }
     }
-    double cur[BOX_U][3];
+    auto issue = [&](int y) {  // entering row of step y
+        if (y < h) {
+            const size_t i = (size_t)reflect101(y + 2, h) * w + xc;
 #pragma unroll
-    for (int u = 0; u < BOX_U; u++) {
-        const size_t i = (size_t)reflect101(u + 2, h) * w + x;
-#pragma unroll
-        for (int c = 0; c < 3; c++) cur[u][c] = rs[c * N + i];
-    }
-    for (int y0 = 0; y0 < h; y0 += BOX_U) {
-        double nxt[BOX_U][3];
-#pragma unroll
-        for (int u = 0; u < BOX_U; u++) {
-            const size_t i = (size_t)reflect101(y0 + BOX_U + u + 2, h) * w + x;
-#pragma unroll
-            for (int c = 0; c < 3; c++) nxt[u][c] = rs[c * N + i];
+            for (int c = 0; c < 3; c++) cp_async8(&ring_s[y % BOX_R][c][lane], rs + c * N + i);
         }
+        cp_async_commit();  // one (possibly empty) group per row keeps the group count uniform
+    };
+    for (int y = 0; y < BOX_R; y++) issue(y);
+    for (int y0 = 0; y0 < h; y0 += 4) {
 #pragma unroll
-        for (int u = 0; u < BOX_U; u++) {
+        for (int u = 0; u < 4; u++) {
             const int y = y0 + u;
+            cp_async_wait<BOX_R - 1>();  // the oldest outstanding row (y) has landed
             if (y < h) {
-                double a[3];
+                double in[3], a[3];
+#pragma unroll
+                for (int c = 0; c < 3; c++) in[c] = ring_s[y % BOX_R][c][lane];
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
-                    a[c] = __dadd_rn(S[c], cur[u][c]);
-                    S[c] = __dsub_rn(a[c], ring[u & 3][c]);  // y0 is a multiple of 4
-                    ring[u & 3][c] = cur[u][c];
+                    a[c] = __dadd_rn(S[c], in[c]);
+                    S[c] = __dsub_rn(a[c], delay[u][c]);  // y0 is a multiple of 4
+                    delay[u][c] = in[c];
                 }
                 const float fa = __fmul_rn(__double2float_rn(a[0]), 0.5f);
                 const float fb = __double2float_rn(a[1]);
                 const float fc = __fmul_rn(__double2float_rn(a[2]), 0.5f);
                 const float t = __fsub_rn(fa, fc);
                 const float r = __fsqrt_rn(__fadd_rn(__fmul_rn(t, t), __fmul_rn(fb, fb)));
-                eig[(size_t)y * w + x] = __fsub_rn(__fadd_rn(fa, fc), r);
+                if (x < w) eig[(size_t)y * w + x] = __fsub_rn(__fadd_rn(fa, fc), r);
             }
+            issue(y + BOX_R);  // refill the slot just consumed
         }
-#pragma unroll
-        for (int u = 0; u < BOX_U; u++)
-#pragma unroll
-            for (int c = 0; c < 3; c++) cur[u][c] = nxt[u][c];
     }
 }
 

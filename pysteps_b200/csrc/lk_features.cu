@@ -216,6 +216,85 @@ __global__ void __launch_bounds__(32) select_kernel(const SelectParams p) {
     if (lane == 0) *p.out_count = accepted;
 }
 
+// Same selection with the cell grid in SHARED memory: every cell is one 32-bit word,
+// [1:0] = count (<= 3), then 3 x (5-bit x, 5-bit y) offsets inside the cell.  A cell of side
+// round(minDistance) can hold at most two corners that are minDistance apart, so three slots
+// are enough.  2048^2 at minDistance 10 is 205 x 205 cells = 168 KB: the whole grid stays on
+// chip and a candidate test costs nine shared-memory loads instead of ~20 dependent global
+// loads.
+__global__ void __launch_bounds__(32) select_smem_kernel(const SelectParams p) {
+    extern __shared__ unsigned cells[];
+    const int lane = threadIdx.x;
+    const int ncell = p.gw * p.gh;
+    for (int i = lane; i < ncell; i += 32) cells[i] = 0u;
+    __syncwarp();
+    const unsigned ncand = min(p.state[1], p.cap);
+    const float md2 = p.min_distance * p.min_distance;
+    int accepted = 0;
+    const bool limited = p.max_corners > 0;
+    for (unsigned basei = 0; basei < ncand; basei += 32) {
+        const unsigned ci = basei + lane;
+        bool ok = ci < ncand;
+        int x = 0, y = 0;
+        if (ok) {
+            const unsigned addr = (unsigned)(p.keys[ci] & 0xffffffffull);
+            y = addr / p.w;
+            x = addr - y * p.w;
+        }
+        const int xc = x / p.cell, yc = y / p.cell;
+        if (ok) {
+            const int x1 = max(0, xc - 1), y1 = max(0, yc - 1);
+            const int x2 = min(p.gw - 1, xc + 1), y2 = min(p.gh - 1, yc + 1);
+            for (int yy = y1; yy <= y2; yy++)
+                for (int xx = x1; xx <= x2; xx++) {
+                    const unsigned wd = cells[yy * p.gw + xx];
+                    const int cnt = wd & 3u;
+                    for (int q = 0; q < cnt; q++) {
+                        const unsigned f = (wd >> (2 + 10 * q)) & 0x3ffu;
+                        const float dx = (float)(x - (xx * p.cell + (int)(f & 31u)));
+                        const float dy = (float)(y - (yy * p.cell + (int)(f >> 5)));
+                        if (dx * dx + dy * dy < md2) ok = false;
+                    }
+                }
+        }
+        for (int i = 0; i < 32; i++) {
+            const bool oki = __shfl_sync(0xffffffffu, ok, i);
+            const int xi = __shfl_sync(0xffffffffu, x, i), yi = __shfl_sync(0xffffffffu, y, i);
+            if (oki && lane > i && ok) {
+                const float dx = (float)(x - xi), dy = (float)(y - yi);
+                if (dx * dx + dy * dy < md2) ok = false;
+            }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, ok);
+        const int rank = __popc(bal & ((1u << lane) - 1u));
+        const bool take = ok && (!limited || accepted + rank < p.max_corners);
+        if (take) {
+            const int o = accepted + rank;
+            p.out_xy[2 * o] = (float)x;
+            p.out_xy[2 * o + 1] = (float)y;
+        }
+        // insert in batch order; lanes sharing a cell must not race on its word
+        unsigned todo = __ballot_sync(0xffffffffu, take);
+        while (todo) {
+            const int i = __ffs(todo) - 1;
+            todo &= todo - 1;
+            if (lane == i) {
+                const int c = yc * p.gw + xc;
+                const unsigned wd = cells[c];
+                const unsigned cnt = wd & 3u;
+                if (cnt < 3u) {
+                    const unsigned f = (unsigned)(x - xc * p.cell) | ((unsigned)(y - yc * p.cell) << 5);
+                    cells[c] = (wd & ~3u) | (f << (2 + 10 * cnt)) | (cnt + 1u);
+                }
+            }
+            __syncwarp();
+        }
+        accepted += __popc(bal);
+        if (limited && accepted >= p.max_corners) { accepted = p.max_corners; break; }
+    }
+    if (lane == 0) *p.out_count = accepted;
+}
+
 }  // namespace
 
 // eig (m,n) float32, valid (m,n) uint8 or NULL -> corners (x, y) float32, count.
@@ -277,6 +356,15 @@ extern "C" int b200_good_features(const float *eig, const uint8_t *valid, int m,
     sp.gw = (n + sp.cell - 1) / sp.cell;
     sp.gh = (m + sp.cell - 1) / sp.cell;
     const size_t ncell = (size_t)sp.gw * sp.gh;
+    sp.out_xy = out_xy;
+    sp.out_count = out_count;
+    if (min_distance >= 1.0 && sp.cell <= 32 && ncell * sizeof(unsigned) <= 200 * 1024) {
+        const size_t smem = ncell * sizeof(unsigned);
+        B200_CUDA(cudaFuncSetAttribute(select_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        select_smem_kernel<<<1, 32, smem, s>>>(sp);
+        B200_LAUNCH_CHECK();
+        return 0;
+    }
     B200_CUDA(cellc.alloc(sizeof(int) * ncell, s));
     B200_CUDA(cellp.alloc(sizeof(short2) * ncell * CELL_CAP, s));
     B200_CUDA(cudaMemsetAsync(cellc.p, 0, sizeof(int) * ncell, s));

@@ -18,7 +18,7 @@
 namespace {
 
 constexpr int LK_MAX_LEVELS = 8;
-constexpr int LK_THREADS = 256;
+constexpr int LK_THREADS = 128;  // 9 CTAs/SM: 1000 features fit in one wave
 constexpr int W_BITS = 14;
 
 struct LKParams {
