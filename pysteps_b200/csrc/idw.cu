@@ -67,22 +67,52 @@ __device__ __forceinline__ double np_sum(const double (&w)[K], int k) {
 // without touching the sorted list.  Order of examination is irrelevant for the result:
 // the list is ordered by (squared distance, index), i.e. equal distances resolve to the
 // lower index exactly as cKDTree-free exhaustive scanning in index order would.
+// Batcher odd-even merge sorting networks (generated, verified exhaustively with the 0-1
+// principle): compile-time comparator lists, so the sorted list never leaves registers.
+__device__ constexpr int NET20[103][2] = {{0,1},{2,3},{4,5},{6,7},{8,9},{10,11},{12,13},{14,15},{16,17},{18,19},{0,2},{1,3},{4,6},{5,7},{8,10},{9,11},{12,14},{13,15},{16,18},{17,19},{1,2},{5,6},{9,10},{13,14},{17,18},{0,4},{1,5},{2,6},{3,7},{8,12},{9,13},{10,14},{11,15},{2,4},{3,5},{10,12},{11,13},{1,2},{3,4},{5,6},{9,10},{11,12},{13,14},{17,18},{0,8},{1,9},{2,10},{3,11},{4,12},{5,13},{6,14},{7,15},{4,8},{5,9},{6,10},{7,11},{2,4},{3,5},{6,8},{7,9},{10,12},{11,13},{1,2},{3,4},{5,6},{7,8},{9,10},{11,12},{13,14},{17,18},{0,16},{1,17},{2,18},{3,19},{8,16},{9,17},{10,18},{11,19},{4,8},{5,9},{6,10},{7,11},{12,16},{13,17},{14,18},{15,19},{2,4},{3,5},{6,8},{7,9},{10,12},{11,13},{14,16},{15,17},{1,2},{3,4},{5,6},{7,8},{9,10},{11,12},{13,14},{15,16},{17,18}};
+__device__ constexpr int NET8[19][2] = {{0,1},{2,3},{4,5},{6,7},{0,2},{1,3},{4,6},{5,7},{1,2},{5,6},{0,4},{1,5},{2,6},{3,7},{2,4},{3,5},{1,2},{3,4},{5,6}};
+template <int K> __device__ __forceinline__ constexpr int net_size() { return K == 20 ? 103 : (K == 8 ? 19 : 0); }
+template <int K> __device__ __forceinline__ constexpr int net_a(int c) { return K == 20 ? NET20[c < 103 ? c : 0][0] : (K == 8 ? NET8[c < 19 ? c : 0][0] : 0); }
+template <int K> __device__ __forceinline__ constexpr int net_b(int c) { return K == 20 ? NET20[c < 103 ? c : 0][1] : (K == 8 ? NET8[c < 19 ? c : 0][1] : 0); }
+
+__device__ __forceinline__ bool key_less(unsigned long long da, int ia, unsigned long long db, int ib) {
+    return da < db || (da == db && ia < ib);
+}
+
 // Sorted list of the k best (squared distance, index) pairs of one pixel.
-// EXACT = true: k == K, the list lives in registers (every index is a compile-time constant)
-// and an insertion is branch free: K independent "key < entry" predicates, then each slot
-// takes its left neighbour, the key, or keeps its value.  Squared distances are >= 0, so
-// their bit patterns order like the doubles; (bits, index) is compared as one integer key.
-// EXACT = false (k < K: fewer vectors than neighbours, or an unusual k): same algorithm with
-// a runtime length; the arrays may live in local memory -- a rare, small-problem path.
+// EXACT = true: k == K, the list lives in registers (every index is a compile-time constant).
+// The first K candidates are loaded as they come and sorted once by a sorting network; every
+// later candidate is tested against the current worst and, if better, inserted branch free:
+// K independent "key < entry" predicates, then each slot takes its left neighbour, the key,
+// or keeps its value.  Squared distances are >= 0, so their bit patterns order like the
+// doubles; (bits, index) is compared as one integer key.
+// EXACT = false (k < K: fewer vectors than neighbours, or an unusual k): insertion only, with
+// a runtime length -- a rare, small-problem path.
 template <int K, bool EXACT>
 __device__ __forceinline__ void topk_scan(const double2 *__restrict__ spt, const int *__restrict__ sidx,
-                                          int ncand, double qx, double qy, int k,
+                                          int ncand, double qx, double qy, int k, bool first,
                                           unsigned long long (&bd)[K], int (&bi)[K]) {
-    for (int t = 0; t < ncand; t++) {
+    auto dist2 = [&](int t) -> unsigned long long {
         const double2 s = spt[t];
         const double dx = __dsub_rn(s.x, qx), dy = __dsub_rn(s.y, qy);
-        const unsigned long long d2 =
-            (unsigned long long)__double_as_longlong(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+        return (unsigned long long)__double_as_longlong(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+    };
+    int t0 = 0;
+    if (EXACT && first && ncand >= K) {
+#pragma unroll
+        for (int q = 0; q < K; q++) { bd[q] = dist2(q); bi[q] = sidx[q]; }
+#pragma unroll
+        for (int c = 0; c < net_size<K>(); c++) {
+            const int a = net_a<K>(c), b = net_b<K>(c);
+            if (key_less(bd[b], bi[b], bd[a], bi[a])) {
+                const unsigned long long td = bd[a]; bd[a] = bd[b]; bd[b] = td;
+                const int ti = bi[a]; bi[a] = bi[b]; bi[b] = ti;
+            }
+        }
+        t0 = K;
+    }
+    for (int t = t0; t < ncand; t++) {
+        const unsigned long long d2 = dist2(t);
         const int last = EXACT ? K - 1 : k - 1;
         unsigned long long wd = bd[K - 1];
         int wi = bi[K - 1];
@@ -92,10 +122,10 @@ __device__ __forceinline__ void topk_scan(const double2 *__restrict__ spt, const
                 if (q == last) { wd = bd[q]; wi = bi[q]; }
         }
         const int id = sidx[t];
-        if (d2 < wd || (d2 == wd && id < wi)) {
+        if (key_less(d2, id, wd, wi)) {
             bool lt[K];
 #pragma unroll
-            for (int q = 0; q < K; q++) lt[q] = d2 < bd[q] || (d2 == bd[q] && id < bi[q]);
+            for (int q = 0; q < K; q++) lt[q] = key_less(d2, id, bd[q], bi[q]);
 #pragma unroll
             for (int q = K - 1; q >= 1; q--) {
                 if (EXACT || q <= last) {
@@ -213,7 +243,7 @@ __global__ void __launch_bounds__(IDW_THREADS) idw_kernel(const IDWParams p) {
             }
         }
         __syncthreads();
-        if (active) topk_scan<K, EXACT>(spt, sidx, cnt, qx, qy, k, bd, bi);
+        if (active) topk_scan<K, EXACT>(spt, sidx, cnt, qx, qy, k, r == 0, bd, bi);
     }
     if (!active || k < 1) return;
     double w[K];

@@ -327,7 +327,7 @@ cov_rowsum_kernel(const uint8_t *__restrict__ q, int h, int w, double *__restric
 // chain: they are streamed BOX_R rows ahead into a shared-memory ring with cp.async
 // (LDGSTS), one commit group per row, so a single resident warp per SM still covers the
 // DRAM latency and the loop runs at the speed of its two dependent FP64 adds.
-constexpr int BOX_R = 48;  // rows in flight per warp: 48 * 3 planes * 32 columns * 8 B = 36 KB
+constexpr int BOX_R = 64;  // rows in flight per warp: 64 rows * 32 columns * 8 B = 16 KB
 
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -338,31 +338,27 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
 
+// grid = (ceil(w/32), 3): one warp per (32 columns, covariance plane), so the three running
+// sums of a column advance in parallel and a row step is ~10 instructions of one warp.
 __global__ void __launch_bounds__(32)
-box_eig_kernel(const double *__restrict__ rs, int h, int w, float *__restrict__ eig) {
-    __shared__ double ring_s[BOX_R][3][32];
+box_chain_kernel(const double *__restrict__ rs, int h, int w, float *__restrict__ box) {
+    __shared__ double ring_s[BOX_R][32];
     const int lane = threadIdx.x;
     const int x = blockIdx.x * 32 + lane;
     const int xc = min(x, w - 1);  // out-of-range lanes shadow the last column
     const size_t N = (size_t)h * w;
+    const double *__restrict__ src = rs + (size_t)blockIdx.y * N;
+    float *__restrict__ dst = box + (size_t)blockIdx.y * N;
     // rows -2, -1, 0, 1 (reflected): the initial sum and the first four leaving rows
-    double delay[4][3];
-    double S[3] = {0.0, 0.0, 0.0};
+    double delay[4];
+    double S = 0.0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const size_t i = (size_t)reflect101(k - 2, h) * w + xc;
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            delay[k][c] = rs[c * N + i];
-            S[c] = __dadd_rn(S[c], delay[k][c]);
-        }
+        delay[k] = src[(size_t)reflect101(k - 2, h) * w + xc];
+        S = __dadd_rn(S, delay[k]);
     }
     auto issue = [&](int y) {  // entering row of step y
-        if (y < h) {
-            const size_t i = (size_t)reflect101(y + 2, h) * w + xc;
-#pragma unroll
-            for (int c = 0; c < 3; c++) cp_async8(&ring_s[y % BOX_R][c][lane], rs + c * N + i);
-        }
+        if (y < h) cp_async8(&ring_s[y % BOX_R][lane], src + (size_t)reflect101(y + 2, h) * w + xc);
         cp_async_commit();  // one (possibly empty) group per row keeps the group count uniform
     };
     for (int y = 0; y < BOX_R; y++) issue(y);
@@ -372,24 +368,26 @@ box_eig_kernel(const double *__restrict__ rs, int h, int w, float *__restrict__ 
             const int y = y0 + u;
             cp_async_wait<BOX_R - 1>();  // the oldest outstanding row (y) has landed
             if (y < h) {
-                double in[3], a[3];
-#pragma unroll
-                for (int c = 0; c < 3; c++) in[c] = ring_s[y % BOX_R][c][lane];
-#pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    a[c] = __dadd_rn(S[c], in[c]);
-                    S[c] = __dsub_rn(a[c], delay[u][c]);  // y0 is a multiple of 4
-                    delay[u][c] = in[c];
-                }
-                const float fa = __fmul_rn(__double2float_rn(a[0]), 0.5f);
-                const float fb = __double2float_rn(a[1]);
-                const float fc = __fmul_rn(__double2float_rn(a[2]), 0.5f);
-                const float t = __fsub_rn(fa, fc);
-                const float r = __fsqrt_rn(__fadd_rn(__fmul_rn(t, t), __fmul_rn(fb, fb)));
-                if (x < w) eig[(size_t)y * w + x] = __fsub_rn(__fadd_rn(fa, fc), r);
+                const double in = ring_s[y % BOX_R][lane];
+                const double a = __dadd_rn(S, in);
+                S = __dsub_rn(a, delay[u]);  // y0 is a multiple of 4
+                delay[u] = in;
+                if (x < w) dst[(size_t)y * w + x] = __double2float_rn(a);
             }
             issue(y + BOX_R);  // refill the slot just consumed
         }
+    }
+}
+
+// eig = (a + c) - sqrt((a - c)^2 + b^2) with a = xx/2, b = xy, c = yy/2, float32 as OpenCV
+__global__ void __launch_bounds__(256)
+eig_from_box_kernel(const float *__restrict__ box, size_t N, float *__restrict__ eig) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+        const float fa = __fmul_rn(box[i], 0.5f), fb = box[N + i], fc = __fmul_rn(box[2 * N + i], 0.5f);
+        const float t = __fsub_rn(fa, fc);
+        const float r = __fsqrt_rn(__fadd_rn(__fmul_rn(t, t), __fmul_rn(fb, fb)));
+        eig[i] = __fsub_rn(__fadd_rn(fa, fc), r);
     }
 }
 
@@ -467,11 +465,16 @@ extern "C" int b200_scharr_i16(const uint8_t *src, int h, int w, int16_t *dst, v
 extern "C" int b200_min_eig(const uint8_t *q, int m, int n, float *eig, void *stream) {
     B200_REQUIRE(q && eig && m >= 1 && n >= 1, "bad arguments");
     cudaStream_t s = (cudaStream_t)stream;
-    b200::Scratch rs;
-    B200_CUDA(rs.alloc(sizeof(double) * 3 * (size_t)m * n, s));
+    b200::Scratch rs, box;
+    const size_t N = (size_t)m * n;
+    B200_CUDA(rs.alloc(sizeof(double) * 3 * N, s));
+    B200_CUDA(box.alloc(sizeof(float) * 3 * N, s));
     cov_rowsum_kernel<<<grid2d(m, n), dim3(TX, TY), 0, s>>>(q, m, n, (double *)rs.p);
     B200_LAUNCH_CHECK();
-    box_eig_kernel<<<b200::ceil_div(n, 32), 32, 0, s>>>((const double *)rs.p, m, n, eig);
+    box_chain_kernel<<<dim3(b200::ceil_div(n, 32), 3), 32, 0, s>>>((const double *)rs.p, m, n, (float *)box.p);
+    B200_LAUNCH_CHECK();
+    const int blocks = (int)std::min<size_t>((N + 255) / 256, (size_t)b200::num_sms() * 16);
+    eig_from_box_kernel<<<blocks, 256, 0, s>>>((const float *)box.p, N, eig);
     B200_LAUNCH_CHECK();
     return 0;
 }
