@@ -145,6 +145,7 @@ __global__ void __launch_bounds__(IDW_THREADS) idw_kernel(const IDWParams p) {
     __shared__ int sidx[IDW_CHUNK];
     __shared__ int hist[IDW_BINS];   // counts, then exclusive offsets
     __shared__ int fill[IDW_BINS];
+    __shared__ unsigned char sbin[IDW_CHUNK];  // bin of the first IDW_CHUNK vectors
     __shared__ int s_bmax, s_total;
     const int npts = p.npts_dev ? min(*p.npts_dev, p.npts_cap) : p.npts_cap;
     const int k = min(min(p.k, npts), K);
@@ -167,14 +168,20 @@ __global__ void __launch_bounds__(IDW_THREADS) idw_kernel(const IDWParams p) {
     const double inv_binw = 1.0 / binw;
     for (int b = tid; b < IDW_BINS; b += IDW_THREADS) { hist[b] = 0; fill[b] = 0; }
     __syncthreads();
+    // The bin only has to be CONSERVATIVE (never below the true distance bin) and the same in
+    // both passes, so it is computed in float32 with 1e-5 slack instead of an FP64 sqrt.
+    const float inv_binw_f = (float)inv_binw * (1.0f + 1e-5f);
     auto bin_of = [&](int t) -> int {
         const double2 s = pts[t];
-        const double dx = s.x - cx, dy = s.y - cy;
-        // conservative: a vector is never put in a bin below its true distance (1e-9 slack)
-        const double d = sqrt(dx * dx + dy * dy) * inv_binw * (1.0 + 1e-9);
-        return d < (double)(IDW_BINS - 1) ? (int)d : IDW_BINS - 1;
+        const float dx = (float)(s.x - cx), dy = (float)(s.y - cy);
+        const float d = sqrtf(dx * dx + dy * dy) * inv_binw_f;
+        return d < (float)(IDW_BINS - 1) ? (int)d : IDW_BINS - 1;
     };
-    for (int t = tid; t < npts; t += IDW_THREADS) atomicAdd(&hist[bin_of(t)], 1);
+    for (int t = tid; t < npts; t += IDW_THREADS) {
+        const int b = bin_of(t);
+        if (t < IDW_CHUNK) sbin[t] = (unsigned char)b;
+        atomicAdd(&hist[b], 1);
+    }
     __syncthreads();
     if (tid < 32) {
         // exclusive prefix over the bins (8 per lane), bin of the k-th vector, search bound
@@ -226,7 +233,7 @@ __global__ void __launch_bounds__(IDW_THREADS) idw_kernel(const IDWParams p) {
         __syncthreads();
         if (sorted) {
             for (int t = tid; t < npts; t += IDW_THREADS) {
-                const int b = bin_of(t);
+                const int b = t < IDW_CHUNK ? (int)sbin[t] : bin_of(t);
                 if (b <= bmax) {
                     const int o = hist[b] + atomicAdd(&fill[b], 1);
                     spt[o] = pts[t];
@@ -250,7 +257,7 @@ __global__ void __launch_bounds__(IDW_THREADS) idw_kernel(const IDWParams p) {
 #pragma unroll
     for (int q = 0; q < K; q++) {
         double d = sqrt(__longlong_as_double((long long)bd[q]));  // exact Euclidean distance
-        d = __ddiv_rn(d, p.mean_res);           // interpolate.py:98
+        if (p.mean_res != 1.0) d = __ddiv_rn(d, p.mean_res);  // interpolate.py:98 (x / 1.0 == x)
         d = __dadd_rn(d, p.offset);             // :101
         const double pw = (p.power == 0.5) ? sqrt(d) : pow(d, p.power);
         w[q] = (q < k) ? __ddiv_rn(1.0, pw) : 0.0;  // :102

@@ -208,7 +208,8 @@ quantise_kernel(const double *__restrict__ img, const uint8_t *__restrict__ mask
     int set = 0;
     if (mode == 1) {
         bool dmask = msk;
-        if (dil > 0) {
+        const bool any_masked0 = stats[2] < (double)m * (double)n;
+        if (dil > 0 && any_masked0) {  // nothing masked: the buffered mask is clear everywhere
             const int r = dil / 2;
             for (int dy = -r; dy <= dil - 1 - r; dy++)
                 for (int dx = -r; dx <= dil - 1 - r; dx++) {

@@ -47,6 +47,10 @@ __device__ __forceinline__ int reflect101(int i, int L) {
 
 __device__ __forceinline__ int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
 
+// i / d for 0 <= i < 2^16 and 1 <= d <= 64 without an integer division (exact: the float
+// product is off by far less than the 0.5/d margin)
+__device__ __forceinline__ int div_small(int i, float inv_d) { return __float2int_rd(((float)i + 0.5f) * inv_d); }
+
 // bilinear fixed-point weights of a sub-pixel offset (a, b)
 __device__ __forceinline__ void make_weights(float a, float b, int &w00, int &w01, int &w10, int &w11) {
     w00 = __float2int_rn((1.f - a) * (1.f - b) * (float)(1 << W_BITS));
@@ -78,6 +82,8 @@ __global__ void __launch_bounds__(LK_THREADS) lk_track_kernel(const LKParams p) 
     float *red = TYp + ntl;                // 16 floats: chain results
     __shared__ float s_b[2];
 
+    const float inv_ww = 1.0f / (float)ww, inv_nchunk = nchunk > 0 ? 1.0f / (float)nchunk : 0.f,
+                inv_ntail = ntail > 0 ? 1.0f / (float)ntail : 0.f;
     const float half_x = (ww - 1) * 0.5f, half_y = (wh - 1) * 0.5f;
     const float FLT_SCALE = 1.f / (float)(1 << 20);
     float nx_out = 0.f, ny_out = 0.f;      // nextPts[ptidx] as carried between levels
@@ -105,22 +111,32 @@ __global__ void __launch_bounds__(LK_THREADS) lk_track_kernel(const LKParams p) 
 
         // ---- patch of I and its derivatives (data parallel) --------------------------------
         __syncthreads();
+        // window (incl. the +1 taps) fully inside the level: no border handling (the common case)
+        const bool inI = ix >= 0 && iy >= 0 && ix + ww < w && iy + wh < h;
         for (int i = tid; i < npx; i += LK_THREADS) {
-            const int y = i / ww, x = i - y * ww;
+            const int y = div_small(i, inv_ww), x = i - y * ww;
             const int yy = iy + y, xx = ix + x;
-            const int r0 = reflect101(yy, h), r1 = reflect101(yy + 1, h);
-            const int c0 = reflect101(xx, w), c1 = reflect101(xx + 1, w);
-            const int ival = descale(I[(size_t)r0 * w + c0] * w00 + I[(size_t)r0 * w + c1] * w01 +
-                                     I[(size_t)r1 * w + c0] * w10 + I[(size_t)r1 * w + c1] * w11, W_BITS - 5);
-            // derivative border is zero (BORDER_CONSTANT), not reflected
+            int v00, v01, v10, v11;
             short2 d00 = make_short2(0, 0), d01 = d00, d10 = d00, d11 = d00;
-            const bool y0in = yy >= 0 && yy < h, y1in = yy + 1 >= 0 && yy + 1 < h;
-            const bool x0in = xx >= 0 && xx < w, x1in = xx + 1 >= 0 && xx + 1 < w;
-            if (y0in && x0in) d00 = dI[(size_t)yy * w + xx];
-            if (y0in && x1in) d01 = dI[(size_t)yy * w + xx + 1];
-            if (y1in && x0in) d10 = dI[(size_t)(yy + 1) * w + xx];
-            if (y1in && x1in) d11 = dI[(size_t)(yy + 1) * w + xx + 1];
-            Iw[i] = (short)ival;
+            if (inI) {
+                const uint8_t *q0 = I + (size_t)yy * w + xx;
+                v00 = q0[0]; v01 = q0[1]; v10 = q0[w]; v11 = q0[w + 1];
+                const short2 *g0 = dI + (size_t)yy * w + xx;
+                d00 = g0[0]; d01 = g0[1]; d10 = g0[w]; d11 = g0[w + 1];
+            } else {
+                const int r0 = reflect101(yy, h), r1 = reflect101(yy + 1, h);
+                const int c0 = reflect101(xx, w), c1 = reflect101(xx + 1, w);
+                v00 = I[(size_t)r0 * w + c0]; v01 = I[(size_t)r0 * w + c1];
+                v10 = I[(size_t)r1 * w + c0]; v11 = I[(size_t)r1 * w + c1];
+                // derivative border is zero (BORDER_CONSTANT), not reflected
+                const bool y0in = yy >= 0 && yy < h, y1in = yy + 1 >= 0 && yy + 1 < h;
+                const bool x0in = xx >= 0 && xx < w, x1in = xx + 1 >= 0 && xx + 1 < w;
+                if (y0in && x0in) d00 = dI[(size_t)yy * w + xx];
+                if (y0in && x1in) d01 = dI[(size_t)yy * w + xx + 1];
+                if (y1in && x0in) d10 = dI[(size_t)(yy + 1) * w + xx];
+                if (y1in && x1in) d11 = dI[(size_t)(yy + 1) * w + xx + 1];
+            }
+            Iw[i] = (short)descale(v00 * w00 + v01 * w01 + v10 * w10 + v11 * w11, W_BITS - 5);
             Dx[i] = (short)descale(d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11, W_BITS);
             Dy[i] = (short)descale(d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11, W_BITS);
         }
@@ -176,22 +192,30 @@ __global__ void __launch_bounds__(LK_THREADS) lk_track_kernel(const LKParams p) 
             make_weights(nx - (float)jx, ny - (float)jy, w00, w01, w10, w11);
             // ---- mismatch J - I and its products with the derivatives (data parallel) --------
             __syncthreads();
+            const bool inJ = jx >= 0 && jy >= 0 && jx + ww < w && jy + wh < h;
             auto mismatch = [&](int y, int x) -> int {
-                const int r0 = reflect101(jy + y, h), r1 = reflect101(jy + y + 1, h);
-                const int c0 = reflect101(jx + x, w), c1 = reflect101(jx + x + 1, w);
-                const int jv = descale(J[(size_t)r0 * w + c0] * w00 + J[(size_t)r0 * w + c1] * w01 +
-                                       J[(size_t)r1 * w + c0] * w10 + J[(size_t)r1 * w + c1] * w11, W_BITS - 5);
+                int v00, v01, v10, v11;
+                if (inJ) {
+                    const uint8_t *q0 = J + (size_t)(jy + y) * w + (jx + x);
+                    v00 = q0[0]; v01 = q0[1]; v10 = q0[w]; v11 = q0[w + 1];
+                } else {
+                    const int r0 = reflect101(jy + y, h), r1 = reflect101(jy + y + 1, h);
+                    const int c0 = reflect101(jx + x, w), c1 = reflect101(jx + x + 1, w);
+                    v00 = J[(size_t)r0 * w + c0]; v01 = J[(size_t)r0 * w + c1];
+                    v10 = J[(size_t)r1 * w + c0]; v11 = J[(size_t)r1 * w + c1];
+                }
+                const int jv = descale(v00 * w00 + v01 * w01 + v10 * w10 + v11 * w11, W_BITS - 5);
                 return jv - (int)Iw[y * ww + x];
             };
             for (int i = tid; i < npair; i += LK_THREADS) {
-                const int q = i & 3, c = (i >> 2) % nchunk, y = (i >> 2) / nchunk;
+                const int q = i & 3, y = div_small(i >> 2, inv_nchunk), c = (i >> 2) - y * nchunk;
                 const int x0 = 8 * c + q, i0 = y * ww + x0;
                 const int d0 = mismatch(y, x0), d1 = mismatch(y, x0 + 4);
                 PX[i] = (float)(d0 * (int)Dx[i0] + d1 * (int)Dx[i0 + 4]);
                 PY[i] = (float)(d0 * (int)Dy[i0] + d1 * (int)Dy[i0 + 4]);
             }
             for (int i = tid; i < ntl; i += LK_THREADS) {
-                const int y = i / ntail, x = simd_w + (i - y * ntail);
+                const int y = div_small(i, inv_ntail), x = simd_w + (i - y * ntail);
                 const int d0 = mismatch(y, x);
                 TXp[i] = (float)(d0 * (int)Dx[y * ww + x]);
                 TYp[i] = (float)(d0 * (int)Dy[y * ww + x]);
