@@ -65,6 +65,7 @@ def make_inputs(seed, lk):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """nvidia-smi in loop mode (-lms 20) for the duration of the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -72,28 +73,33 @@ class ClockSampler:
     def __init__(self, index=0):
         self.index = index
         self.samples = []
-        self._stop = threading.Event()
-        self._t = threading.Thread(target=self._run, daemon=True)
-
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True,
-                                     text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.1)
+        self.proc = None
 
     def __enter__(self):
-        self._t.start()
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "20"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.25)  # let the first samples arrive before the timed region starts
+        except Exception:
+            self.proc = None
         return self
 
     def __exit__(self, *exc):
-        self._stop.set()
-        self._t.join(timeout=6)
+        if self.proc is None:
+            return
+        time.sleep(0.05)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        for line in (out or "").splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) >= 6:
+                self.samples.append(parts)
 
     def summary(self):
         if not self.samples:

@@ -232,12 +232,17 @@ __global__ void __launch_bounds__(32) select_smem_kernel(const SelectParams p) {
     const float md2 = p.min_distance * p.min_distance;
     int accepted = 0;
     const bool limited = p.max_corners > 0;
+    // software prefetch of the next batch's key hides the global-load latency of this
+    // single-warp kernel behind the current batch
+    unsigned long long key_next = lane < ncand ? p.keys[lane] : 0ull;
     for (unsigned basei = 0; basei < ncand; basei += 32) {
         const unsigned ci = basei + lane;
         bool ok = ci < ncand;
+        const unsigned long long key = key_next;
+        if (ci + 32 < ncand) key_next = p.keys[ci + 32];
         int x = 0, y = 0;
         if (ok) {
-            const unsigned addr = (unsigned)(p.keys[ci] & 0xffffffffull);
+            const unsigned addr = (unsigned)(key & 0xffffffffull);
             y = addr / p.w;
             x = addr - y * p.w;
         }
@@ -257,13 +262,17 @@ __global__ void __launch_bounds__(32) select_smem_kernel(const SelectParams p) {
                     }
                 }
         }
-        for (int i = 0; i < 32; i++) {
-            const bool oki = __shfl_sync(0xffffffffu, ok, i);
+        // order inside the batch: a still-valid earlier lane suppresses later lanes within
+        // minDistance.  Only lanes that are still valid need to be visited.
+        unsigned rem = __ballot_sync(0xffffffffu, ok);
+        while (rem) {
+            const int i = __ffs(rem) - 1;
             const int xi = __shfl_sync(0xffffffffu, x, i), yi = __shfl_sync(0xffffffffu, y, i);
-            if (oki && lane > i && ok) {
+            if (lane > i && ok) {
                 const float dx = (float)(x - xi), dy = (float)(y - yi);
                 if (dx * dx + dy * dy < md2) ok = false;
             }
+            rem = __ballot_sync(0xffffffffu, ok) & ~((2u << i) - 1u);  // valid lanes after i
         }
         const unsigned bal = __ballot_sync(0xffffffffu, ok);
         const int rank = __popc(bal & ((1u << lane) - 1u));
@@ -273,22 +282,38 @@ __global__ void __launch_bounds__(32) select_smem_kernel(const SelectParams p) {
             p.out_xy[2 * o] = (float)x;
             p.out_xy[2 * o + 1] = (float)y;
         }
-        // insert in batch order; lanes sharing a cell must not race on its word
-        unsigned todo = __ballot_sync(0xffffffffu, take);
-        while (todo) {
-            const int i = __ffs(todo) - 1;
-            todo &= todo - 1;
-            if (lane == i) {
-                const int c = yc * p.gw + xc;
-                const unsigned wd = cells[c];
-                const unsigned cnt = wd & 3u;
-                if (cnt < 3u) {
-                    const unsigned f = (unsigned)(x - xc * p.cell) | ((unsigned)(y - yc * p.cell) << 5);
-                    cells[c] = (wd & ~3u) | (f << (2 + 10 * cnt)) | (cnt + 1u);
+        // insert: lanes in different cells update their words concurrently; lanes sharing a
+        // cell (rare) are serialised by the lowest lane of the group, in batch order
+        const unsigned tmask = __ballot_sync(0xffffffffu, take);
+        const int c = yc * p.gw + xc;
+        if (take) {
+            const unsigned grp = __match_any_sync(tmask, c);
+            if (lane == __ffs(grp) - 1) {
+                unsigned wd = cells[c];
+                unsigned g = grp;
+                while (g) {
+                    const int j = __ffs(g) - 1;
+                    g &= g - 1;
+                    const int xj = __shfl_sync(grp, x, j), yj = __shfl_sync(grp, y, j);
+                    const unsigned cnt = wd & 3u;
+                    if (cnt < 3u) {
+                        const unsigned f = (unsigned)(xj - xc * p.cell) | ((unsigned)(yj - yc * p.cell) << 5);
+                        wd = (wd & ~3u) | (f << (2 + 10 * cnt)) | (cnt + 1u);
+                    }
+                }
+                cells[c] = wd;
+            } else {
+                // non-leader members only serve the leader's shuffles
+                unsigned g = grp;
+                while (g) {
+                    const int j = __ffs(g) - 1;
+                    g &= g - 1;
+                    __shfl_sync(grp, x, j);
+                    __shfl_sync(grp, y, j);
                 }
             }
-            __syncwarp();
         }
+        __syncwarp();
         accepted += __popc(bal);
         if (limited && accepted >= p.max_corners) { accepted = p.max_corners; break; }
     }

@@ -339,3 +339,35 @@ def test_full_size_recovers_translation(env):
     wet = fr[1] > 0
     assert abs(V[0][wet].mean() - 3.0) < 0.02 and abs(V[1][wet].mean() + 2.0) < 0.02
     assert np.percentile(np.abs(V[0] - 3.0), 99) < 0.2
+
+
+@pytest.mark.parametrize("shape,seed", [((40, 44), 3), ((64, 51), 4), ((120, 33), 5), ((257, 300), 6)])
+def test_small_and_ragged_frames_vs_oracle(env, shape, seed):
+    """Frames smaller than the 50x50 tracking window (single pyramid level, windows that hang
+    over the border), odd sizes, three frames: sparse vectors identical, dense field <= 1e-12."""
+    from oracle import lucaskanade as ora
+    from pysteps_b200 import _synthetic as syn
+    from pysteps_b200.motion import get_method
+    lk = get_method("lk")
+    fr = syn.rain_frames(shape[0], shape[1], 3, seed, dx=2, dy=-1)
+    sxy, suv = lk(fr, dense=False)
+    oxy, ouv = ora.dense_lucaskanade(fr, dense=False)
+    assert np.array_equal(sxy, oxy) and np.array_equal(suv, ouv)
+    V = lk(fr)
+    Vo = ora.dense_lucaskanade(fr)
+    assert V.shape == Vo.shape and np.abs(V - Vo).max() <= 1e-12
+
+
+def test_kwargs_variants_vs_oracle(env):
+    """Non-default lk / fd / interp kwargs flow through to the kernels like in the reference."""
+    from oracle import lucaskanade as ora
+    from pysteps_b200 import _synthetic as syn
+    from pysteps_b200.motion import get_method
+    lk = get_method("lk")
+    fr = syn.rain_frames(200, 220, 2, 8)
+    for kw in (dict(lk_kwargs=dict(winsize=(21, 21), nr_levels=2), fd_kwargs=dict(max_corners=150, min_distance=6)),
+               dict(fd_kwargs=dict(quality_level=0.05, buffer_mask=0), interp_kwargs=dict(k=8, power=1.5)),
+               dict(size_opening=0, decl_scale=1, k_outlier=10, nr_std_outlier=2)):
+        V = lk(fr, **kw)
+        Vo = ora.dense_lucaskanade(fr, **kw)
+        assert np.abs(V - Vo).max() <= 1e-11, kw
