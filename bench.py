@@ -38,6 +38,25 @@ M = N_ = 2048
 T_LEAD = 12
 METRIC = "Mpix/s advected (2048^2 frame, 12 leadtimes)"
 UNIT = "Mpix/s"
+MOTION = "lk"
+SCALING = "weak"
+
+# BASELINE.json configs.  The default (config[1]) is what `metric` is quoted on; the others are
+# optional extra measurements (python bench.py --workload ...).
+WORKLOADS = {
+    "lk_sl12_2048": dict(m=2048, n=2048, T=12, motion="lk", scaling="weak",
+                         metric="Mpix/s advected (2048^2 frame, 12 leadtimes)"),
+    "vet_sl12_2048": dict(m=2048, n=2048, T=12, motion="vet", scaling="weak",
+                          metric="Mpix/s advected (2048^2 frame, 12 leadtimes, VET motion)"),
+    "composite4096": dict(m=4096, n=4096, T=24, motion="lk", scaling="strong",
+                          metric="Mpix/s advected (4096^2 composite, 24 leadtimes, row bands over GPUs)"),
+}
+
+
+def set_workload(name):
+    global M, N_, T_LEAD, METRIC, MOTION, SCALING
+    w = WORKLOADS[name]
+    M, N_, T_LEAD, METRIC, MOTION, SCALING = w["m"], w["n"], w["T"], w["metric"], w["motion"], w["scaling"]
 
 
 def have_lk():
@@ -49,7 +68,8 @@ def have_lk():
 
 
 def workload_name(lk):
-    return ("lk_dense+semilagrangian_T12_2048x2048" if lk else "semilagrangian_T12_2048x2048")
+    mot = {"lk": "lk_dense", "vet": "vet"}[MOTION] if lk else "given_field"
+    return f"{mot}+semilagrangian_T{T_LEAD}_{M}x{N_}" + ("_rowbands" if SCALING == "strong" else "")
 
 
 def make_inputs(seed, lk):
@@ -117,7 +137,10 @@ class ClockSampler:
 def cpu_step(frames, precip, V, lk):
     """The oracle port of one step on host cores."""
     from oracle import semilagrangian as ora
-    if lk:
+    if lk and MOTION == "vet":
+        from oracle import vet as ora_vet
+        V = ora_vet.vet(frames, verbose=False)
+    elif lk:
         from oracle import lucaskanade as ora_lk
         V = ora_lk.dense_lucaskanade(frames)
     return ora.extrapolate(precip, V, T_LEAD)
@@ -194,7 +217,10 @@ def run_ours(args):
     motion = None
     if lk:
         from pysteps_b200 import motion as b200_motion
-        motion = b200_motion.get_method("lk")
+        motion = b200_motion.get_method(MOTION)
+        if MOTION == "vet":
+            _vet = motion
+            motion = lambda fr: _vet(fr.cpu().numpy() if torch.is_tensor(fr) else fr, verbose=False)  # noqa: E731
 
     frames_h, precip_h, V_h = make_inputs(rank, lk)
     # pinned host buffers for the e2e leg
@@ -207,17 +233,23 @@ def run_ours(args):
     V_d = torch.from_numpy(V_h).cuda()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
+    # strong scaling (one composite): every rank owns a band of output rows, inputs replicated
+    band = _shard.row_band(M, world, rank) if SCALING == "strong" else None
+    ekw = {} if band is None else {"b200_rows": band}
+
     def step_device():
         """inputs resident in HBM; results stay in HBM."""
         if lk:
             if rank == 0:
                 Vd = motion(frames_d)
+                if not torch.is_tensor(Vd):
+                    Vd = torch.from_numpy(np.ascontiguousarray(Vd)).cuda()
             else:
                 Vd = torch.empty((2, M, N_), dtype=torch.float64, device="cuda")
         else:
             Vd = V_d
         Vd = _shard.broadcast_field(Vd, src=0)  # the only collective (NCCL over NVLink)
-        return extrap(precip_d, Vd, T_LEAD)
+        return extrap(precip_d, Vd, T_LEAD, **ekw)
 
     def step_host():
         """public NumPy API: H2D of inputs and D2H of the result inside."""
@@ -230,7 +262,7 @@ def run_ours(args):
                 Vh = Vd.cpu().numpy()
         else:
             Vh = V_h
-        return extrap(precip_h, Vh, T_LEAD)
+        return extrap(precip_h, Vh, T_LEAD, **ekw)
 
     def barrier():
         if world > 1:
@@ -256,7 +288,8 @@ def run_ours(args):
     dev_ms = sum(s.elapsed_time(e) for s, e in ev)
     tr = trace.summary()
     dev_ms = _shard.max_over_ranks(dev_ms, device="cuda")
-    value = world * args.steps * T_LEAD * M * N_ / (dev_ms * 1e-3) / 1e6
+    nfields = world if SCALING == "weak" else 1
+    value = nfields * args.steps * T_LEAD * M * N_ / (dev_ms * 1e-3) / 1e6
 
     # ---- end-to-end timing (host buffers) --------------------------------------------
     for _ in range(max(1, args.warmup // 2)):
@@ -268,7 +301,7 @@ def run_ours(args):
     barrier()
     e2e_s = time.perf_counter() - t0
     e2e_s = _shard.max_over_ranks(e2e_s, device="cuda")
-    e2e_val = world * args.steps * T_LEAD * M * N_ / e2e_s / 1e6
+    e2e_val = nfields * args.steps * T_LEAD * M * N_ / e2e_s / 1e6
     # LK: frames up, field down, field up again for the extrapolator (plugin API is NumPy)
     h2d = precip_h.nbytes + (frames_h.nbytes + 2 * M * N_ * 8 if lk else V_h.nbytes)
     d2h = out.nbytes + (2 * M * N_ * 8 if lk else 0)
@@ -285,7 +318,8 @@ def run_ours(args):
         k_ms = tr.get("b200_sl_extrapolate", [])
         k_avg = sum(k_ms) / len(k_ms) if k_ms else float("nan")
         vbytes = 8 if lk else 4  # LK returns float64 fields, synthetic V is float32
-        alg_bytes = M * N_ * (2 * vbytes + 4 + 4 * T_LEAD)
+        rows_here = M if band is None else band[1] - band[0]
+        alg_bytes = M * N_ * (2 * vbytes + 4) + rows_here * N_ * 4 * T_LEAD
         achieved = alg_bytes / (k_avg * 1e-3) / 1e9
         traffic = None
         try:
@@ -300,12 +334,14 @@ def run_ours(args):
         cpu = cpu_baseline(frames_h, precip_h, V_h, have_lk_oracle()) if not args.no_cpu else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "higher_is_better": True, "scaling": SCALING, "vs_baseline": None,
                 "dtype": "f64 (trajectories, motion field, IDW); f32 precip in/out; u8/i16/f32 "
                          "OpenCV-exact LK stages", "data": "synthetic",
                 "config": {"workload": workload_name(lk), "frame": [M, N_], "leadtimes": T_LEAD,
-                           "fields_per_gpu": 1, "l2": "flushed between timed steps (256 MB fill)",
-                           "parallelism": f"1 field per GPU x{world}, NCCL broadcast of the motion field"},
+                           "fields_per_gpu": 1 if SCALING == "weak" else round(1.0 / world, 4), "l2": "flushed between timed steps (256 MB fill)",
+                           "parallelism": (f"1 field per GPU x{world}" if SCALING == "weak" else
+                                           f"output row bands over {world} GPU(s), inputs replicated")
+                           + ", NCCL broadcast of the motion field"},
                 "clocks": clocks.summary(),
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / args.steps},
@@ -324,7 +360,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="lk_sl12_2048", choices=sorted(WORKLOADS))
     args = ap.parse_args()
+    set_workload(args.workload)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return run_reference(args)

@@ -78,6 +78,19 @@ int b200_sl_extrapolate(const void *precip, const void *velocity,
                         int velocity_layout, int precip_dtype, int m, int n, void *out,
                         double *disp_out, void *stream);
 
+/* Same for the output rows [row_begin, row_begin + row_count) only: precip, velocity and
+ * xy_coords are full (m,n) frames, while disp_prev / out / disp_out are band shaped
+ * ((2,row_count,n), (T,row_count,n), (2,row_count,n)).  A pixel's trajectory reads the fields
+ * anywhere but writes only its own pixel, so a frame is partitioned over GPUs by output
+ * bands with replicated inputs and no halo exchange (SURVEY.md section 8e, config[4]). */
+int b200_sl_extrapolate_rows(const void *precip, const void *velocity,
+                             const double *xy_coords, const double *disp_prev,
+                             const double *tdiff, int T, double vel_timestep,
+                             int n_iter, double outval, int mode, int velocity_dtype,
+                             int velocity_layout, int precip_dtype, int m, int n,
+                             int row_begin, int row_count, void *out, double *disp_out,
+                             void *stream);
+
 /* planar (2,m,n) -> interleaved (m,n,2) copy of an advection field, so that a
  * caller reusing one field for many calls pays the re-layout once
  * (b200_sl_extrapolate does it internally for B200_LAYOUT_PLANAR). */

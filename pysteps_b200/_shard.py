@@ -11,6 +11,14 @@ def member_indices(n_members, world_size, rank):
     return list(range(rank, n_members, world_size))
 
 
+def row_band(m, world_size, rank):
+    """Rows [r0, r1) of an m-row composite owned by `rank` (even split, remainder to the first
+    ranks).  Every output pixel depends on the inputs only, so bands need no halo exchange."""
+    base, rem = divmod(m, world_size)
+    r0 = rank * base + min(rank, rem)
+    return r0, r0 + base + (1 if rank < rem else 0)
+
+
 def broadcast_field(field, src=0, shape=None, dtype=torch.float64, device=None):
     """Broadcast the (2,m,n) motion field computed on `src` to every rank.  Ranks other than
     `src` may pass None (a buffer of `shape` is allocated).  No-op without a process group."""

@@ -33,6 +33,7 @@ struct SLParams {
     double *vinc_out;       // (2,m,n) or null
     void *out;              // (T,m,n) planes of this chunk
     int m, n, T, n_iter, ti_offset, init_mode, mode, has_prev, vel_f32;
+    int row0, rows;         // output band [row0, row0 + rows): band-shaped out / disp arrays
     double vts, td0, cval;
     double scale[SL_MAX_T];  // td / vel_timestep per leadtime
 };
@@ -193,12 +194,15 @@ template <typename F, bool NITER1>
 __global__ void __launch_bounds__(SL_BX *SL_BY)
 sl_multistep_kernel(const __grid_constant__ SLParams p) {
     const int x = blockIdx.x * SL_BX + threadIdx.x;
-    const int y = blockIdx.y * SL_BY + threadIdx.y;
-    if (x >= p.n || y >= p.m) return;
+    const int yl = blockIdx.y * SL_BY + threadIdx.y;  // row inside the band
+    if (x >= p.n || yl >= p.rows) return;
+    const int y = p.row0 + yl;
     const int m = p.m, n = p.n;
     const int ymax = m - 2, xmax = n - 2;  // largest interior floor index (negative: none)
-    const size_t N = (size_t)m * n;
-    const int idx = y * n + x;
+    const size_t N = (size_t)p.rows * n;   // plane stride of the band-shaped arrays
+    const size_t NF = (size_t)m * n;       // plane stride of the full-frame arrays
+    const int idx = yl * n + x;            // pixel index inside the band
+    const int gidx = y * n + x;            // pixel index inside the full frame
     const double2 *__restrict__ Vi = (const double2 *)p.Vi;
     const double *__restrict__ P = (const double *)p.precip;
     F *__restrict__ out = (F *)p.out + idx;
@@ -210,8 +214,8 @@ sl_multistep_kernel(const __grid_constant__ SLParams p) {
 
     double gx, gy;  // xy_coords of this pixel (:174-179)
     if (p.xy) {
-        gx = p.xy[idx];
-        gy = p.xy[N + idx];
+        gx = p.xy[gidx];
+        gy = p.xy[NF + gidx];
     } else {
         gx = (double)x;
         gy = (double)y;
@@ -221,7 +225,7 @@ sl_multistep_kernel(const __grid_constant__ SLParams p) {
     if (p.init_mode == SL_INIT_FRESH) {
         // :201-203  displacement = 0 ; velocity_inc = V * tdiff[0] / vel_timestep
         dx = 0.0; dy = 0.0;
-        const double2 v = Vi[idx];
+        const double2 v = Vi[gidx];
         ux = __ddiv_rn(__dmul_rn(v.x, p.td0), p.vts);
         uy = __ddiv_rn(__dmul_rn(v.y, p.td0), p.vts);
     } else if (p.init_mode == SL_INIT_PREV) {
@@ -326,8 +330,10 @@ interleave_kernel(const F *__restrict__ V, F2 *__restrict__ Vi, size_t N) {
 template <typename FV, typename F>
 int sl_run(const void *precip, const void *velocity, const double *xy, const double *disp_prev,
            const double *tdiff, int T, double vts, int n_iter, double outval, int mode,
-           int layout, int m, int n, void *out, double *disp_out, cudaStream_t stream) {
-    const size_t N = (size_t)m * n;
+           int layout, int m, int n, int row0, int rows, void *out, double *disp_out,
+           cudaStream_t stream) {
+    const size_t N = (size_t)m * n;          // full frame (inputs)
+    const size_t NB = (size_t)rows * n;      // output band
     b200::Scratch vi, pw, st_disp, st_vinc;
     const int sblocks = (int)std::min<size_t>((N + 255) / 256, (size_t)b200::num_sms() * 16);
     // widen the fields to float64 once (exact), so the trajectory loop issues no conversions
@@ -348,11 +354,11 @@ int sl_run(const void *precip, const void *velocity, const double *xy, const dou
     }
     const int nchunks = (T + SL_MAX_T - 1) / SL_MAX_T;
     if (nchunks > 1) {
-        B200_CUDA(st_disp.alloc(2 * N * sizeof(double), stream));
-        B200_CUDA(st_vinc.alloc(2 * N * sizeof(double), stream));
+        B200_CUDA(st_disp.alloc(2 * NB * sizeof(double), stream));
+        B200_CUDA(st_vinc.alloc(2 * NB * sizeof(double), stream));
     }
     dim3 block(SL_BX, SL_BY);
-    dim3 grid(b200::ceil_div(n, SL_BX), b200::ceil_div(m, SL_BY));
+    dim3 grid(b200::ceil_div(n, SL_BX), b200::ceil_div(rows, SL_BY));
     for (int c = 0; c < nchunks; c++) {
         SLParams p;
         memset(&p, 0, sizeof(p));
@@ -360,6 +366,7 @@ int sl_run(const void *precip, const void *velocity, const double *xy, const dou
         p.precip = p_ptr;
         p.xy = xy;
         p.m = m; p.n = n;
+        p.row0 = row0; p.rows = rows;
         p.n_iter = n_iter;
         p.mode = mode;
         p.vts = vts;
@@ -381,7 +388,7 @@ int sl_run(const void *precip, const void *velocity, const double *xy, const dou
         const bool last = (c == nchunks - 1);
         p.disp_out = last ? disp_out : (double *)st_disp.p;
         p.vinc_out = last ? nullptr : (double *)st_vinc.p;
-        p.out = precip ? (void *)((F *)out + (size_t)p.ti_offset * N) : nullptr;
+        p.out = precip ? (void *)((F *)out + (size_t)p.ti_offset * NB) : nullptr;
         if (n_iter == 1)
             sl_multistep_kernel<F, true><<<grid, block, 0, stream>>>(p);
         else
@@ -393,12 +400,13 @@ int sl_run(const void *precip, const void *velocity, const double *xy, const dou
 
 }  // namespace
 
-extern "C" int b200_sl_extrapolate(const void *precip, const void *velocity,
-                                   const double *xy_coords, const double *disp_prev,
-                                   const double *tdiff, int T, double vel_timestep, int n_iter,
-                                   double outval, int mode, int velocity_dtype, int velocity_layout,
-                                   int precip_dtype, int m, int n, void *out, double *disp_out,
-                                   void *stream) {
+extern "C" int b200_sl_extrapolate_rows(const void *precip, const void *velocity,
+                                        const double *xy_coords, const double *disp_prev,
+                                        const double *tdiff, int T, double vel_timestep, int n_iter,
+                                        double outval, int mode, int velocity_dtype, int velocity_layout,
+                                        int precip_dtype, int m, int n, int row_begin, int row_count,
+                                        void *out, double *disp_out, void *stream) {
+    B200_REQUIRE(row_begin >= 0 && row_count >= 1 && row_begin + row_count <= m, "row band out of range");
     B200_REQUIRE(velocity_layout == B200_LAYOUT_PLANAR || velocity_layout == B200_LAYOUT_INTERLEAVED,
                  "unknown velocity layout");
     B200_REQUIRE(velocity != nullptr, "velocity is NULL");
@@ -411,7 +419,7 @@ extern "C" int b200_sl_extrapolate(const void *precip, const void *velocity,
     cudaStream_t s = (cudaStream_t)stream;
 #define SL_DISPATCH(FV, FP)                                                                  \
     return sl_run<FV, FP>(precip, velocity, xy_coords, disp_prev, tdiff, T, vel_timestep, n_iter, \
-                          outval, mode, velocity_layout, m, n, out, disp_out, s)
+                          outval, mode, velocity_layout, m, n, row_begin, row_count, out, disp_out, s)
     if (velocity_dtype == B200_F32 && precip_dtype == B200_F32) SL_DISPATCH(float, float);
     if (velocity_dtype == B200_F32 && precip_dtype == B200_F64) SL_DISPATCH(float, double);
     if (velocity_dtype == B200_F64 && precip_dtype == B200_F32) SL_DISPATCH(double, float);
@@ -419,6 +427,17 @@ extern "C" int b200_sl_extrapolate(const void *precip, const void *velocity,
 #undef SL_DISPATCH
     b200::set_error("unknown field dtypes %d / %d", velocity_dtype, precip_dtype);
     return B200_EINVAL;
+}
+
+extern "C" int b200_sl_extrapolate(const void *precip, const void *velocity,
+                                   const double *xy_coords, const double *disp_prev,
+                                   const double *tdiff, int T, double vel_timestep, int n_iter,
+                                   double outval, int mode, int velocity_dtype, int velocity_layout,
+                                   int precip_dtype, int m, int n, void *out, double *disp_out,
+                                   void *stream) {
+    return b200_sl_extrapolate_rows(precip, velocity, xy_coords, disp_prev, tdiff, T, vel_timestep, n_iter,
+                                    outval, mode, velocity_dtype, velocity_layout, precip_dtype, m, n, 0, m,
+                                    out, disp_out, stream);
 }
 
 extern "C" int b200_sl_extrapolate_host(const void *precip, const void *velocity,

@@ -117,6 +117,10 @@ def extrapolate(precip, velocity, timesteps, outval=np.nan, xy_coords=None,
     return_displacement = kwargs.get("return_displacement", False)
     interp_order = kwargs.get("interp_order", 1)
     map_coordinates_mode = kwargs.get("map_coordinates_mode", "constant")
+    # extension (ignored by the reference like any unknown kwarg): compute only the output rows
+    # [r0, r1) -- results and displacement arrays are then band shaped (tile partitioning of
+    # one composite over GPUs; inputs stay full frames)
+    rows = kwargs.get("b200_rows", None)
 
     if precip is None and not return_displacement:
         raise ValueError("precip is None but return_displacement is False")
@@ -163,30 +167,35 @@ def extrapolate(precip, velocity, timesteps, outval=np.nan, xy_coords=None,
         if tuple(d_xy.shape) != (2, m, n):
             raise ValueError("xy_coords must have shape (2, m, n)")
 
+    r0, r1 = (0, m) if rows is None else (int(rows[0]), int(rows[1]))
+    if not (0 <= r0 < r1 <= m):
+        raise ValueError("b200_rows must satisfy 0 <= r0 < r1 <= m")
+    mb = r1 - r0
+
     d_prev = None
     if displacement_prev is not None:
         d_prev = _device.to_device(displacement_prev, torch.float64)
-        if tuple(d_prev.shape) != (2, m, n):
+        if tuple(d_prev.shape) != (2, mb, n):
             raise ValueError("displacement_prev must have shape (2, m, n)")
 
     T = int(timestep_diff.size)
     d_out = None
     if d_precip is not None:
-        d_out = torch.empty((T, m, n), dtype=d_precip.dtype, device="cuda")
-    d_disp = torch.empty((2, m, n), dtype=torch.float64, device="cuda") \
+        d_out = torch.empty((T, mb, n), dtype=d_precip.dtype, device="cuda")
+    d_disp = torch.empty((2, mb, n), dtype=torch.float64, device="cuda") \
         if return_displacement else None
 
     # re-layout (2,m,n) -> (m,n,2) once, then the fused trajectory kernel
     d_vi = torch.empty((m, n, 2), dtype=d_vel.dtype, device="cuda")
     _lib.call("b200_sl_interleave_velocity", d_vel.data_ptr(), _device.dtype_code(d_vel.dtype),
               m, n, d_vi.data_ptr(), _device.stream_ptr())
-    _lib.call("b200_sl_extrapolate",
+    _lib.call("b200_sl_extrapolate_rows",
               _device.ptr(d_precip), d_vi.data_ptr(), _device.ptr(d_xy), _device.ptr(d_prev),
               timestep_diff.ctypes.data_as(_lib.c_dp), T, float(vel_timestep),
               max(int(n_iter), 0), float(outval), _MODES[map_coordinates_mode],
               _device.dtype_code(d_vel.dtype), _lib.LAYOUT_INTERLEAVED,
               _device.dtype_code(d_precip.dtype) if d_precip is not None else _lib.F64,
-              m, n, _device.ptr(d_out), _device.ptr(d_disp), _device.stream_ptr())
+              m, n, r0, mb, _device.ptr(d_out), _device.ptr(d_disp), _device.stream_ptr())
 
     if on_device:
         out, disp = d_out, d_disp

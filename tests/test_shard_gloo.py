@@ -61,3 +61,7 @@ def test_single_process_noop():
     assert _shard.broadcast_field(f) is f
     assert _shard.max_over_ranks(3.5) == 3.5
     assert _shard.member_indices(5, 1, 0) == [0, 1, 2, 3, 4]
+    bands = [_shard.row_band(4097, 8, r) for r in range(8)]
+    assert bands[0][0] == 0 and bands[-1][1] == 4097
+    assert all(bands[i][1] == bands[i + 1][0] for i in range(7))
+    assert max(b[1] - b[0] for b in bands) - min(b[1] - b[0] for b in bands) <= 1

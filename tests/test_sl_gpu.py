@@ -198,3 +198,26 @@ def test_full_size_properties(sl):
         assert bool((o[0] == full[t]).all() | True)
         assert torch.equal(torch.nan_to_num(o[0], nan=-1.0), torch.nan_to_num(full[t], nan=-1.0))
     assert torch.equal(d, dfull)
+
+
+def test_row_bands_equal_full_frame(sl):
+    """Tile partitioning (config[4]): any output band computed alone is bitwise the
+    corresponding rows of the full-frame result, incl. carried displacements."""
+    from pysteps_b200 import _shard, _synthetic as syn
+    m, n = 301, 260
+    P = syn.nan_disc(syn.rain_field(m, n, 9))
+    V = syn.velocity_field(m, n, 9, "rotation") * 6.0
+    full, dfull = sl.extrapolate(P, V, 5, allow_nonfinite_values=True, return_displacement=True)
+    covered = 0
+    for rank in range(3):
+        r0, r1 = _shard.row_band(m, 3, rank)
+        band, dband = sl.extrapolate(P, V, 3, allow_nonfinite_values=True, return_displacement=True,
+                                     b200_rows=(r0, r1))
+        band2, dband2 = sl.extrapolate(P, V, [1.0, 2.0], allow_nonfinite_values=True,
+                                       return_displacement=True, displacement_prev=dband, b200_rows=(r0, r1))
+        assert band.shape == (3, r1 - r0, n)
+        assert_bits_equal(band, full[:3, r0:r1], f"band {rank}")
+        assert_bits_equal(band2, full[3:, r0:r1], f"band {rank} continued")
+        assert_bits_equal(dband2, dfull[:, r0:r1], f"band {rank} displacement")
+        covered += r1 - r0
+    assert covered == m
