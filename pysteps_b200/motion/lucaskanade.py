@@ -40,46 +40,65 @@ def _s():
 
 
 class _Frame:
-    """Device state of one input frame after masking and morphological opening."""
-    __slots__ = ("img", "mask", "stats0", "opened", "stats", "q_track")
+    """Device state of one input frame after masking and morphological opening.  All buffers
+    are allocated up front (on the caller's stream) so that the work itself can be enqueued on
+    either stream without involving the caching allocator."""
+    __slots__ = ("img", "user_mask", "mask", "stats0", "opened", "stats", "q_track",
+                 "prepared", "have_stats", "have_q")
+
+    def __init__(self, img_d, user_mask_d, m, n, size_opening):
+        self.img = img_d
+        self.user_mask = user_mask_d
+        self.mask = torch.empty((m, n), dtype=torch.uint8, device="cuda")
+        self.stats0 = torch.empty(3, dtype=torch.float64, device="cuda")
+        self.opened = torch.empty((m, n), dtype=torch.float64, device="cuda") if size_opening > 0 else img_d
+        self.stats = torch.empty(12, dtype=torch.float64, device="cuda")
+        self.q_track = torch.empty((m, n), dtype=torch.uint8, device="cuda")
+        self.prepared = self.have_stats = self.have_q = False
 
 
-def _prepare_frame(img_d, user_mask_d, m, n, size_opening):
-    """masked_invalid + fill value + morph_opening (lucaskanade.py:213-224) and the uint8
-    image track_features would build from it (tracking/lucaskanade.py:144-160)."""
-    f = _Frame()
-    f.img = img_d
-    f.mask = torch.empty((m, n), dtype=torch.uint8, device="cuda")
-    f.stats0 = torch.empty(3, dtype=torch.float64, device="cuda")
-    _call("b200_mask_invalid", img_d.data_ptr(), _device.ptr(user_mask_d), m, n, f.mask.data_ptr(),
+def _prepare_frame(f, m, n, size_opening):
+    """masked_invalid + fill value + morph_opening (lucaskanade.py:213-224)."""
+    if f.prepared:
+        return f
+    _call("b200_mask_invalid", f.img.data_ptr(), _device.ptr(f.user_mask), m, n, f.mask.data_ptr(),
           f.stats0.data_ptr(), _s())
     if size_opening > 0:
-        f.opened = torch.empty((m, n), dtype=torch.float64, device="cuda")
         # thr = prvs_img.min(); removed pixels take np.nanmin(prvs_img): both stats0[0]
-        _call("b200_morph_opening", img_d.data_ptr(), f.mask.data_ptr(), m, n, int(size_opening),
+        _call("b200_morph_opening", f.img.data_ptr(), f.mask.data_ptr(), m, n, int(size_opening),
               f.stats0.data_ptr(), f.stats0.data_ptr(), f.opened.data_ptr(), _s())
-    else:
-        f.opened = img_d
-    f.stats = None
-    f.q_track = None
+    f.prepared = True
     return f
 
 
 def _frame_stats(f, m, n, buffer_mask):
-    if f.stats is None:
-        f.stats = torch.empty(12, dtype=torch.float64, device="cuda")
+    if not f.have_stats:
         _call("b200_masked_minmax", f.opened.data_ptr(), f.mask.data_ptr(), m, n, int(buffer_mask),
               f.stats0.data_ptr(), f.stats.data_ptr(), _s())
+        f.have_stats = True
     return f.stats
 
 
 def _track_image(f, m, n, buffer_mask):
-    if f.q_track is None:
+    """the uint8 image track_features builds (tracking/lucaskanade.py:144-160)"""
+    if not f.have_q:
         st = _frame_stats(f, m, n, buffer_mask)
-        f.q_track = torch.empty((m, n), dtype=torch.uint8, device="cuda")
         _call("b200_quantise_u8", f.opened.data_ptr(), f.mask.data_ptr(), m, n, 0, 0, st.data_ptr(),
               st.data_ptr(), f.q_track.data_ptr(), None, _s())
+        f.have_q = True
     return f.q_track
+
+
+_side_streams = {}
+
+
+def _side_stream():
+    """One auxiliary stream per (device, host thread)."""
+    import threading
+    key = (torch.cuda.current_device(), threading.get_ident())
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream()
+    return _side_streams[key]
 
 
 def _pyramid_layout(m, n, win, max_level):
@@ -165,48 +184,72 @@ def dense_lucaskanade(input_images, lk_kwargs=None, fd_method="shitomasi", fd_kw
     else:
         frames_d = _device.to_device(input_images, torch.float64)
 
-    frames = [_prepare_frame(frames_d[t], None if user_mask_d is None else user_mask_d[t], m, n,
-                             size_opening) for t in range(nr_fields)]
+    # Two streams: the Shi-Tomasi chain of the previous frame (min-eigenvalue map, sort, ordered
+    # selection -- latency-bound kernels that leave most SMs idle) runs on the caller's stream
+    # while the side stream prepares the next frame and builds both pyramids.
+    main = torch.cuda.current_stream()
+    side = _side_stream()
+    frames = [_Frame(frames_d[t], None if user_mask_d is None else user_mask_d[t], m, n, size_opening)
+              for t in range(nr_fields)]
+
+    def prepare(t):
+        return _prepare_frame(frames[t], m, n, size_opening)
 
     pool_cap = max_corners * max(nr_fields - 1, 1)
     pool_xy = torch.empty((pool_cap, 2), dtype=torch.float64, device="cuda")
     pool_uv = torch.empty((pool_cap, 2), dtype=torch.float64, device="cuda")
     counts = torch.zeros(4, dtype=torch.int32, device="cuda")  # pool, kept, declustered, corners
     lv, total = _pyramid_layout(m, n, winsize, nr_levels)
-    pyr = {}
+    # pyramids: Gaussian levels of every frame, Scharr levels of every frame but the last
+    pyr = [[torch.empty(total, dtype=torch.uint8, device="cuda"),
+            torch.empty(2 * total, dtype=torch.int16, device="cuda") if t < nr_fields - 1 else None,
+            False, False] for t in range(nr_fields)]
 
     def pyramid(t, with_deriv):
         """Gaussian pyramid of frame t's uint8 image (+ Scharr pyramid when it is the previous
         frame of a pair); a middle frame is built once and reused by both of its pairs."""
         args = (m, n, int(winsize[0]), int(winsize[1]), nr_levels)
-        if t not in pyr:
-            P = torch.empty(total, dtype=torch.uint8, device="cuda")
-            D = torch.empty(2 * total, dtype=torch.int16, device="cuda") if with_deriv else None
+        P, D, have_p, have_d = pyr[t]
+        want_d = with_deriv and not have_d
+        if not have_p:
             _call("b200_lk_build_pyramid", _track_image(frames[t], m, n, buffer_mask).data_ptr(), *args,
-                  P.data_ptr(), _device.ptr(D), _s())
-            pyr[t] = [P, D]
-        elif with_deriv and pyr[t][1] is None:
-            pyr[t][1] = torch.empty(2 * total, dtype=torch.int16, device="cuda")
-            _call("b200_lk_build_pyramid", None, *args, pyr[t][0].data_ptr(), pyr[t][1].data_ptr(), _s())
+                  P.data_ptr(), D.data_ptr() if want_d else None, _s())
+            pyr[t][2] = True
+            pyr[t][3] = have_d or want_d
+        elif want_d:
+            _call("b200_lk_build_pyramid", None, *args, P.data_ptr(), D.data_ptr(), _s())
+            pyr[t][3] = True
         return pyr[t]
 
+    if nr_fields >= 1:
+        prepare(0)
     for t in range(nr_fields - 1):
         f = frames[t]
         st = _frame_stats(f, m, n, buffer_mask)
-        # ---- feature detection on the previous frame (:227) -------------------------------
+        # ---- main stream: feature detection on the previous frame (:227) -------------------
         q_det = torch.empty((m, n), dtype=torch.uint8, device="cuda")
         valid = torch.empty((m, n), dtype=torch.uint8, device="cuda")
+        eig = torch.empty((m, n), dtype=torch.float32, device="cuda")
+        ev_stats = torch.cuda.Event()
+        ev_stats.record(main)
         _call("b200_quantise_u8", f.opened.data_ptr(), f.mask.data_ptr(), m, n, 1, buffer_mask,
               st.data_ptr(), st.data_ptr(), q_det.data_ptr(), valid.data_ptr(), _s())
-        eig = torch.empty((m, n), dtype=torch.float32, device="cuda")
         _call("b200_min_eig", q_det.data_ptr(), m, n, eig.data_ptr(), _s())
+        # ---- side stream: next frame + both pyramids (needs this frame's stats only).  Enqueued
+        # after the eigenvalue map so that it fills the SMs the sequential box-filter chains,
+        # the sort and the single-warp selection leave idle ---------------------------------
+        side.wait_event(ev_stats)
+        with torch.cuda.stream(side):
+            g = prepare(t + 1)
+            _frame_stats(g, m, n, buffer_mask)
+            pI = pyramid(t, True)
+            pJ = pyramid(t + 1, False)
         corners = torch.empty((max_corners, 2), dtype=torch.float32, device="cuda")
         ncorner = counts[3:4]
         _call("b200_good_features", eig.data_ptr(), valid.data_ptr(), m, n, max_corners,
               float(quality_level), float(min_distance), corners.data_ptr(), ncorner.data_ptr(), _s())
         # ---- sparse tracking previous -> next (:234) --------------------------------------
-        pI = pyramid(t, True)
-        pJ = pyramid(t + 1, False)
+        main.wait_stream(side)
         nxt = torch.empty((max_corners, 2), dtype=torch.float32, device="cuda")
         status = torch.empty(max_corners, dtype=torch.uint8, device="cuda")
         _call("b200_lk_track", pI[0].data_ptr(), pJ[0].data_ptr(), pI[1].data_ptr(), m, n,
@@ -216,7 +259,6 @@ def dense_lucaskanade(input_images, lk_kwargs=None, fd_method="shitomasi", fd_kw
         _call("b200_lk_compact_tracks", corners.data_ptr(), nxt.data_ptr(), status.data_ptr(),
               ncorner.data_ptr(), max_corners, pool_xy.data_ptr(), pool_uv.data_ptr(),
               counts[0:1].data_ptr(), pool_cap, _s())
-        del pyr[t]
 
     def zeros_or_empty():
         if dense:
