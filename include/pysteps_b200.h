@@ -203,11 +203,14 @@ int b200_decluster(const double *xy, const double *uv, const int *n_dev, int n_c
                    int min_samples, double *out_xy, double *out_uv, int *out_count, void *stream);
 
 /* pysteps/utils/interpolate.py:26-114 idwinterp2d: k-nearest inverse-distance weighting of
- * (npts, nvar) values onto the (ny, nx) grid -> out (nvar, ny, nx). k <= 32. */
+ * (npts, nvar) values onto the (ny, nx) grid -> out (nvar, ny, nx). k <= 32.
+ * coords_on_16th_grid != 0 is the caller's promise that every vector and grid coordinate is
+ * a multiple of 1/16 with magnitude < 2^14 (true for dense_lucaskanade: pixel grids and
+ * medians of integer corners); it enables a faster, result-identical key packing. */
 int b200_idw_fill(const double *xy, const double *vals, const int *npts_dev, int npts_cap,
                   int nvar, int k, double power, double dist_offset, double mean_res,
-                  const double *xgrid, int nx, const double *ygrid, int ny, double *out,
-                  void *stream);
+                  const double *xgrid, int nx, const double *ygrid, int ny,
+                  int coords_on_16th_grid, double *out, void *stream);
 
 /* ------------------------------------------------------------------------
  * Variational Echo Tracking -- replaces the native extension of the reference,

@@ -88,25 +88,40 @@ __device__ __forceinline__ bool key_less(unsigned long long da, int ia, unsigned
 // doubles; (bits, index) is compared as one integer key.
 // EXACT = false (k < K: fewer vectors than neighbours, or an unusual k): insertion only, with
 // a runtime length -- a rare, small-problem path.
-template <int K, bool EXACT>
+// PACKED (fast path of dense_lucaskanade): all coordinates are multiples of 1/16 below 2^14
+// and there are at most 2048 vectors, so a squared distance is a multiple of 1/256 below 2^29
+// and the 11 low mantissa bits of its float64 pattern are zero: the vector index is stored
+// there.  One 64-bit integer then carries (distance, index) in exactly the required order --
+// a comparator is one compare and two selects, and the index array disappears.
+template <int K, bool EXACT, bool PACKED>
 __device__ __forceinline__ void topk_scan(const double2 *__restrict__ spt, const int *__restrict__ sidx,
                                           int ncand, double qx, double qy, int k, bool first,
                                           unsigned long long (&bd)[K], int (&bi)[K]) {
     auto dist2 = [&](int t) -> unsigned long long {
         const double2 s = spt[t];
         const double dx = __dsub_rn(s.x, qx), dy = __dsub_rn(s.y, qy);
-        return (unsigned long long)__double_as_longlong(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+        const unsigned long long b =
+            (unsigned long long)__double_as_longlong(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+        return PACKED ? (b | (unsigned long long)sidx[t]) : b;
     };
     int t0 = 0;
     if (EXACT && first && ncand >= K) {
 #pragma unroll
-        for (int q = 0; q < K; q++) { bd[q] = dist2(q); bi[q] = sidx[q]; }
+        for (int q = 0; q < K; q++) { bd[q] = dist2(q); if (!PACKED) bi[q] = sidx[q]; }
 #pragma unroll
         for (int c = 0; c < net_size<K>(); c++) {
             const int a = net_a<K>(c), b = net_b<K>(c);
-            if (key_less(bd[b], bi[b], bd[a], bi[a])) {
-                const unsigned long long td = bd[a]; bd[a] = bd[b]; bd[b] = td;
-                const int ti = bi[a]; bi[a] = bi[b]; bi[b] = ti;
+            if (PACKED) {
+                const unsigned long long va = bd[a], vb = bd[b];
+                const bool sw = vb < va;
+                bd[a] = sw ? vb : va;
+                bd[b] = sw ? va : vb;
+            } else {
+                const bool sw = key_less(bd[b], bi[b], bd[a], bi[a]);
+                const unsigned long long va = bd[a], vb = bd[b];
+                const int ia = bi[a], ib = bi[b];
+                bd[a] = sw ? vb : va; bd[b] = sw ? va : vb;
+                bi[a] = sw ? ib : ia; bi[b] = sw ? ia : ib;
             }
         }
         t0 = K;
@@ -115,31 +130,34 @@ __device__ __forceinline__ void topk_scan(const double2 *__restrict__ spt, const
         const unsigned long long d2 = dist2(t);
         const int last = EXACT ? K - 1 : k - 1;
         unsigned long long wd = bd[K - 1];
-        int wi = bi[K - 1];
+        int wi = PACKED ? 0 : bi[K - 1];
         if (!EXACT) {
 #pragma unroll
             for (int q = 0; q < K; q++)
                 if (q == last) { wd = bd[q]; wi = bi[q]; }
         }
-        const int id = sidx[t];
-        if (key_less(d2, id, wd, wi)) {
+        const int id = PACKED ? 0 : sidx[t];
+        if (PACKED ? (d2 < wd) : key_less(d2, id, wd, wi)) {
             bool lt[K];
 #pragma unroll
-            for (int q = 0; q < K; q++) lt[q] = key_less(d2, id, bd[q], bi[q]);
+            for (int q = 0; q < K; q++) lt[q] = PACKED ? (d2 < bd[q]) : key_less(d2, id, bd[q], bi[q]);
 #pragma unroll
             for (int q = K - 1; q >= 1; q--) {
                 if (EXACT || q <= last) {
                     const unsigned long long nd = lt[q - 1] ? bd[q - 1] : (lt[q] ? d2 : bd[q]);
-                    const int ni = lt[q - 1] ? bi[q - 1] : (lt[q] ? id : bi[q]);
-                    bd[q] = nd; bi[q] = ni;
+                    bd[q] = nd;
+                    if (!PACKED) {
+                        const int ni = lt[q - 1] ? bi[q - 1] : (lt[q] ? id : bi[q]);
+                        bi[q] = ni;
+                    }
                 }
             }
-            if (lt[0]) { bd[0] = d2; bi[0] = id; }
+            if (lt[0]) { bd[0] = d2; if (!PACKED) bi[0] = id; }
         }
     }
 }
 
-template <int K, bool EXACT>
+template <int K, bool EXACT, bool PACKED>
 __global__ void __launch_bounds__(IDW_THREADS) idw_kernel(const IDWParams p) {
     __shared__ double2 spt[IDW_CHUNK];
     __shared__ int sidx[IDW_CHUNK];
@@ -250,12 +268,13 @@ __global__ void __launch_bounds__(IDW_THREADS) idw_kernel(const IDWParams p) {
             }
         }
         __syncthreads();
-        if (active) topk_scan<K, EXACT>(spt, sidx, cnt, qx, qy, k, r == 0, bd, bi);
+        if (active) topk_scan<K, EXACT, PACKED>(spt, sidx, cnt, qx, qy, k, r == 0, bd, bi);
     }
     if (!active || k < 1) return;
     double w[K];
 #pragma unroll
     for (int q = 0; q < K; q++) {
+        if (PACKED) { bi[q] = (int)(bd[q] & 2047ull); bd[q] &= ~2047ull; }
         double d = sqrt(__longlong_as_double((long long)bd[q]));  // exact Euclidean distance
         if (p.mean_res != 1.0) d = __ddiv_rn(d, p.mean_res);  // interpolate.py:98 (x / 1.0 == x)
         d = __dadd_rn(d, p.offset);             // :101
@@ -279,8 +298,8 @@ __global__ void __launch_bounds__(IDW_THREADS) idw_kernel(const IDWParams p) {
 
 extern "C" int b200_idw_fill(const double *xy, const double *vals, const int *npts_dev, int npts_cap,
                              int nvar, int k, double power, double dist_offset, double mean_res,
-                             const double *xgrid, int nx, const double *ygrid, int ny, double *out,
-                             void *stream) {
+                             const double *xgrid, int nx, const double *ygrid, int ny,
+                             int coords_on_16th_grid, double *out, void *stream) {
     B200_REQUIRE(xy && vals && xgrid && ygrid && out && npts_cap >= 1 && nvar >= 1 && nx >= 1 && ny >= 1 &&
                      k >= 1, "bad arguments");
     if (k > 32) {
@@ -296,9 +315,13 @@ extern "C" int b200_idw_fill(const double *xy, const double *vals, const int *np
     cudaStream_t s = (cudaStream_t)stream;
     // the host knows npts only as a capacity when npts_dev is given; EXACT needs k == K <= npts
     const bool exact_ok = (npts_dev == nullptr) && npts_cap >= k;
-    if (k == 20 && exact_ok) idw_kernel<20, true><<<grid, block, 0, s>>>(p);
-    else if (k == 8 && exact_ok) idw_kernel<8, true><<<grid, block, 0, s>>>(p);
-    else idw_kernel<32, false><<<grid, block, 0, s>>>(p);
+    // the caller vouches that every coordinate (vectors and grid) is a multiple of 1/16 with
+    // magnitude < 2^14; with <= 2048 vectors the index fits the zero low bits of the distance
+    const bool packed = coords_on_16th_grid != 0 && exact_ok && npts_cap <= IDW_CHUNK;
+    if (k == 20 && packed) idw_kernel<20, true, true><<<grid, block, 0, s>>>(p);
+    else if (k == 20 && exact_ok) idw_kernel<20, true, false><<<grid, block, 0, s>>>(p);
+    else if (k == 8 && exact_ok) idw_kernel<8, true, false><<<grid, block, 0, s>>>(p);
+    else idw_kernel<32, false, false><<<grid, block, 0, s>>>(p);
     B200_LAUNCH_CHECK();
     return 0;
 }

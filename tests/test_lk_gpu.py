@@ -259,10 +259,35 @@ def test_outliers_decluster_idw_vs_oracle(env):
             gy = torch.arange(ny, dtype=torch.float64, device="cuda")
             for k in (20, 5, 32):
                 out = torch.empty((2, ny, nx), dtype=torch.float64, device="cuda")
-                L.call("b200_idw_fill", oxy.data_ptr(), ouv.data_ptr(), None, d, 2, min(k, d), 0.5, 0.5,
-                       1.0, gx.data_ptr(), nx, gy.data_ptr(), ny, out.data_ptr(), s)
                 ref = ora.idwinterp2d(wxy, wuv, np.arange(nx), np.arange(ny), k=k)
-                assert np.abs(out.cpu().numpy() - ref).max() <= 1e-12, f"idw k={k}"
+                # the coordinates here are integers / half-integers: both the packed-key fast
+                # path (flag 1) and the general path (flag 0) must reproduce the oracle
+                for on_grid in (1, 0):
+                    out.zero_()
+                    L.call("b200_idw_fill", oxy.data_ptr(), ouv.data_ptr(), None, d, 2, min(k, d), 0.5, 0.5,
+                           1.0, gx.data_ptr(), nx, gy.data_ptr(), ny, on_grid, out.data_ptr(), s)
+                    assert np.abs(out.cpu().numpy() - ref).max() <= 1e-12, f"idw k={k} on_grid={on_grid}"
+
+
+def test_idw_general_coordinates(env):
+    torch, L = env
+    from oracle import lucaskanade as ora
+    rng = np.random.default_rng(12)
+    s = torch.cuda.current_stream().cuda_stream
+    for npts in (7, 300, 2500):
+        xy = rng.uniform(-5, 260, (npts, 2))
+        vals = rng.normal(size=(npts, 2))
+        gxh = np.linspace(0.3, 250.7, 211)
+        gyh = np.linspace(-2.0, 240.0, 173)
+        ref = ora.idwinterp2d(xy, vals, gxh, gyh, k=20)
+        mean_res = float(np.mean(np.abs([np.gradient(gxh).mean(), np.gradient(gyh).mean()])))
+        out = torch.empty((2, gyh.size, gxh.size), dtype=torch.float64, device="cuda")
+        dxy, dv = torch.from_numpy(xy).cuda(), torch.from_numpy(vals).cuda()  # keep alive
+        dgx, dgy = torch.from_numpy(gxh).cuda(), torch.from_numpy(gyh).cuda()
+        L.call("b200_idw_fill", dxy.data_ptr(), dv.data_ptr(), None, npts, 2, min(20, npts), 0.5, 0.5,
+               mean_res, dgx.data_ptr(), gxh.size, dgy.data_ptr(), gyh.size, 0, out.data_ptr(), s)
+        torch.cuda.synchronize()
+        assert np.abs(out.cpu().numpy() - ref).max() <= 1e-11, npts
 
 
 @pytest.mark.parametrize("name", ["plain_160x200", "nan_200x176", "three_frames_192x160",
