@@ -262,18 +262,27 @@ __global__ void __launch_bounds__(32) select_smem_kernel(const SelectParams p) {
                     }
                 }
         }
-        // order inside the batch: a still-valid earlier lane suppresses later lanes within
-        // minDistance.  Only lanes that are still valid need to be visited.
-        unsigned rem = __ballot_sync(0xffffffffu, ok);
-        while (rem) {
-            const int i = __ffs(rem) - 1;
+        // order inside the batch: an ACCEPTED earlier lane suppresses later lanes within
+        // minDistance.  All-pairs proximity first (32 independent shuffle steps, no dependency
+        // chain), then only the few lanes that have a close earlier lane are resolved in order.
+        unsigned close = 0u;  // earlier lanes of this batch within minDistance of this lane
+#pragma unroll 8
+        for (int i = 0; i < 32; i++) {
             const int xi = __shfl_sync(0xffffffffu, x, i), yi = __shfl_sync(0xffffffffu, y, i);
-            if (lane > i && ok) {
-                const float dx = (float)(x - xi), dy = (float)(y - yi);
-                if (dx * dx + dy * dy < md2) ok = false;
-            }
-            rem = __ballot_sync(0xffffffffu, ok) & ~((2u << i) - 1u);  // valid lanes after i
+            const float dx = (float)(x - xi), dy = (float)(y - yi);
+            if (i < lane && dx * dx + dy * dy < md2) close |= 1u << i;
         }
+        const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+        close &= okmask;                                        // only valid lanes can suppress
+        unsigned acc = __ballot_sync(0xffffffffu, ok && close == 0u);  // decided: accepted
+        unsigned pend = okmask & ~acc;                          // need their earlier lanes decided
+        while (pend) {
+            const int i = __ffs(pend) - 1;                      // lowest undecided lane: all of its
+            pend &= pend - 1;                                   // earlier lanes are decided now
+            const bool oki = (__shfl_sync(0xffffffffu, close, i) & acc) == 0u;
+            if (oki) acc |= 1u << i;
+        }
+        ok = (acc >> lane) & 1u;
         const unsigned bal = __ballot_sync(0xffffffffu, ok);
         const int rank = __popc(bal & ((1u << lane) - 1u));
         const bool take = ok && (!limited || accepted + rank < p.max_corners);
