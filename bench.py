@@ -40,6 +40,7 @@ METRIC = "Mpix/s advected (2048^2 frame, 12 leadtimes)"
 UNIT = "Mpix/s"
 MOTION = "lk"
 SCALING = "weak"
+MEMBERS = 0
 
 # BASELINE.json configs.  The default (config[1]) is what `metric` is quoted on; the others are
 # optional extra measurements (python bench.py --workload ...).
@@ -50,6 +51,11 @@ WORKLOADS = {
                           metric="Mpix/s advected (2048^2 frame, 12 leadtimes, VET motion)"),
     "composite4096": dict(m=4096, n=4096, T=24, motion="lk", scaling="strong",
                           metric="Mpix/s advected (4096^2 composite, 24 leadtimes, row bands over GPUs)"),
+    # config[3]'s advection component: the call shape of nowcasts/utils.py:441-458 -- every
+    # member has its own (perturbed) velocity, precipitation field and carried displacement,
+    # one single-step extrapolator call per member and lead time; members sharded over ranks
+    "ensemble24": dict(m=2048, n=2048, T=12, motion="lk", scaling="strong", members=24,
+                       metric="Mpix/s advected (24-member ensemble, 2048^2, 12 single-step calls per member)"),
 }
 
 
@@ -57,6 +63,8 @@ def set_workload(name):
     global M, N_, T_LEAD, METRIC, MOTION, SCALING
     w = WORKLOADS[name]
     M, N_, T_LEAD, METRIC, MOTION, SCALING = w["m"], w["n"], w["T"], w["metric"], w["motion"], w["scaling"]
+    global MEMBERS
+    MEMBERS = w.get("members", 0)
 
 
 def have_lk():
@@ -69,6 +77,8 @@ def have_lk():
 
 def workload_name(lk):
     mot = {"lk": "lk_dense", "vet": "vet"}[MOTION] if lk else "given_field"
+    if MEMBERS:
+        return f"{mot}+semilagrangian_{MEMBERS}members_x{T_LEAD}single_steps_{M}x{N_}"
     return f"{mot}+semilagrangian_T{T_LEAD}_{M}x{N_}" + ("_rowbands" if SCALING == "strong" else "")
 
 
@@ -251,8 +261,37 @@ def run_ours(args):
         Vd = _shard.broadcast_field(Vd, src=0)  # the only collective (NCCL over NVLink)
         return extrap(precip_d, Vd, T_LEAD, **ekw)
 
+    if MEMBERS:
+        mine = _shard.member_indices(MEMBERS, world, rank)
+        # per-member precipitation fields and velocity perturbations (synthetic: a member-specific
+        # multiple of the rotated field, like BPS' parallel/perpendicular components)
+        gen = torch.Generator(device="cuda").manual_seed(1234)
+        member_precip = [precip_d * (1.0 + 0.01 * i) for i in mine]
+        member_eps = [(0.05 * ((i * 7) % 11 - 5) / 5.0, 0.05 * ((i * 3) % 7 - 3) / 3.0) for i in mine]
+        del gen
+
+        def step_device():  # noqa: F811
+            """rank 0: motion field; broadcast; then T lead times x this rank's members, each a
+            single-step call carrying its own displacement (nowcasts/utils.py:453-458)."""
+            if rank == 0:
+                Vd = motion(frames_d)
+            else:
+                Vd = torch.empty((2, M, N_), dtype=torch.float64, device="cuda")
+            Vd = _shard.broadcast_field(Vd, src=0)
+            Vperp = torch.stack([-Vd[1], Vd[0]])
+            disp = [None] * len(mine)
+            last = None
+            for t in range(T_LEAD):
+                for j in range(len(mine)):
+                    Vm = Vd + member_eps[j][0] * Vd + member_eps[j][1] * Vperp
+                    last, disp[j] = extrap(member_precip[j], Vm, [1.0], displacement_prev=disp[j],
+                                           return_displacement=True)
+            return last
+
     def step_host():
         """public NumPy API: H2D of inputs and D2H of the result inside."""
+        if MEMBERS:
+            return step_device().cpu().numpy()
         if lk:
             Vh = motion(frames_h) if rank == 0 else None  # NumPy (2,m,n) float64, as pysteps returns
             if world > 1:
@@ -294,10 +333,12 @@ def run_ours(args):
     tr = trace.summary()
     dev_ms = _shard.max_over_ranks(dev_ms, device="cuda")
     nfields = world if SCALING == "weak" else 1
+    if MEMBERS:
+        nfields = MEMBERS
     value = nfields * args.steps * T_LEAD * M * N_ / (dev_ms * 1e-3) / 1e6
 
     # ---- end-to-end timing (host buffers) --------------------------------------------
-    for _ in range(max(1, args.warmup // 2)):
+    for _ in range(max(3, args.warmup // 2)):  # pinned-buffer allocation happens on the first calls
         step_host()
     barrier()
     t0 = time.perf_counter()

@@ -221,3 +221,22 @@ def test_row_bands_equal_full_frame(sl):
         assert_bits_equal(dband2, dfull[:, r0:r1], f"band {rank} displacement")
         covered += r1 - r0
     assert covered == m
+
+
+def test_concurrent_calls_from_threads(sl):
+    """nowcasts/utils.py:464-468 calls the extrapolator from dask threads: concurrent calls must
+    not interfere (stream-ordered scratch, no global mutable state in the kernels)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from pysteps_b200 import _synthetic as syn
+    cases = []
+    for i in range(6):
+        P = syn.rain_field(180 + 8 * i, 200, 20 + i)
+        V = syn.velocity_field(180 + 8 * i, 200, 20 + i, "rotation") * (2.0 + i)
+        cases.append((P, V))
+    serial = [sl.extrapolate(P, V, 4, return_displacement=True) for P, V in cases]
+    with ThreadPoolExecutor(max_workers=6) as ex:
+        futs = [ex.submit(sl.extrapolate, P, V, 4, return_displacement=True) for P, V in cases for _ in range(3)]
+        res = [f.result() for f in futs]
+    for k, (out, disp) in enumerate(res):
+        assert_bits_equal(out, serial[k // 3][0], f"thread result {k}")
+        assert_bits_equal(disp, serial[k // 3][1], f"thread displacement {k}")
