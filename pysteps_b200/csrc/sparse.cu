@@ -198,13 +198,36 @@ decluster_kernel(const double *__restrict__ xy, const double *__restrict__ uv, c
             }
             __syncthreads();
         }
-    if (tid == 0) {
-        int ns = 0;
-        for (int i = 0; i < n; i++) {
-            if (i == 0 || (key[i] >> 22) != (key[i - 1] >> 22)) seg_start[ns++] = (unsigned short)i;
+    // segment heads (first vector of every occupied cell) by a block-wide exclusive scan
+    {
+        __shared__ int warp_sum[32];
+        const int per = (npad + (int)blockDim.x - 1) / (int)blockDim.x;  // consecutive elements per thread
+        const int i0 = tid * per;
+        int local = 0;
+        for (int q = 0; q < per; q++) {
+            const int i = i0 + q;
+            if (i < n && (i == 0 || (key[i] >> 22) != (key[i - 1] >> 22))) local++;
         }
-        seg_start[ns] = (unsigned short)n;
-        s_nseg = ns;
+        int incl = local;
+        const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) warp_sum[wid] = incl;
+        __syncthreads();
+        int base = 0;
+        for (int w = 0; w < wid; w++) base += warp_sum[w];
+        int pos = base + incl - local;  // number of heads before this thread's elements
+        for (int q = 0; q < per; q++) {
+            const int i = i0 + q;
+            if (i < n && (i == 0 || (key[i] >> 22) != (key[i - 1] >> 22))) seg_start[pos++] = (unsigned short)i;
+        }
+        if (tid == (int)blockDim.x - 1) {
+            s_nseg = base + incl;
+            seg_start[base + incl] = (unsigned short)n;
+        }
     }
     __syncthreads();
     const int nseg = s_nseg;
@@ -213,8 +236,11 @@ decluster_kernel(const double *__restrict__ xy, const double *__restrict__ uv, c
     for (int sgi = tid; sgi < nseg; sgi += blockDim.x) {
         const int s0 = seg_start[sgi], s = seg_start[sgi + 1] - s0;
         if (s < min_samples) continue;
-        int o = 0;
-        for (int q = 0; q < sgi; q++) o += (seg_start[q + 1] - seg_start[q]) >= min_samples;
+        int o = sgi;  // every cell is kept when min_samples <= 1 (what dense_lucaskanade passes)
+        if (min_samples > 1) {
+            o = 0;
+            for (int q = 0; q < sgi; q++) o += (seg_start[q + 1] - seg_start[q]) >= min_samples;
+        }
         ouv[2 * o] = median_of(uv, 2, key + s0, s);
         ouv[2 * o + 1] = median_of(uv + 1, 2, key + s0, s);
         oxy[2 * o] = median_of(xy, 2, key + s0, s);
