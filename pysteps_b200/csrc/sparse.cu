@@ -11,11 +11,16 @@
 
 namespace {
 
-constexpr int OUT_WARPS = 8;
+constexpr int OUT_WARPS = 4;
 constexpr int OUT_KMAX = 64;  // neighbours incl. self
 
 // one warp per vector: k+1 nearest by (distance, index) via repeated warp arg-min, then the
 // 2x2 sample covariance of the k neighbours and the Mahalanobis distance of the vector.
+// CACHED: n <= 32 * OUT_CACHE, every lane keeps its squared distances in registers, so the
+// k+1 selection rounds only compare (the distances are computed once, not k+1 times).
+constexpr int OUT_CACHE = 64;
+
+template <bool CACHED>
 __global__ void __launch_bounds__(32 * OUT_WARPS)
 outliers_kernel(const double *__restrict__ uv, const double *__restrict__ xy, const int *__restrict__ n_dev,
                 int n_cap, double thr, int k, uint8_t *__restrict__ out) {
@@ -32,14 +37,37 @@ outliers_kernel(const double *__restrict__ uv, const double *__restrict__ xy, co
     const double xi = xy[2 * i], yi = xy[2 * i + 1];
     double last_d = -1.0;
     int last_j = -1;
+    double dc[CACHED ? OUT_CACHE : 1];
+    if (CACHED) {
+#pragma unroll
+        for (int q = 0; q < OUT_CACHE; q++) {
+            const int j = q * 32 + lane;
+            dc[q] = CUDART_INF;
+            if (j < n) {
+                const double dx = __dsub_rn(xy[2 * j], xi), dy = __dsub_rn(xy[2 * j + 1], yi);
+                dc[q] = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+            }
+        }
+    }
     for (int r = 0; r < kk; r++) {
         double bd = CUDART_INF;
         int bj = 0x7fffffff;
-        for (int j = lane; j < n; j += 32) {
-            const double dx = __dsub_rn(xy[2 * j], xi), dy = __dsub_rn(xy[2 * j + 1], yi);
-            const double d = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-            const bool after = (d > last_d) || (d == last_d && j > last_j);
-            if (after && (d < bd || (d == bd && j < bj))) { bd = d; bj = j; }
+        if (CACHED) {
+#pragma unroll
+            for (int q = 0; q < OUT_CACHE; q++) {
+                const int j = q * 32 + lane;
+                const double d = dc[q];
+                // ascending j within a lane: the first strict improvement is the lowest index
+                const bool after = (d > last_d) || (d == last_d && j > last_j);
+                if (j < n && after && d < bd) { bd = d; bj = j; }
+            }
+        } else {
+            for (int j = lane; j < n; j += 32) {
+                const double dx = __dsub_rn(xy[2 * j], xi), dy = __dsub_rn(xy[2 * j + 1], yi);
+                const double d = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                const bool after = (d > last_d) || (d == last_d && j > last_j);
+                if (after && (d < bd || (d == bd && j < bj))) { bd = d; bj = j; }
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -264,8 +292,12 @@ extern "C" int b200_detect_outliers(const double *uv, const double *xy, const in
         return B200_ENOTSUP;
     }
     if (n_cap == 0) return 0;
-    outliers_kernel<<<b200::ceil_div(n_cap, OUT_WARPS), 32 * OUT_WARPS, 0, (cudaStream_t)stream>>>(
-        uv, xy, n_dev, n_cap, thr, k, out);
+    if (n_cap <= 32 * OUT_CACHE)
+        outliers_kernel<true><<<b200::ceil_div(n_cap, OUT_WARPS), 32 * OUT_WARPS, 0, (cudaStream_t)stream>>>(
+            uv, xy, n_dev, n_cap, thr, k, out);
+    else
+        outliers_kernel<false><<<b200::ceil_div(n_cap, OUT_WARPS), 32 * OUT_WARPS, 0, (cudaStream_t)stream>>>(
+            uv, xy, n_dev, n_cap, thr, k, out);
     B200_LAUNCH_CHECK();
     return 0;
 }
