@@ -240,3 +240,45 @@ def test_concurrent_calls_from_threads(sl):
     for k, (out, disp) in enumerate(res):
         assert_bits_equal(out, serial[k // 3][0], f"thread result {k}")
         assert_bits_equal(disp, serial[k // 3][1], f"thread displacement {k}")
+
+
+def test_randomised_differential_vs_oracle(sl):
+    """40 random argument combinations (shapes incl. degenerate axes, dtypes, n_iter, integer /
+    list timesteps, modes, outval, carried displacement, custom coordinates, NaNs): outputs and
+    displacements bit-identical to the oracle every time."""
+    from oracle import semilagrangian as ora
+    rng = np.random.default_rng(2024)
+    for trial in range(40):
+        m = int(rng.choice([1, 2, 3, 17, 64, 97, 130]))
+        n = int(rng.choice([1, 2, 5, 33, 64, 101, 257]))
+        pdt = rng.choice([np.float32, np.float64])
+        vdt = rng.choice([np.float32, np.float64])
+        P = (rng.gamma(1.0, 4.0, (m, n)) * (rng.random((m, n)) > 0.5)).astype(pdt)
+        V = (rng.normal(size=(2, m, n)) * rng.choice([0.3, 2.0, 9.0]) + rng.normal(size=(2, 1, 1))).astype(vdt)
+        kw = {}
+        if rng.random() < 0.3:
+            P = P.copy()
+            P[rng.integers(0, m), rng.integers(0, n)] = np.nan
+            if m * n > 1:
+                kw["allow_nonfinite_values"] = True
+            else:
+                P = np.nan_to_num(P)
+        kw["n_iter"] = int(rng.choice([0, 1, 1, 1, 2, 3]))
+        if rng.random() < 0.5:
+            ts = int(rng.integers(1, 5))
+        else:
+            ts = sorted(set(np.round(rng.uniform(0.1, 4.0, int(rng.integers(1, 4))), 3).tolist()))
+            kw["vel_timestep"] = float(rng.choice([1.0, 2.0, 5.0]))
+        kw["map_coordinates_mode"] = str(rng.choice(["constant", "nearest"]))
+        outval = rng.choice(["nan", "min", "num"])
+        outval = {"nan": np.nan, "min": "min", "num": -3.25}[outval]
+        if rng.random() < 0.5:
+            kw["return_displacement"] = True
+        if rng.random() < 0.35:
+            kw["displacement_prev"] = rng.normal(size=(2, m, n)) * 3.0
+        if rng.random() < 0.25:
+            x, y = np.meshgrid(np.arange(n) * 0.9 + 0.3, np.arange(m) * 1.1 - 0.2)
+            kw["xy_coords"] = np.stack([x, y])
+        got = sl.extrapolate(P, V, ts, outval, **kw)
+        want = ora.extrapolate(P, V, ts, outval, **kw)
+        _compare(got, want, f"trial {trial}: {(m, n)} {pdt.__name__}/{vdt.__name__} ts={ts} {sorted(kw)}")
