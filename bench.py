@@ -249,6 +249,13 @@ def run_ours(args):
 
     def step_device():
         """inputs resident in HBM; results stay in HBM."""
+        if lk and band is not None and world > 1 and MOTION == "lk":
+            # one composite over GPUs: the sparse LK stages are deterministic and replicated, every
+            # rank fills its band of the motion field, the bands are all-gathered (the exchange
+            # step of this path), and every rank advects its band of output rows
+            Vband = motion(frames_d, interp_kwargs={"b200_rows": band})
+            Vd = _shard.gather_row_bands(Vband, M, world, rank)
+            return extrap(precip_d, Vd, T_LEAD, **ekw)
         if lk:
             if rank == 0:
                 Vd = motion(frames_d)
@@ -292,7 +299,10 @@ def run_ours(args):
         """public NumPy API: H2D of inputs and D2H of the result inside."""
         if MEMBERS:
             return step_device().cpu().numpy()
-        if lk:
+        if lk and band is not None and world > 1 and MOTION == "lk":
+            Vband = motion(frames_h, interp_kwargs={"b200_rows": band})  # NumPy band
+            Vh = _shard.gather_row_bands(torch.from_numpy(Vband).cuda(), M, world, rank).cpu().numpy()
+        elif lk:
             Vh = motion(frames_h) if rank == 0 else None  # NumPy (2,m,n) float64, as pysteps returns
             if world > 1:
                 Vd = torch.from_numpy(Vh).cuda() if rank == 0 else \
@@ -387,7 +397,9 @@ def run_ours(args):
                            "fields_per_gpu": 1 if SCALING == "weak" else round(1.0 / world, 4), "l2": "flushed between timed steps (256 MB fill)",
                            "parallelism": (f"1 field per GPU x{world}" if SCALING == "weak" else
                                            f"output row bands over {world} GPU(s), inputs replicated")
-                           + ", NCCL broadcast of the motion field"},
+                           + (", NCCL all-gather of the motion-field bands" if (SCALING == "strong" and not MEMBERS
+                                                                               and world > 1 and MOTION == "lk")
+                              else ", NCCL broadcast of the motion field")},
                 "clocks": clocks.summary(),
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / args.steps},

@@ -39,3 +39,26 @@ def max_over_ranks(value, device=None):
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def gather_row_bands(band, m, world_size, rank):
+    """Full (c, m, n) field from every rank's (c, rows, n) band of it (bands as `row_band`
+    assigns them).  The one exchange step of the tile-partitioned path: the trajectory kernel
+    samples the motion field anywhere, so every rank needs all of it."""
+    if world_size == 1:
+        return band
+    c, rows, n = band.shape
+    full = torch.empty((c, m, n), dtype=band.dtype, device=band.device)
+    bands = [row_band(m, world_size, r) for r in range(world_size)]
+    assert bands[rank][1] - bands[rank][0] == rows
+    even = all(b[1] - b[0] == rows for b in bands)
+    for ch in range(c):
+        views = [full[ch, b[0]:b[1]] for b in bands]
+        if even:
+            dist.all_gather(views, band[ch].contiguous())
+        else:
+            for r, v in enumerate(views):
+                if r == rank:
+                    v.copy_(band[ch])
+                dist.broadcast(v, src=r)
+    return full

@@ -175,6 +175,13 @@ def dense_lucaskanade(input_images, lk_kwargs=None, fd_method="shitomasi", fd_kw
     nr_fields = int(input_images.shape[0])
     m, n = int(input_images.shape[1]), int(input_images.shape[2])
 
+    # extension, see the interpolation stage below
+    rows = interp_kwargs.get("b200_rows", None)
+    r0, r1 = (0, m) if rows is None else (int(rows[0]), int(rows[1]))
+    if not (0 <= r0 < r1 <= m):
+        raise ValueError("b200_rows must satisfy 0 <= r0 < r1 <= m")
+    mb = r1 - r0
+
     # ---- upload (the reference copies its input, :182) ------------------------------------
     user_mask_d = None
     if isinstance(input_images, MaskedArray):
@@ -262,8 +269,8 @@ def dense_lucaskanade(input_images, lk_kwargs=None, fd_method="shitomasi", fd_kw
 
     def zeros_or_empty():
         if dense:
-            z = torch.zeros((2, m, n), dtype=torch.float64, device="cuda")
-            return z if on_device else np.zeros((2, m, n))
+            z = torch.zeros((2, mb, n), dtype=torch.float64, device="cuda")
+            return z if on_device else np.zeros((2, mb, n))
         e = np.empty(shape=(0, 2))
         return (torch.from_numpy(e).cuda(), torch.from_numpy(e).cuda()) if on_device else (e, e.copy())
 
@@ -307,7 +314,11 @@ def dense_lucaskanade(input_images, lk_kwargs=None, fd_method="shitomasi", fd_kw
     dist_offset = float(interp_kwargs.get("dist_offset", 0.5))
     if k is None:
         raise NotImplementedError("pysteps_b200 LK: idwinterp2d with k=None is not implemented")
-    out = torch.empty((2, m, n), dtype=torch.float64, device="cuda")
+    # extension (an unknown interpolator kwarg is ignored by the reference): fill only the grid
+    # rows [r0, r1) -- the result is then band shaped (2, r1-r0, n).  The sparse stages are
+    # deterministic, so ranks that each fill one band of the same frames agree bit for bit with
+    # the rows of the full field (tile partitioning of one composite over GPUs).
+    out = torch.empty((2, mb, n), dtype=torch.float64, device="cuda")
     xy_h = dec_xy[:n_dec].cpu().numpy()
     uv_h = dec_uv[:n_dec].cpu().numpy()
     if np.any(~np.isfinite(uv_h)):
@@ -316,21 +327,21 @@ def dense_lucaskanade(input_images, lk_kwargs=None, fd_method="shitomasi", fd_kw
         raise ValueError("argument 'xy_coord' contains non-finite values")
     if n_dec == 1:  # decorators.py:200-204
         for c in range(2):
-            _call("b200_fill_f64", out[c].data_ptr(), m * n, float(1.0 * uv_h[0, c]), _s())
+            _call("b200_fill_f64", out[c].data_ptr(), mb * n, float(1.0 * uv_h[0, c]), _s())
     elif uv_h.max() == uv_h.min():  # decorators.py:207-208
-        _call("b200_fill_f64", out.data_ptr(), 2 * m * n, float(1.0 * uv_h.ravel()[0]), _s())
+        _call("b200_fill_f64", out.data_ptr(), 2 * mb * n, float(1.0 * uv_h.ravel()[0]), _s())
     else:
         if n < 2 or m < 2:
             raise ValueError("Shape of array too small to calculate a numerical gradient, "
                              "at least (edge_order + 1) elements are required.")
         xgrid = torch.arange(n, dtype=torch.float64, device="cuda")
-        ygrid = torch.arange(m, dtype=torch.float64, device="cuda")
+        ygrid = torch.arange(r0, r1, dtype=torch.float64, device="cuda")
         # integer pixel grid + corner coordinates that are integers or cell medians (multiples
         # of 1/2): squared distances are exact small multiples of 1/256 -> packed-key fast path
         on_grid = bool(np.all(xy_h * 16.0 == np.rint(xy_h * 16.0)) and np.abs(xy_h).max() < 16384.0
                        and max(m, n) < 16384)
         _call("b200_idw_fill", dec_xy.data_ptr(), dec_uv.data_ptr(), None, n_dec, 2, int(min(int(k), n_dec)),
-              power, dist_offset, 1.0, xgrid.data_ptr(), n, ygrid.data_ptr(), m, int(on_grid),
+              power, dist_offset, 1.0, xgrid.data_ptr(), n, ygrid.data_ptr(), mb, int(on_grid),
               out.data_ptr(), _s())
 
     if verbose:

@@ -396,3 +396,18 @@ def test_kwargs_variants_vs_oracle(env):
         V = lk(fr, **kw)
         Vo = ora.dense_lucaskanade(fr, **kw)
         assert np.abs(V - Vo).max() <= 1e-11, kw
+
+
+def test_row_band_fill_equals_rows_of_full_field(env):
+    """interp_kwargs b200_rows: a band of the motion field is bit-identical to the same rows of
+    the full field (what the tile-partitioned multi-GPU path all-gathers)."""
+    from pysteps_b200.motion.lucaskanade import dense_lucaskanade as lk
+    frames = _frames("nan_200x176")
+    full = lk(frames)
+    for r0, r1 in ((0, 200), (0, 67), (67, 134), (134, 200), (93, 94)):
+        band = lk(frames, interp_kwargs={"b200_rows": (r0, r1)})
+        assert band.shape == (2, r1 - r0, 176)
+        assert np.array_equal(band, full[:, r0:r1])
+    with pytest.raises(ValueError):
+        lk(frames, interp_kwargs={"b200_rows": (10, 10)})
+    assert lk(frames[:1], interp_kwargs={"b200_rows": (5, 9)}).shape == (2, 4, 176)

@@ -29,7 +29,13 @@ def _worker(rank, world, port, q):
     field = torch.arange(2 * 6 * 5, dtype=torch.float64).reshape(2, 6, 5) * 0.25 if rank == 0 else None
     got = _shard.broadcast_field(field, src=0, shape=(2, 6, 5))
     slow = _shard.max_over_ranks(1.0 + rank)
-    q.put((rank, mine, got.numpy().copy(), slow))
+    # row bands of a composite, gathered back into the full field (even and uneven splits)
+    gathered = []
+    for m in (8, 7):
+        whole = torch.arange(2 * m * 5, dtype=torch.float64).reshape(2, m, 5)
+        r0, r1 = _shard.row_band(m, world, rank)
+        gathered.append(torch.equal(_shard.gather_row_bands(whole[:, r0:r1].contiguous(), m, world, rank), whole))
+    q.put((rank, mine, got.numpy().copy(), slow, gathered))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -46,10 +52,11 @@ def test_sharding_and_broadcast_world2():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    members = sorted(i for _, mine, _, _ in res for i in mine)
+    members = sorted(i for _, mine, _, _, _ in res for i in mine)
     assert members == list(range(24))
     ref = (np.arange(60, dtype=np.float64) * 0.25).reshape(2, 6, 5)
-    for rank, mine, got, slow in res:
+    for rank, mine, got, slow, gathered in res:
+        assert gathered == [True, True]
         assert len(mine) == 12
         assert np.array_equal(got, ref)
         assert slow == 2.0
