@@ -95,21 +95,27 @@ def make_inputs(seed, lk):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """nvidia-smi in loop mode (-lms 20) for the duration of the timed region."""
+    """nvidia-smi in loop mode (-lms 200, the profiling recipe's clocks line) from the warm-up to the
+    end of the end-to-end leg.  The first sample (taken before any load) is dropped."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index=0):
+    def __init__(self, index=0, enabled=True):
         self.index = index
+        # one sampler per job (rank 0's GPU): nvidia-smi polls serialise on a driver-wide lock
+        # that kernel launches of every process on the box also take
+        self.enabled = enabled and not os.environ.get("BENCH_NO_CLOCKS")
         self.samples = []
         self.proc = None
 
     def __enter__(self):
+        if not self.enabled:
+            return self
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "20"],
+                 "--format=csv,noheader,nounits", "-lms", "200"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             time.sleep(0.25)  # let the first samples arrive before the timed region starts
         except Exception:
@@ -130,6 +136,8 @@ class ClockSampler:
             parts = [x.strip() for x in line.split(",")]
             if len(parts) >= 6:
                 self.samples.append(parts)
+        if len(self.samples) >= 3:
+            self.samples = self.samples[1:]
 
     def summary(self):
         if not self.samples:
@@ -319,9 +327,9 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timing ------------------------------------------------------
-    # the clock sampler (nvidia-smi -lms 20) spans warm-up and the timed steps: the timed
-    # region alone lasts well under 100 ms
-    clocks = ClockSampler(local)
+    # the clock sampler spans warm-up, the timed steps and the end-to-end leg (a 20 ms polling
+    # period was measured to slow a 6 ms step by 3 ms: queries and launches share a driver lock)
+    clocks = ClockSampler(local, enabled=(rank == 0))
     clocks.__enter__()
     for _ in range(args.warmup):
         step_device()
@@ -337,7 +345,6 @@ def run_ours(args):
             step_device()
             e.record()
         barrier()
-    clocks.__exit__(None, None, None)
     launches = _lib.load().b200_launch_count() - launches0
     dev_ms = sum(s.elapsed_time(e) for s, e in ev)
     tr = trace.summary()
@@ -356,6 +363,7 @@ def run_ours(args):
         out = step_host()
     barrier()
     e2e_s = time.perf_counter() - t0
+    clocks.__exit__(None, None, None)
     e2e_s = _shard.max_over_ranks(e2e_s, device="cuda")
     e2e_val = nfields * args.steps * T_LEAD * M * N_ / e2e_s / 1e6
     # LK: frames up, field down, field up again for the extrapolator (plugin API is NumPy)

@@ -54,7 +54,9 @@ def gather_row_bands(band, m, world_size, rank):
     even = all(b[1] - b[0] == rows for b in bands)
     for ch in range(c):
         views = [full[ch, b[0]:b[1]] for b in bands]
-        if even:
+        if even and dist.get_backend() == "nccl":
+            dist.all_gather_into_tensor(full[ch], band[ch].contiguous())  # bands are consecutive
+        elif even:
             dist.all_gather(views, band[ch].contiguous())
         else:
             for r, v in enumerate(views):
