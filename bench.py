@@ -161,21 +161,42 @@ def cpu_step(frames, precip, V, lk):
     elif lk:
         from oracle import lucaskanade as ora_lk
         V = ora_lk.dense_lucaskanade(frames)
+    if MEMBERS:
+        # bounded sample: ONE member of the ensemble (the members are independent and identical
+        # in cost); the caller extrapolates to MEMBERS members
+        from oracle import noise_motion as ora_bps
+        t1 = time.perf_counter()
+        pert = ora_bps.initialize_bps(V, 1.0, 5.0, randstate=np.random.RandomState(1000))
+        disp, res = None, None
+        for t in range(T_LEAD):
+            Vm = ora_bps.perturbed_velocity(V, pert, (t + 1) * 5.0)
+            res, disp = ora.extrapolate(precip, Vm, [1.0], displacement_prev=disp, return_displacement=True)
+        return res, time.perf_counter() - t1
     return ora.extrapolate(precip, V, T_LEAD)
+
+
+def _timed_cpu_step(frames, precip, V, lk):
+    """seconds of one whole step on the host (ensemble: motion + MEMBERS x the sampled member)"""
+    t0 = time.perf_counter()
+    r = cpu_step(frames, precip, V, lk)
+    dt = time.perf_counter() - t0
+    if MEMBERS:
+        member = r[1]
+        return (dt - member) + MEMBERS * member
+    return dt
 
 
 def cpu_baseline(frames, precip, V, lk, reps=1):
     import oracle
     best = None
     for _ in range(reps):
-        t0 = time.perf_counter()
-        cpu_step(frames, precip, V, lk)
-        dt = time.perf_counter() - t0
+        dt = _timed_cpu_step(frames, precip, V, lk)
         best = dt if best is None else min(best, dt)
-    return {"value": T_LEAD * M * N_ / best / 1e6, "unit": UNIT, "cores": oracle.num_threads(),
+    return {"value": (MEMBERS or 1) * T_LEAD * M * N_ / best / 1e6, "unit": UNIT, "cores": oracle.num_threads(),
             "kind": "port",
             "sample": f"{reps} full step(s) of {workload_name(lk)} (oracle C/NumPy port, "
-                      f"OpenMP {oracle.num_threads()} threads), best of {reps}; {best:.2f} s"}
+                      f"OpenMP {oracle.num_threads()} threads), best of {reps}; {best:.2f} s"
+                      + (f" (1 of {MEMBERS} members run, scaled)" if MEMBERS else "")}
 
 
 def run_reference(args):
@@ -188,11 +209,10 @@ def run_reference(args):
     for _ in range(args.warmup):
         cpu_step(np.ascontiguousarray(frames[:, :256, :256]), np.ascontiguousarray(precip[:256, :256]),
                  np.ascontiguousarray(V[:, :256, :256]), lk)
-    t0 = time.perf_counter()
+    dt = 0.0
     for _ in range(args.steps):
-        cpu_step(frames, precip, V, lk)
-    dt = time.perf_counter() - t0
-    val = args.steps * T_LEAD * M * N_ / dt / 1e6
+        dt += _timed_cpu_step(frames, precip, V, lk)
+    val = args.steps * (MEMBERS or 1) * T_LEAD * M * N_ / dt / 1e6
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -277,36 +297,51 @@ def run_ours(args):
         return extrap(precip_d, Vd, T_LEAD, **ekw)
 
     if MEMBERS:
+        from pysteps_b200 import noise as b200_noise
+        bps_init, bps_gen = b200_noise.get_method("bps")
         mine = _shard.member_indices(MEMBERS, world, rank)
-        # per-member precipitation fields and velocity perturbations (synthetic: a member-specific
-        # multiple of the rotated field, like BPS' parallel/perpendicular components)
-        gen = torch.Generator(device="cuda").manual_seed(1234)
+        # per-member precipitation fields (synthetic); the velocity perturbations are the BPS
+        # perturbator's (noise/motion.py), one seeded RandomState per member as in
+        # nowcasts/steps.py:915-926, evaluated inside the advection call (fused kernel)
         member_precip = [precip_d * (1.0 + 0.01 * i) for i in mine]
-        member_eps = [(0.05 * ((i * 7) % 11 - 5) / 5.0, 0.05 * ((i * 3) % 7 - 3) / 3.0) for i in mine]
-        del gen
+        member_precip_h = [pin(precip_h * np.float32(1.0 + 0.01 * i)) for i in mine]
+        KMPP, DT_MIN = 1.0, 5.0
+
+        def member_loop(V, fields, resident):
+            """nowcasts/utils.py:440-458: T lead times x this rank's members, each a single-step
+            call with a freshly perturbed motion field, carrying its own displacement."""
+            perts = [bps_init(V, 1.0 / KMPP, DT_MIN, randstate=np.random.RandomState(1000 + i)) for i in mine]
+            disp = [None] * len(mine)
+            last = None
+            for t in range(T_LEAD):
+                for j in range(len(mine)):
+                    Vm = V + bps_gen(perts[j], (t + 1) * DT_MIN)
+                    last, disp[j] = extrap(fields[j], Vm, [1.0], displacement_prev=disp[j],
+                                           return_displacement=True, b200_resident=resident)
+            return last
 
         def step_device():  # noqa: F811
-            """rank 0: motion field; broadcast; then T lead times x this rank's members, each a
-            single-step call carrying its own displacement (nowcasts/utils.py:453-458)."""
+            """rank 0: motion field; broadcast; member loop on device-resident fields."""
             if rank == 0:
                 Vd = motion(frames_d)
             else:
                 Vd = torch.empty((2, M, N_), dtype=torch.float64, device="cuda")
             Vd = _shard.broadcast_field(Vd, src=0)
-            Vperp = torch.stack([-Vd[1], Vd[0]])
-            disp = [None] * len(mine)
-            last = None
-            for t in range(T_LEAD):
-                for j in range(len(mine)):
-                    Vm = Vd + member_eps[j][0] * Vd + member_eps[j][1] * Vperp
-                    last, disp[j] = extrap(member_precip[j], Vm, [1.0], displacement_prev=disp[j],
-                                           return_displacement=True)
-            return last
+            return member_loop(Vd, member_precip, False)
 
     def step_host():
         """public NumPy API: H2D of inputs and D2H of the result inside."""
         if MEMBERS:
-            return step_device().cpu().numpy()
+            # NumPy API as nowcast_main_loop uses it: the motion field is uploaded once per
+            # forecast, every member-step uploads its precipitation field and downloads the
+            # advected one; perturbed fields and displacements never leave the device
+            Vh = motion(frames_h) if rank == 0 else None
+            if world > 1:
+                Vd = torch.from_numpy(Vh).cuda() if rank == 0 else \
+                    torch.empty((2, M, N_), dtype=torch.float64, device="cuda")
+                dist.broadcast(Vd, src=0)
+                Vh = Vd.cpu().numpy()
+            return member_loop(Vh, member_precip_h, True)
         if lk and band is not None and world > 1 and MOTION == "lk":
             Vband = motion(frames_h, interp_kwargs={"b200_rows": band})  # NumPy band
             Vh = _shard.gather_row_bands(torch.from_numpy(Vband).cuda(), M, world, rank).cpu().numpy()
@@ -369,6 +404,9 @@ def run_ours(args):
     # LK: frames up, field down, field up again for the extrapolator (plugin API is NumPy)
     h2d = precip_h.nbytes + (frames_h.nbytes + 2 * M * N_ * 8 if lk else V_h.nbytes)
     d2h = out.nbytes + (2 * M * N_ * 8 if lk else 0)
+    if MEMBERS:  # per rank: frames + field once, one precipitation field up / one down per member-step
+        h2d = frames_h.nbytes + 2 * M * N_ * 8 + len(mine) * T_LEAD * precip_h.nbytes
+        d2h = 2 * M * N_ * 8 + len(mine) * T_LEAD * precip_h.nbytes
 
     if rank == 0:
         # ---- roofline of the trajectory kernel (this run's launches) -----------------

@@ -97,6 +97,25 @@ int b200_sl_extrapolate_rows(const void *precip, const void *velocity,
 int b200_sl_interleave_velocity(const void *velocity, int velocity_dtype, int m, int n,
                                 void *out, void *stream);
 
+/* pysteps/noise/motion.py:129-180 (initialize_bps :129-141, generate_bps :172-180) fused with
+ * the call site pysteps/nowcasts/utils.py:448-451 `velocity + velocity_pert_gen[i](t)`:
+ *   p = (a_par * V/|V| + a_perp * perp(V/|V|)) / vsf     at every grid node,
+ * a_par = g_par(t)*eps_par, a_perp = g_perp(t)*eps_perp (host scalars).  velocity is planar
+ * (2,m,n) of velocity_dtype; `what` selects the float64 output:
+ *   B200_BPS_FIELD_INTERLEAVED  V + p as (m,n,2) -- what b200_sl_extrapolate takes with
+ *                               B200_LAYOUT_INTERLEAVED; replaces a 64 MB host array and its
+ *                               upload per member and time step
+ *   B200_BPS_FIELD_PLANAR       V + p as (2,m,n)
+ *   B200_BPS_PERTURBATION       p as (2,m,n)       (the value of generate_bps)
+ *   B200_BPS_UNIT               V/|V| as (2,m,n)   (perturbator["V_par"]; a, b, vsf unused) */
+#define B200_BPS_FIELD_INTERLEAVED 0
+#define B200_BPS_FIELD_PLANAR 1
+#define B200_BPS_PERTURBATION 2
+#define B200_BPS_UNIT 3
+int b200_bps_perturb_velocity(const void *velocity, int velocity_dtype, int m, int n,
+                              double a_par, double a_perp, double vsf, int what, double *out,
+                              void *stream);
+
 /* Same operation on HOST buffers: allocates device scratch from the stream
  * ordered pool, copies in, runs, copies out and synchronises.  This is the
  * call a non-Python binding (cgo / JNI / plain C) would make. */

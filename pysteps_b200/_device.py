@@ -49,9 +49,37 @@ def is_device_tensor(x):
     return isinstance(x, torch.Tensor) and x.is_cuda
 
 
+class DeviceField:
+    """A result left in HBM on request (``b200_resident=True``): array-like enough to be stored
+    and handed back (shape / ndim / dtype); ``np.asarray(x)`` downloads it once.  Passing it
+    back to a pysteps_b200 function costs no transfer."""
+    __slots__ = ("tensor", "_host")
+
+    def __init__(self, tensor):
+        self.tensor = tensor
+        self._host = None
+
+    shape = property(lambda self: tuple(self.tensor.shape))
+    ndim = property(lambda self: self.tensor.ndim)
+    dtype = property(lambda self: np.dtype(str(self.tensor.dtype).replace("torch.", "")))
+
+    def __array__(self, dtype=None, copy=None):
+        if self._host is None:
+            self._host = to_host(self.tensor)
+        return self._host if dtype is None else self._host.astype(dtype, copy=False)
+
+    def __getitem__(self, idx):
+        return np.asarray(self)[idx]
+
+    def __len__(self):
+        return self.tensor.shape[0]
+
+
 def to_device(a, dtype=None):
     """numpy array / torch tensor -> contiguous CUDA tensor (async H2D on the current stream;
     full PCIe speed when the host buffer is pinned)."""
+    if isinstance(a, DeviceField):
+        a = a.tensor
     if isinstance(a, torch.Tensor):
         t = a
     else:

@@ -501,3 +501,82 @@ extern "C" int b200_sl_interleave_velocity(const void *velocity, int velocity_dt
     B200_LAUNCH_CHECK();
     return 0;
 }
+
+// BPS motion perturbation (pysteps/noise/motion.py:129-180) applied at the grid nodes while the
+// field is re-laid out for the trajectory kernel: out = V + (a*V_par + b*V_perp)/vsf with
+// V_par = V/|V| (zero where |V| <= 1e-12), V_perp = (-V_par.y, V_par.x), a = g_par(t)*eps_par,
+// b = g_perp(t)*eps_perp.  The norm and the division run in the field's own dtype, as NumPy does
+// (linalg.norm and V/N keep float32; the result is stored into a float64 array, :138-139).
+template <typename F, int WHAT>
+__global__ void __launch_bounds__(256)
+bps_perturb_kernel(const F *__restrict__ V, double *__restrict__ out, size_t N, double a, double b,
+                   double vsf) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+        const F vx = __ldg(V + i), vy = __ldg(V + N + i);
+        double nx, ny;
+        if (sizeof(F) == 4) {
+            const float nrm = __fsqrt_rn(__fadd_rn(__fmul_rn((float)vx, (float)vx), __fmul_rn((float)vy, (float)vy)));
+            const bool ok = nrm > (float)1e-12;  // NaN compares false
+            nx = ok ? (double)__fdiv_rn((float)vx, nrm) : 0.0;
+            ny = ok ? (double)__fdiv_rn((float)vy, nrm) : 0.0;
+        } else {
+            const double nrm = __dsqrt_rn(__dadd_rn(__dmul_rn((double)vx, (double)vx), __dmul_rn((double)vy, (double)vy)));
+            const bool ok = nrm > 1e-12;
+            nx = ok ? __ddiv_rn((double)vx, nrm) : 0.0;
+            ny = ok ? __ddiv_rn((double)vy, nrm) : 0.0;
+        }
+        double ox, oy;
+        if (WHAT == B200_BPS_UNIT) {
+            ox = nx;
+            oy = ny;
+        } else {
+            ox = __ddiv_rn(__dadd_rn(__dmul_rn(a, nx), __dmul_rn(b, -ny)), vsf);
+            oy = __ddiv_rn(__dadd_rn(__dmul_rn(a, ny), __dmul_rn(b, nx)), vsf);
+            if (WHAT != B200_BPS_PERTURBATION) {
+                ox = __dadd_rn((double)vx, ox);
+                oy = __dadd_rn((double)vy, oy);
+            }
+        }
+        if (WHAT == B200_BPS_FIELD_INTERLEAVED) {
+            reinterpret_cast<double2 *>(out)[i] = make_double2(ox, oy);
+        } else {
+            out[i] = ox;
+            out[N + i] = oy;
+        }
+    }
+}
+
+template <typename F>
+static int bps_launch(const void *velocity, size_t N, double a, double b, double vsf, int what, double *out,
+                      cudaStream_t s) {
+    const int blocks = (int)std::min<size_t>((N + 255) / 256, (size_t)b200::num_sms() * 16);
+    const F *V = (const F *)velocity;
+    switch (what) {
+    case B200_BPS_FIELD_INTERLEAVED:
+        bps_perturb_kernel<F, B200_BPS_FIELD_INTERLEAVED><<<blocks, 256, 0, s>>>(V, out, N, a, b, vsf); break;
+    case B200_BPS_FIELD_PLANAR:
+        bps_perturb_kernel<F, B200_BPS_FIELD_PLANAR><<<blocks, 256, 0, s>>>(V, out, N, a, b, vsf); break;
+    case B200_BPS_PERTURBATION:
+        bps_perturb_kernel<F, B200_BPS_PERTURBATION><<<blocks, 256, 0, s>>>(V, out, N, a, b, vsf); break;
+    case B200_BPS_UNIT:
+        bps_perturb_kernel<F, B200_BPS_UNIT><<<blocks, 256, 0, s>>>(V, out, N, a, b, vsf); break;
+    default:
+        b200::set_error("unknown BPS output selector %d", what);
+        return B200_EINVAL;
+    }
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int b200_bps_perturb_velocity(const void *velocity, int velocity_dtype, int m, int n,
+                                         double a_par, double a_perp, double vsf, int what,
+                                         double *out, void *stream) {
+    B200_REQUIRE(velocity != nullptr && out != nullptr && m >= 1 && n >= 1, "bad arguments");
+    const size_t N = (size_t)m * n;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (velocity_dtype == B200_F32) return bps_launch<float>(velocity, N, a_par, a_perp, vsf, what, out, s);
+    if (velocity_dtype == B200_F64) return bps_launch<double>(velocity, N, a_par, a_perp, vsf, what, out, s);
+    b200::set_error("unknown velocity dtype %d", velocity_dtype);
+    return B200_EINVAL;
+}

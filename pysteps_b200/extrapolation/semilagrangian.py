@@ -21,6 +21,7 @@ import numpy as np
 import torch
 
 from .. import _device, _lib
+from ..noise import motion as _bps
 
 _MODES = {"constant": _lib.MODE_CONSTANT, "nearest": _lib.MODE_NEAREST}
 
@@ -97,9 +98,12 @@ def extrapolate(precip, velocity, timesteps, outval=np.nan, xy_coords=None,
         raise ValueError("velocity must be a three-dimensional array")
 
     _device.require_cuda()
-    on_device = _device.is_device_tensor(velocity)
+    # `velocity + generate_bps(...)` of pysteps_b200.noise.motion (nowcasts/utils.py:448-451):
+    # the perturbed field is produced on the device, directly in the trajectory kernel's layout
+    perturbed = isinstance(velocity, _bps.PerturbedVelocity)
+    on_device = _device.is_device_tensor(precip) if perturbed else _device.is_device_tensor(velocity)
 
-    d_vel = _field_tensor(velocity)
+    d_vel = velocity.device_interleaved() if perturbed else _field_tensor(velocity)
     d_precip = None if precip is None else _field_tensor(precip)
 
     # semilagrangian.py:112-123 -- finiteness checks, as device reductions.  Only ENQUEUED here:
@@ -184,7 +188,8 @@ def _extrapolate_checked(precip, velocity, d_precip, d_vel, stats, on_device, ti
         outval = stats.get()[0][1]  # np.nanmin(precip), :171-172
 
     m, n = int(velocity.shape[1]), int(velocity.shape[2])
-    if d_vel.shape[0] != 2:
+    interleaved = isinstance(velocity, _bps.PerturbedVelocity)
+    if velocity.shape[0] != 2:
         raise ValueError("velocity must have shape (2, m, n)")
     if d_precip is not None and tuple(d_precip.shape) != (m, n):
         raise ValueError("precip and velocity have incompatible shapes")
@@ -216,9 +221,9 @@ def _extrapolate_checked(precip, velocity, d_precip, d_vel, stats, on_device, ti
     # The library re-lays the field out as (m,n) float64 pairs internally.  While a Trace is
     # active (bench.py / profiling) the re-layout is issued as its own C call so that the
     # trajectory kernel is timed alone.
-    layout = _lib.LAYOUT_PLANAR
+    layout = _lib.LAYOUT_INTERLEAVED if interleaved else _lib.LAYOUT_PLANAR
     d_v = d_vel
-    if _lib._trace is not None:
+    if _lib._trace is not None and not interleaved:
         d_v = torch.empty((m, n, 2), dtype=d_vel.dtype, device="cuda")
         _lib.call("b200_sl_interleave_velocity", d_vel.data_ptr(), _device.dtype_code(d_vel.dtype),
                   m, n, d_v.data_ptr(), _device.stream_ptr())
@@ -235,7 +240,14 @@ def _extrapolate_checked(precip, velocity, d_precip, d_vel, stats, on_device, ti
         out, disp = d_out, d_disp
     else:
         out = None if d_out is None else _device.to_host(d_out)
-        disp = None if d_disp is None else _device.to_host(d_disp)
+        if d_disp is None:
+            disp = None
+        elif kwargs.get("b200_resident", False):
+            # extension: the displacement is only ever handed back as displacement_prev
+            # (nowcasts/utils.py:442-458) -- leave it in HBM, 2 x 32 MB of PCIe per call at 2048^2
+            disp = _device.DeviceField(d_disp)
+        else:
+            disp = _device.to_host(d_disp)
 
     if verbose:
         torch.cuda.current_stream().synchronize()

@@ -4,6 +4,7 @@ pysteps has no entry-point discovery for motion / extrapolation methods; the
 "plugin API" is the module-level dict read by ``get_method``:
   pysteps/extrapolation/interface.py:107-111  ``_extrapolation_methods``
   pysteps/motion/interface.py:36-46           ``_methods``
+  pysteps/noise/interface.py:24-45            ``_noise_methods``  ("bps": the velocity perturbator)
 ``register()`` inserts the B200 callables under new names and, on request,
 under the stock names so that ``nowcasts.steps`` (which fetches the
 extrapolator by name at pysteps/nowcasts/steps.py:656 and
@@ -15,7 +16,10 @@ def methods():
     """name -> callable for everything this package provides."""
     from .extrapolation import semilagrangian
 
-    out = {"extrapolation": {"semilagrangian_b200": semilagrangian.extrapolate}, "motion": {}}
+    from .noise import motion as bps
+
+    out = {"extrapolation": {"semilagrangian_b200": semilagrangian.extrapolate}, "motion": {},
+           "noise": {"bps_b200": (bps.initialize_bps, bps.generate_bps)}}
     try:
         from .motion import lucaskanade
         out["motion"]["lk_b200"] = lucaskanade.dense_lucaskanade
@@ -35,11 +39,13 @@ def register(override=False):
 
     override=False: only the ``*_b200`` names are added (the identity checks of
     pysteps/tests/test_interfaces.py keep passing).  override=True additionally
-    replaces ``"semilagrangian"``, ``"lk"``/``"lucaskanade"`` and ``"vet"``.
+    replaces ``"semilagrangian"``, ``"lk"``/``"lucaskanade"``, ``"vet"`` and the noise
+    method ``"bps"``.
     Returns the list of registered names.
     """
     import pysteps.extrapolation.interface as ei
     import pysteps.motion.interface as mi
+    import pysteps.noise.interface as ni
 
     done = []
     m = methods()
@@ -55,4 +61,10 @@ def register(override=False):
         if override:
             mi._methods[name.replace("_b200", "")] = fn
             done.append("motion:" + name.replace("_b200", ""))
+    for name, fns in m["noise"].items():
+        ni._noise_methods[name] = fns
+        done.append("noise:" + name)
+        if override:
+            ni._noise_methods[name.replace("_b200", "")] = fns
+            done.append("noise:" + name.replace("_b200", ""))
     return done
