@@ -107,14 +107,17 @@ int b200_sl_interleave_velocity(const void *velocity, int velocity_dtype, int m,
  *                               upload per member and time step
  *   B200_BPS_FIELD_PLANAR       V + p as (2,m,n)
  *   B200_BPS_PERTURBATION       p as (2,m,n)       (the value of generate_bps)
- *   B200_BPS_UNIT               V/|V| as (2,m,n)   (perturbator["V_par"]; a, b, vsf unused) */
+ *   B200_BPS_UNIT               V/|V| as (2,m,n)   (perturbator["V_par"]; a, b, vsf unused)
+ * n_nonfinite (device, may be NULL) receives the number of non-finite output elements -- the
+ * np.isfinite(velocity) check of extrapolation/semilagrangian.py:116-123 on the field the
+ * reference would have been given -- without another pass over it. */
 #define B200_BPS_FIELD_INTERLEAVED 0
 #define B200_BPS_FIELD_PLANAR 1
 #define B200_BPS_PERTURBATION 2
 #define B200_BPS_UNIT 3
 int b200_bps_perturb_velocity(const void *velocity, int velocity_dtype, int m, int n,
                               double a_par, double a_perp, double vsf, int what, double *out,
-                              void *stream);
+                              double *n_nonfinite, void *stream);
 
 /* Same operation on HOST buffers: allocates device scratch from the stream
  * ordered pool, copies in, runs, copies out and synchronises.  This is the

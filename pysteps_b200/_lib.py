@@ -38,7 +38,7 @@ _SIGNATURES = {
                                          c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "b200_sl_interleave_velocity": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "b200_bps_perturb_velocity": (c_int, [c_void_p, c_int, c_int, c_int, c_double, c_double, c_double,
-                                          c_int, c_void_p, c_void_p]),
+                                          c_int, c_void_p, c_void_p, c_void_p]),
     "b200_sl_extrapolate_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_dp, c_int,
                                          c_double, c_int, c_double, c_int, c_int, c_int, c_int,
                                          c_int, c_void_p, c_void_p]),

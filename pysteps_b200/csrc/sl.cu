@@ -510,8 +510,9 @@ extern "C" int b200_sl_interleave_velocity(const void *velocity, int velocity_dt
 template <typename F, int WHAT>
 __global__ void __launch_bounds__(256)
 bps_perturb_kernel(const F *__restrict__ V, double *__restrict__ out, size_t N, double a, double b,
-                   double vsf) {
+                   double vsf, double *__restrict__ n_nonfinite) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
+    int bad = 0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
         const F vx = __ldg(V + i), vy = __ldg(V + N + i);
         double nx, ny;
@@ -538,6 +539,8 @@ bps_perturb_kernel(const F *__restrict__ V, double *__restrict__ out, size_t N, 
                 oy = __dadd_rn((double)vy, oy);
             }
         }
+        bad += !isfinite(ox);
+        bad += !isfinite(oy);
         if (WHAT == B200_BPS_FIELD_INTERLEAVED) {
             reinterpret_cast<double2 *>(out)[i] = make_double2(ox, oy);
         } else {
@@ -545,22 +548,28 @@ bps_perturb_kernel(const F *__restrict__ V, double *__restrict__ out, size_t N, 
             out[N + i] = oy;
         }
     }
+    // number of non-finite output elements (the check of semilagrangian.py:116-123 on the
+    // perturbed field) -- exact in a double up to 2^53; atomics only in the rare bad case
+    if (n_nonfinite != nullptr && __any_sync(0xffffffffu, bad != 0)) {
+        if (bad) atomicAdd(n_nonfinite, (double)bad);
+    }
 }
 
 template <typename F>
 static int bps_launch(const void *velocity, size_t N, double a, double b, double vsf, int what, double *out,
-                      cudaStream_t s) {
+                      double *nnf, cudaStream_t s) {
+    if (nnf) B200_CUDA(cudaMemsetAsync(nnf, 0, sizeof(double), s));
     const int blocks = (int)std::min<size_t>((N + 255) / 256, (size_t)b200::num_sms() * 16);
     const F *V = (const F *)velocity;
     switch (what) {
     case B200_BPS_FIELD_INTERLEAVED:
-        bps_perturb_kernel<F, B200_BPS_FIELD_INTERLEAVED><<<blocks, 256, 0, s>>>(V, out, N, a, b, vsf); break;
+        bps_perturb_kernel<F, B200_BPS_FIELD_INTERLEAVED><<<blocks, 256, 0, s>>>(V, out, N, a, b, vsf, nnf); break;
     case B200_BPS_FIELD_PLANAR:
-        bps_perturb_kernel<F, B200_BPS_FIELD_PLANAR><<<blocks, 256, 0, s>>>(V, out, N, a, b, vsf); break;
+        bps_perturb_kernel<F, B200_BPS_FIELD_PLANAR><<<blocks, 256, 0, s>>>(V, out, N, a, b, vsf, nnf); break;
     case B200_BPS_PERTURBATION:
-        bps_perturb_kernel<F, B200_BPS_PERTURBATION><<<blocks, 256, 0, s>>>(V, out, N, a, b, vsf); break;
+        bps_perturb_kernel<F, B200_BPS_PERTURBATION><<<blocks, 256, 0, s>>>(V, out, N, a, b, vsf, nnf); break;
     case B200_BPS_UNIT:
-        bps_perturb_kernel<F, B200_BPS_UNIT><<<blocks, 256, 0, s>>>(V, out, N, a, b, vsf); break;
+        bps_perturb_kernel<F, B200_BPS_UNIT><<<blocks, 256, 0, s>>>(V, out, N, a, b, vsf, nnf); break;
     default:
         b200::set_error("unknown BPS output selector %d", what);
         return B200_EINVAL;
@@ -571,12 +580,12 @@ static int bps_launch(const void *velocity, size_t N, double a, double b, double
 
 extern "C" int b200_bps_perturb_velocity(const void *velocity, int velocity_dtype, int m, int n,
                                          double a_par, double a_perp, double vsf, int what,
-                                         double *out, void *stream) {
+                                         double *out, double *n_nonfinite, void *stream) {
     B200_REQUIRE(velocity != nullptr && out != nullptr && m >= 1 && n >= 1, "bad arguments");
     const size_t N = (size_t)m * n;
     cudaStream_t s = (cudaStream_t)stream;
-    if (velocity_dtype == B200_F32) return bps_launch<float>(velocity, N, a_par, a_perp, vsf, what, out, s);
-    if (velocity_dtype == B200_F64) return bps_launch<double>(velocity, N, a_par, a_perp, vsf, what, out, s);
+    if (velocity_dtype == B200_F32) return bps_launch<float>(velocity, N, a_par, a_perp, vsf, what, out, n_nonfinite, s);
+    if (velocity_dtype == B200_F64) return bps_launch<double>(velocity, N, a_par, a_perp, vsf, what, out, n_nonfinite, s);
     b200::set_error("unknown velocity dtype %d", velocity_dtype);
     return B200_EINVAL;
 }

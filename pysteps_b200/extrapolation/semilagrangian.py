@@ -74,8 +74,9 @@ class _Stats:
         self.buf = torch.empty((len(tensors), 4), dtype=torch.float64, device="cuda")
         s = _device.stream_ptr()
         for i, t in enumerate(tensors):
-            _lib.call("b200_field_stats", t.data_ptr(), _device.dtype_code(t.dtype), t.numel(),
-                      self.buf[i].data_ptr(), s)
+            if t is not None:  # None: the row is filled by the kernel that produces the field
+                _lib.call("b200_field_stats", t.data_ptr(), _device.dtype_code(t.dtype), t.numel(),
+                          self.buf[i].data_ptr(), s)
         self.host = None
 
     def get(self):
@@ -103,14 +104,19 @@ def extrapolate(precip, velocity, timesteps, outval=np.nan, xy_coords=None,
     perturbed = isinstance(velocity, _bps.PerturbedVelocity)
     on_device = _device.is_device_tensor(precip) if perturbed else _device.is_device_tensor(velocity)
 
-    d_vel = velocity.device_interleaved() if perturbed else _field_tensor(velocity)
     d_precip = None if precip is None else _field_tensor(precip)
 
     # semilagrangian.py:112-123 -- finiteness checks, as device reductions.  Only ENQUEUED here:
     # the verdict is read after the trajectory kernel has been launched (below), so a call costs
     # one host<->device round trip instead of two.  Error precedence is the reference's: a
     # finiteness error outranks every later argument error.
-    stats = _Stats(*([d_vel] if d_precip is None else [d_precip, d_vel]))
+    if perturbed:
+        # the producing kernel counts the non-finite elements of the perturbed field itself
+        stats = _Stats(*([None] if d_precip is None else [d_precip, None]))
+        d_vel = velocity.device_interleaved(stats.buf[-1, 0:1])
+    else:
+        d_vel = _field_tensor(velocity)
+        stats = _Stats(*([d_vel] if d_precip is None else [d_precip, d_vel]))
 
     def finiteness_errors():
         st = stats.get()

@@ -57,12 +57,13 @@ class _BaseField:
                   self.tensor.numel(), st.data_ptr(), _device.stream_ptr())
         self.finite = float(st[0].item()) == 0.0
 
-    def run(self, a, b, vsf, what):
+    def run(self, a, b, vsf, what, n_nonfinite=None):
         _, m, n = self.shape
         shape = (m, n, 2) if what == _FIELD_INTERLEAVED else (2, m, n)
         out = torch.empty(shape, dtype=torch.float64, device="cuda")
         _lib.call("b200_bps_perturb_velocity", self.tensor.data_ptr(), _device.dtype_code(self.tensor.dtype),
-                  m, n, float(a), float(b), float(vsf), what, out.data_ptr(), _device.stream_ptr())
+                  m, n, float(a), float(b), float(vsf), what, out.data_ptr(), _device.ptr(n_nonfinite),
+                  _device.stream_ptr())
         return out
 
 
@@ -165,9 +166,11 @@ class PerturbedVelocity(_Handle):
         self.pert = pert
         self.shape = pert.shape
 
-    def device_interleaved(self):
+    def device_interleaved(self, n_nonfinite=None):
+        """(m,n,2) float64 field for the trajectory kernel; `n_nonfinite` (a device float64)
+        receives the count of non-finite elements."""
         p = self.pert
-        return p.field.run(p.a, p.b, p.vsf, _FIELD_INTERLEAVED)
+        return p.field.run(p.a, p.b, p.vsf, _FIELD_INTERLEAVED, n_nonfinite)
 
     def device_planar(self):
         p = self.pert

@@ -130,6 +130,15 @@ def test_argument_errors(b200):
     bad[0, 1, 1] = np.nan
     with pytest.raises(ValueError, match="infs or NaNs"):
         init(bad, 1, 1)
+    # an overflowing perturbation makes the advection field non-finite: the extrapolator's own
+    # check (semilagrangian.py:118-119) fires on the field the kernel produced
+    _, gen = b200.noise.get_method("bps")
+    pert = init(v, 1, 1, p_par=(1e308, 1.0, 0.0), seed=1)
+    extrap = b200.extrapolation.get_method("semilagrangian")
+    with pytest.raises(ValueError, match="velocity contains non-finite values"):
+        extrap(np.ones((4, 4)), v + gen(pert, 100.0), 1)
+    with pytest.raises(ValueError, match="velocity contains only non-finite values"):  # :122-123
+        extrap(np.ones((4, 4)), v + gen(pert, 100.0), 1, allow_nonfinite_values=True)
     with pytest.raises(TypeError):
         b200.noise.get_method(None)
     with pytest.raises(ValueError, match="Unknown method"):
