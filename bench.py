@@ -362,12 +362,25 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timing ------------------------------------------------------
-    # the clock sampler spans warm-up, the timed steps and the end-to-end leg (a 20 ms polling
-    # period was measured to slow a 6 ms step by 3 ms: queries and launches share a driver lock)
+    # The clock sampler (nvidia-smi -lms 200, one per job) spans the warm-up and the timed steps and
+    # is stopped before the end-to-end leg: every poll holds a driver lock that launches and copies
+    # also take (a 20 ms period was measured to slow a 6 ms step by 3 ms, a 200 ms period the
+    # 10.7 ms end-to-end step by 3.7 ms).  The warm-up is stretched to >= 0.5 s of the same load
+    # so that the median is over several samples under load although the timed region is short.
     clocks = ClockSampler(local, enabled=(rank == 0))
     clocks.__enter__()
-    for _ in range(args.warmup):
+    t_w, n_w = time.perf_counter(), 0
+    while True:
         step_device()
+        torch.cuda.synchronize()
+        n_w += 1
+        done = n_w >= args.warmup and (n_w >= 400 or time.perf_counter() - t_w >= 0.5)
+        if world > 1:  # rank 0 decides, so every rank runs the same number of steps
+            flag = torch.tensor([int(done)], device="cuda")
+            dist.broadcast(flag, src=0)
+            done = bool(flag.item())
+        if done:
+            break
     barrier()
     launches0 = _lib.load().b200_launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -380,6 +393,7 @@ def run_ours(args):
             step_device()
             e.record()
         barrier()
+    clocks.__exit__(None, None, None)
     launches = _lib.load().b200_launch_count() - launches0
     dev_ms = sum(s.elapsed_time(e) for s, e in ev)
     tr = trace.summary()
@@ -398,7 +412,6 @@ def run_ours(args):
         out = step_host()
     barrier()
     e2e_s = time.perf_counter() - t0
-    clocks.__exit__(None, None, None)
     e2e_s = _shard.max_over_ranks(e2e_s, device="cuda")
     e2e_val = nfields * args.steps * T_LEAD * M * N_ / e2e_s / 1e6
     # LK: frames up, field down, field up again for the extrapolator (plugin API is NumPy)
