@@ -6,12 +6,14 @@ extrapolation.
     python bench.py --gpus N --steps K --warmup W          (ours, CUDA)
     python bench.py --impl reference ...                   (CPU oracle port, host cores)
 
-One "step" = one pass of the hot path over one batch of synthetic input:
-  [rank 0] motion field from the last frames (dense Lucas-Kanade)         (when built)
-  [N > 1]  NCCL broadcast of the motion field (the only collective)
-  [all]    12-leadtime semi-Lagrangian extrapolation of this rank's field
-Metric: Mpix/s advected = (N * T * m * n) / step time, max over ranks (weak scaling:
-per-GPU work is fixed, one field per GPU, as ensemble members shard in nowcasts.steps).
+One "step" = one pass of the hot path over one batch of synthetic input, on every rank:
+  motion field from this rank's last three frames (dense Lucas-Kanade),
+  12-leadtime semi-Lagrangian extrapolation of this rank's field with it.
+Metric: Mpix/s advected = (N * T * m * n) / step time, max over ranks (weak scaling: N
+independent nowcasts, one per GPU, no collective on the data path).
+Other workloads (--workload): ensemble24 (24 BPS-perturbed members round-robin over the GPUs,
+one NCCL broadcast of the motion field), composite4096 (one 4096^2 composite, output row bands
+over the GPUs, NCCL all-gather of the motion-field bands), vet_sl12_2048.
 
 value  : inputs resident in HBM, device time by CUDA events, L2 flushed between steps.
 e2e    : the same step through the public NumPy API with pinned HOST buffers, H2D and
@@ -284,6 +286,13 @@ def run_ours(args):
             Vband = motion(frames_d, interp_kwargs={"b200_rows": band})
             Vd = _shard.gather_row_bands(Vband, M, world, rank)
             return extrap(precip_d, Vd, T_LEAD, **ekw)
+        if lk and SCALING == "weak":
+            # independent nowcasts: every rank estimates the motion of ITS frames and advects ITS
+            # field -- no collective on the data path
+            Vd = motion(frames_d)
+            if not torch.is_tensor(Vd):
+                Vd = torch.from_numpy(np.ascontiguousarray(Vd)).cuda()
+            return extrap(precip_d, Vd, T_LEAD)
         if lk:
             if rank == 0:
                 Vd = motion(frames_d)
@@ -345,8 +354,10 @@ def run_ours(args):
         if lk and band is not None and world > 1 and MOTION == "lk":
             Vband = motion(frames_h, interp_kwargs={"b200_rows": band})  # NumPy band
             Vh = _shard.gather_row_bands(torch.from_numpy(Vband).cuda(), M, world, rank).cpu().numpy()
+        elif lk and SCALING == "weak":
+            Vh = motion(frames_h)  # NumPy (2,m,n) float64, as pysteps returns; independent per rank
         elif lk:
-            Vh = motion(frames_h) if rank == 0 else None  # NumPy (2,m,n) float64, as pysteps returns
+            Vh = motion(frames_h) if rank == 0 else None
             if world > 1:
                 Vd = torch.from_numpy(Vh).cuda() if rank == 0 else \
                     torch.empty((2, M, N_), dtype=torch.float64, device="cuda")
@@ -454,11 +465,13 @@ def run_ours(args):
                          "OpenCV-exact LK stages", "data": "synthetic",
                 "config": {"workload": workload_name(lk), "frame": [M, N_], "leadtimes": T_LEAD,
                            "fields_per_gpu": 1 if SCALING == "weak" else round(1.0 / world, 4), "l2": "flushed between timed steps (256 MB fill)",
-                           "parallelism": (f"1 field per GPU x{world}" if SCALING == "weak" else
-                                           f"output row bands over {world} GPU(s), inputs replicated")
-                           + (", NCCL all-gather of the motion-field bands" if (SCALING == "strong" and not MEMBERS
-                                                                               and world > 1 and MOTION == "lk")
-                              else ", NCCL broadcast of the motion field")},
+                           "parallelism": (
+                               f"{world} independent nowcast(s), one per GPU, no collective" if SCALING == "weak" else
+                               f"{MEMBERS} members round-robin over {world} GPU(s), NCCL broadcast of the motion field"
+                               if MEMBERS else
+                               f"output row bands over {world} GPU(s), inputs replicated"
+                               + (", NCCL all-gather of the motion-field bands" if world > 1 and MOTION == "lk"
+                                  else ""))},
                 "clocks": clocks.summary(),
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / args.steps},
