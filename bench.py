@@ -415,7 +415,9 @@ def run_ours(args):
     value = nfields * args.steps * T_LEAD * M * N_ / (dev_ms * 1e-3) / 1e6
 
     # ---- end-to-end timing (host buffers) --------------------------------------------
-    for _ in range(max(3, args.warmup // 2)):  # pinned-buffer allocation happens on the first calls
+    # the pinned host pool (torch's caching host allocator: one cudaHostAlloc per new block, tens of
+    # ms for a 200 MB result) reaches its steady state after a few calls
+    for _ in range(max(6, args.warmup)):
         step_host()
     barrier()
     t0 = time.perf_counter()
@@ -423,6 +425,14 @@ def run_ours(args):
         out = step_host()
     barrier()
     e2e_s = time.perf_counter() - t0
+    if os.environ.get("BENCH_E2E_BREAKDOWN") and lk and not MEMBERS:  # diagnostic only
+        tm = te = 0.0
+        for _ in range(args.steps):
+            a = time.perf_counter(); Vx = motion(frames_h); b = time.perf_counter()
+            out = extrap(precip_h, Vx, T_LEAD); c = time.perf_counter()
+            tm += b - a; te += c - b
+        print(f"e2e breakdown: loop {1e3 * e2e_s / args.steps:.2f} ms/step; motion {1e3 * tm / args.steps:.2f} "
+              f"extrap {1e3 * te / args.steps:.2f}", file=sys.stderr)
     e2e_s = _shard.max_over_ranks(e2e_s, device="cuda")
     e2e_val = nfields * args.steps * T_LEAD * M * N_ / e2e_s / 1e6
     # LK: frames up, field down, field up again for the extrapolator (plugin API is NumPy)

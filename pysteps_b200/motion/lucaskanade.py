@@ -90,6 +90,20 @@ def _track_image(f, m, n, buffer_mask):
 
 
 _side_streams = {}
+_grids = {}
+
+
+def _pixel_grid(a, b):
+    """np.arange(a, b) as a float64 device vector (lucaskanade.py:271-272), built once."""
+    key = (torch.cuda.current_device(), a, b)
+    g = _grids.get(key)
+    if g is None:
+        if len(_grids) > 64:
+            _grids.clear()
+        g = _grids[key] = _device.to_device(np.arange(a, b, dtype=np.float64))
+        torch.cuda.current_stream().synchronize()
+    return g
+
 
 
 def _side_stream():
@@ -334,8 +348,7 @@ def dense_lucaskanade(input_images, lk_kwargs=None, fd_method="shitomasi", fd_kw
         if n < 2 or m < 2:
             raise ValueError("Shape of array too small to calculate a numerical gradient, "
                              "at least (edge_order + 1) elements are required.")
-        xgrid = torch.arange(n, dtype=torch.float64, device="cuda")
-        ygrid = torch.arange(r0, r1, dtype=torch.float64, device="cuda")
+        xgrid, ygrid = _pixel_grid(0, n), _pixel_grid(r0, r1)
         # integer pixel grid + corner coordinates that are integers or cell medians (multiples
         # of 1/2): squared distances are exact small multiples of 1/256 -> packed-key fast path
         on_grid = bool(np.all(xy_h * 16.0 == np.rint(xy_h * 16.0)) and np.abs(xy_h).max() < 16384.0
