@@ -153,6 +153,40 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.samples)}
 
 
+def stage_rooflines(trace_ms, steps, m, n, peak_gbs, sl_bytes):
+    """Per C-ABI call of the step: algorithmic bytes per call (SURVEY.md section 8d figures, with
+    the float64 frames this implementation keeps), achieved GB/s over the CUDA-event time of
+    the call, fraction of the HBM peak, and what actually bounds it (from the ncu captures in
+    profiles/).  `trace_ms` = {name: [ms of every call in the timed region]}."""
+    px = m * n
+    table = {
+        "b200_idw_fill": (16 * px, "alu/latency: exhaustive-in-tile k-NN with register-resident sorted lists"),
+        "b200_sl_extrapolate_rows": (sl_bytes, "L1 wavefronts + FP64 pipe (reference-order float64 trajectories)"),
+        "b200_min_eig": (5 * px, "latency: one sequential FP64 running sum per column (OpenCV-exact box filter)"),
+        "b200_quantise_u8": (10 * px, "hbm/l2 streaming"),
+        "b200_mask_invalid": (9 * px, "hbm streaming + reduction"),
+        "b200_morph_opening": (17 * px, "hbm/l2 streaming stencil"),
+        "b200_masked_minmax": (9 * px, "hbm streaming reduction"),
+        "b200_lk_track": (None, "latency: ordered float32 window sums, one CTA per feature"),
+        "b200_good_features": (None, "latency: sort + ordered greedy selection"),
+        "b200_bps_perturb_velocity": (32 * px, "hbm streaming"),
+    }
+    out = []
+    for name, ms in trace_ms.items():
+        if name not in table or not ms:
+            continue
+        nbytes, bound = table[name]
+        avg = sum(ms) / len(ms)
+        row = {"call": name, "ms_per_call": avg, "calls_per_step": len(ms) / steps,
+               "algorithmic_bytes_per_call": nbytes, "bound": bound}
+        if nbytes is not None and avg > 0:
+            row["achieved_gbs"] = nbytes / (avg * 1e-3) / 1e9
+            row["frac_of_hbm_peak"] = row["achieved_gbs"] / peak_gbs
+        out.append(row)
+    out.sort(key=lambda r: -r["ms_per_call"] * r["calls_per_step"])
+    return out
+
+
 # ----------------------------------------------------------------------------- CPU legs
 def cpu_step(frames, precip, V, lk):
     """The oracle port of one step on host cores."""
@@ -456,6 +490,8 @@ def run_ours(args):
         vbytes = 8 if lk else 4  # LK returns float64 fields, synthetic V is float32
         rows_here = M if band is None else band[1] - band[0]
         alg_bytes = M * N_ * (2 * vbytes + 4) + rows_here * N_ * 4 * T_LEAD
+        if MEMBERS:  # single-step member calls: V 16 + precip 4 + displacement in/out 32 + out 4 B per pixel
+            alg_bytes = M * N_ * 56
         achieved = alg_bytes / (k_avg * 1e-3) / 1e9
         traffic = None
         try:
@@ -467,6 +503,10 @@ def run_ours(args):
                     "peak_source": peak_src, "kernel_ms": k_avg,
                     "algorithmic_bytes_per_launch": alg_bytes}
         stage_ms = {k: sum(v) / args.steps for k, v in tr.items()}
+        try:
+            stages = stage_rooflines(tr, args.steps, M, N_, peak, alg_bytes)
+        except Exception as exc:  # supplementary table only
+            stages = [{"error": repr(exc)}]
         cpu = cpu_baseline(frames_h, precip_h, V_h, have_lk_oracle()) if not args.no_cpu else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
@@ -486,7 +526,8 @@ def run_ours(args):
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / args.steps},
                 "gpu_launches": int(launches),
-                "roofline": roofline, "cpu_baseline": cpu, "stage_ms_per_step": stage_ms}
+                "roofline": roofline, "cpu_baseline": cpu, "stage_ms_per_step": stage_ms,
+                "stage_rooflines": stages}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

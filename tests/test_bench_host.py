@@ -1,0 +1,31 @@
+"""CPU tests of bench.py's host-side arithmetic (no GPU)."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+
+
+def test_stage_rooflines_table():
+    m = n = 2048
+    trace = {"b200_idw_fill": [0.9, 0.8], "b200_sl_extrapolate_rows": [0.5, 0.4],
+             "b200_lk_track": [0.4, 0.4, 0.4, 0.4], "b200_compact_rows": [0.01, 0.01], "b200_min_eig": []}
+    rows = bench.stage_rooflines(trace, 2, m, n, 6576.7, 285212672)
+    assert [r["call"] for r in rows] == ["b200_idw_fill", "b200_lk_track", "b200_sl_extrapolate_rows"]
+    idw = rows[0]
+    assert idw["calls_per_step"] == 1 and abs(idw["ms_per_call"] - 0.85) < 1e-12
+    assert idw["algorithmic_bytes_per_call"] == 16 * m * n
+    assert abs(idw["achieved_gbs"] - 16 * m * n / 0.85e-3 / 1e9) < 1e-9
+    assert abs(idw["frac_of_hbm_peak"] - idw["achieved_gbs"] / 6576.7) < 1e-15
+    assert rows[1]["calls_per_step"] == 2 and "achieved_gbs" not in rows[1]
+    json.dumps(rows)
+
+
+def test_workloads_and_metric_names():
+    for name, w in bench.WORKLOADS.items():
+        bench.set_workload(name)
+        assert bench.M == w["m"] and bench.T_LEAD == w["T"] and bench.SCALING in ("weak", "strong")
+        assert "Mpix/s" in bench.METRIC
+    bench.set_workload("lk_sl12_2048")
+    assert bench.MEMBERS == 0 and bench.workload_name(True) == "lk_dense+semilagrangian_T12_2048x2048"
