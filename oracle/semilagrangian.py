@@ -91,7 +91,8 @@ def extrapolate(precip, velocity, timesteps, outval=np.nan, xy_coords=None,
                                      ctypes.c_int64, ctypes.c_double, ctypes.c_int, _dp,
                                      ctypes.c_double, ctypes.c_int, ctypes.c_int, _dp, _dp]
     rc = L.ora_sl_extrapolate(_p(P), _p(V), m, n, _p(XY), _p(timestep_diff), T,
-                              float(vel_timestep), int(n_iter), _p(DP), float(outval),
+                              float(vel_timestep), int(n_iter), _p(DP),
+                              float(outval) if precip is not None else 0.0,  # cval unused without precip
                               _MODES[map_coordinates_mode],
                               int(velocity.dtype == np.float32), _p(out), _p(disp))
     if rc != 0:

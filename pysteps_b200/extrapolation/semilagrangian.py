@@ -132,18 +132,25 @@ def extrapolate(precip, velocity, timesteps, outval=np.nan, xy_coords=None,
         if st_v[0] == d_vel.numel():
             raise ValueError("velocity contains only non-finite values")
 
+    # warnings of the later stages are held back until the finiteness verdict is in: the
+    # reference raises those errors before it warns
+    deferred = []
     try:
         result = _extrapolate_checked(precip, velocity, d_precip, d_vel, stats, on_device, timesteps,
-                                      outval, xy_coords, vel_timestep, kwargs)
+                                      outval, xy_coords, vel_timestep, kwargs, deferred)
     except Exception:
         finiteness_errors()  # raises first if the reference would have
+        for msg in deferred:
+            warnings.warn(msg, stacklevel=2)
         raise
     finiteness_errors()
+    for msg in deferred:
+        warnings.warn(msg, stacklevel=2)
     return result
 
 
 def _extrapolate_checked(precip, velocity, d_precip, d_vel, stats, on_device, timesteps, outval,
-                         xy_coords, vel_timestep, kwargs):
+                         xy_coords, vel_timestep, kwargs, deferred_warnings):
     """semilagrangian.py:125-266 (everything after the finiteness checks)."""
     if isinstance(timesteps, list) and not sorted(timesteps) == timesteps:
         raise ValueError("timesteps is not in ascending order")
@@ -164,9 +171,7 @@ def _extrapolate_checked(precip, velocity, d_precip, d_vel, stats, on_device, ti
         raise ValueError("precip is None but return_displacement is False")
 
     if "D_prev" in kwargs.keys():
-        warnings.warn(
-            "deprecated argument D_prev is ignored, use displacement_prev instead",
-        )
+        deferred_warnings.append("deprecated argument D_prev is ignored, use displacement_prev instead")
 
     if interp_order != 1:
         raise NotImplementedError(
@@ -237,7 +242,9 @@ def _extrapolate_checked(precip, velocity, d_precip, d_vel, stats, on_device, ti
     _lib.call("b200_sl_extrapolate_rows",
               _device.ptr(d_precip), d_v.data_ptr(), _device.ptr(d_xy), _device.ptr(d_prev),
               timestep_diff.ctypes.data_as(_lib.c_dp), T, float(vel_timestep),
-              max(int(n_iter), 0), float(outval), _MODES[map_coordinates_mode],
+              max(int(n_iter), 0),
+              float(outval) if d_precip is not None else 0.0,  # cval is unused without precip (:171-172)
+              _MODES[map_coordinates_mode],
               _device.dtype_code(d_vel.dtype), layout,
               _device.dtype_code(d_precip.dtype) if d_precip is not None else _lib.F64,
               m, n, r0, mb, _device.ptr(d_out), _device.ptr(d_disp), _device.stream_ptr())

@@ -1,0 +1,149 @@
+"""TEST INFRASTRUCTURE: run the HOST side of pysteps_b200 (argument handling, validation order,
+dtype / shape logic, lazy handles) on a machine without a GPU, by standing the oracle in for the
+C-ABI entry points the semi-Lagrangian and BPS paths call.  Numerically this proves nothing about
+the CUDA kernels (that is what the `-m gpu` tests are for); it lets the CPU suite compare the
+host logic with the live reference on thousands of argument combinations.
+
+    with cpu_abi.emulated():
+        out = pysteps_b200.extrapolation.semilagrangian.extrapolate(P, V, 3)
+"""
+import contextlib
+import ctypes
+from unittest import mock
+
+import numpy as np
+import torch
+
+from oracle import lib as oracle_lib
+from oracle import noise_motion as ora_bps
+from pysteps_b200 import _device, _lib
+
+_NP = {_lib.F32: np.float32, _lib.F64: np.float64}
+_C = {np.float32: ctypes.c_float, np.float64: ctypes.c_double}
+
+
+def _addr(p):
+    if p is None:
+        return None
+    if isinstance(p, int):
+        return p or None
+    return ctypes.cast(p, ctypes.c_void_p).value
+
+
+def _view(p, shape, dtype=np.float64):
+    a = _addr(p)
+    if a is None:
+        return None
+    n = int(np.prod(shape))
+    buf = (_C[dtype] * n).from_address(a)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+
+def _field_stats(ptr, code, numel, out, stream):
+    a = _view(ptr, (numel,), _NP[code])
+    o = _view(out, (4,))
+    fin = np.isfinite(a)
+    o[0] = float(np.count_nonzero(~fin))
+    nn = a[~np.isnan(a)]
+    o[1] = nn.min() if nn.size else np.nan
+    o[2] = nn.max() if nn.size else np.nan
+    o[3] = float(np.count_nonzero(np.isnan(a)))
+
+
+def _sl_rows(precip, velocity, xy, disp_prev, tdiff, T, vts, n_iter, outval, mode, vdt, layout, pdt,
+             m, n, r0, rows, out, disp_out, stream):
+    vt, pt = _NP[vdt], _NP[pdt]
+    if layout == _lib.LAYOUT_INTERLEAVED:
+        V = np.ascontiguousarray(np.moveaxis(_view(velocity, (m, n, 2), vt), 2, 0), dtype=np.float64)
+    else:
+        V = np.ascontiguousarray(_view(velocity, (2, m, n), vt), dtype=np.float64)
+    P = _view(precip, (m, n), pt)
+    P = None if P is None else np.ascontiguousarray(P, dtype=np.float64)
+    XY = _view(xy, (2, m, n))
+    DP = None
+    if _addr(disp_prev) is not None:
+        DP = np.zeros((2, m, n))
+        DP[:, r0:r0 + rows] = _view(disp_prev, (2, rows, n))
+    td = np.ascontiguousarray(_view(tdiff, (T,)))
+    full = None if P is None else np.empty((T, m, n))
+    disp = np.empty((2, m, n))
+    L = oracle_lib()
+    dp = ctypes.POINTER(ctypes.c_double)
+    L.ora_sl_extrapolate.restype = ctypes.c_int
+    L.ora_sl_extrapolate.argtypes = [dp, dp, ctypes.c_int64, ctypes.c_int64, dp, dp, ctypes.c_int64,
+                                     ctypes.c_double, ctypes.c_int, dp, ctypes.c_double, ctypes.c_int,
+                                     ctypes.c_int, dp, dp]
+    p = lambda a: None if a is None else a.ctypes.data_as(dp)  # noqa: E731
+    rc = L.ora_sl_extrapolate(p(P), p(V), m, n, p(XY), p(td), T, vts, n_iter, p(DP), outval, mode,
+                              int(vt is np.float32), p(full), p(disp))
+    assert rc == 0
+    if full is not None:
+        _view(out, (T, rows, n), pt)[...] = full[:, r0:r0 + rows].astype(pt)
+    if _addr(disp_out) is not None:
+        _view(disp_out, (2, rows, n))[...] = disp[:, r0:r0 + rows]
+
+
+def _bps(velocity, code, m, n, a, b, vsf, what, out, nnf, stream):
+    V = _view(velocity, (2, m, n), _NP[code])
+    unit = np.zeros((2, m, n))
+    with np.errstate(all="ignore"):
+        speed = np.sqrt(V[0] * V[0] + V[1] * V[1])
+        ok = speed > 1e-12
+        for c in range(2):
+            q = np.zeros((m, n), dtype=V.dtype)
+            np.divide(V[c], speed, out=q, where=ok)
+            unit[c] = q
+        pert = (a * unit + b * np.stack([-unit[1], unit[0]])) / vsf
+        res = {0: V + pert, 1: V + pert, 2: pert, 3: unit}[what]
+    if what == 0:
+        _view(out, (m, n, 2))[...] = np.moveaxis(res, 0, 2)
+    else:
+        _view(out, (2, m, n))[...] = res
+    if _addr(nnf) is not None:
+        _view(nnf, (1,))[0] = float(np.count_nonzero(~np.isfinite(res)))
+
+
+_TABLE = {"b200_field_stats": _field_stats, "b200_sl_extrapolate_rows": _sl_rows,
+          "b200_bps_perturb_velocity": _bps}
+
+
+def _call(name, *args):
+    if name not in _TABLE:
+        raise NotImplementedError(f"cpu_abi: {name} is not emulated")
+    _TABLE[name](*args)
+
+
+def _to_device(a, dtype=None):
+    if isinstance(a, _device.DeviceField):
+        a = a.tensor
+    t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.array(a, order="C"))
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+class _Stream:
+    cuda_stream = 0
+
+    def synchronize(self):
+        pass
+
+
+@contextlib.contextmanager
+def emulated():
+    real_empty = torch.empty
+
+    def empty(*a, **k):
+        k.pop("device", None)
+        k.pop("pin_memory", None)
+        return real_empty(*a, **k)
+
+    with contextlib.ExitStack() as st:
+        st.enter_context(mock.patch.object(_device, "require_cuda", lambda: None))
+        st.enter_context(mock.patch.object(_device, "to_device", _to_device))
+        st.enter_context(mock.patch.object(_device, "to_host", lambda t: t.numpy()))
+        st.enter_context(mock.patch.object(_device, "stream_ptr", lambda: 0))
+        st.enter_context(mock.patch.object(_lib, "call", _call))
+        st.enter_context(mock.patch.object(torch, "empty", empty))
+        st.enter_context(mock.patch.object(torch.cuda, "current_stream", lambda *a: _Stream()))
+        yield

@@ -1,0 +1,171 @@
+"""CPU test of the HOST logic of pysteps_b200.extrapolation.semilagrangian.extrapolate and of the
+BPS handles: argument validation (order, types, messages), defaults, return structure, dtypes
+and shapes, over randomised valid AND invalid argument combinations -- against the live
+reference when /root/reference exists, else against the oracle.  The C ABI is emulated by the
+oracle (tests/cpu_abi.py), so numerics here say nothing about the kernels."""
+import warnings
+
+import numpy as np
+import pytest
+
+import cpu_abi
+from oracle import noise_motion as ora_bps
+from oracle import semilagrangian as ora
+
+
+def _reference():
+    from _refimport import available, ref_module
+    if available():
+        return ref_module("pysteps.extrapolation.semilagrangian").extrapolate, True
+    return ora.extrapolate, False
+
+
+def _bits_equal(a, b):
+    return (a.shape == b.shape and a.dtype == b.dtype
+            and np.array_equal(np.ascontiguousarray(a).view(np.uint8), np.ascontiguousarray(b).view(np.uint8)))
+
+
+def _random_call(rng):
+    m, n = int(rng.integers(1, 24)), int(rng.integers(1, 24))
+    pd = rng.choice([np.float64, np.float32])
+    vd = rng.choice([np.float64, np.float32])
+    P = (rng.standard_normal((m, n)) * 5).astype(pd)
+    scale = rng.choice([0.3, 1.0, 3.0, 15.0, 1e3])
+    V = (rng.standard_normal((2, m, n)) * scale).astype(vd)
+    kw = {}
+    r = rng.random
+    if r() < 0.25:
+        P[rng.random((m, n)) < 0.3] = np.nan
+    if r() < 0.05:
+        P[...] = np.nan
+    if r() < 0.1:
+        V[:, rng.random((m, n)) < 0.2] = rng.choice([np.nan, np.inf])
+    if r() < 0.03:
+        V[...] = np.nan
+    if r() < 0.45:
+        kw["allow_nonfinite_values"] = bool(r() < 0.8)
+    if r() < 0.5:
+        kw["n_iter"] = int(rng.integers(0, 4))
+    if r() < 0.5:
+        kw["map_coordinates_mode"] = str(rng.choice(["constant", "nearest"]))
+    if r() < 0.5:
+        kw["return_displacement"] = bool(r() < 0.8)
+    if r() < 0.3:
+        kw["displacement_prev"] = rng.standard_normal((2, m, n)) * scale
+    if r() < 0.2:
+        xx, yy = np.meshgrid(np.arange(n) + 0.25, np.arange(m) * rng.choice([1.0, 0.5]))
+        kw["xy_coords"] = np.stack([xx, yy])
+    if r() < 0.1:
+        kw["xy_coords"] = np.stack(np.meshgrid(np.arange(n), np.arange(m)))  # the default grid
+    if r() < 0.1:
+        kw["D_prev"] = None
+    if r() < 0.1:
+        kw["verbose"] = False
+    if r() < 0.1:
+        kw["interp_order"] = 1
+    outval = rng.choice([np.nan, 0.0, -15.0])
+    if r() < 0.2:
+        outval = "min"
+    q = r()
+    if q < 0.4:
+        ts = int(rng.integers(1, 4))
+    elif q < 0.8:
+        ts = sorted(set(np.round(rng.uniform(0.1, 4, int(rng.integers(1, 4))), 2).tolist()))
+        kw["vel_timestep"] = float(rng.choice([1.0, 0.5, 2.0]))
+    elif q < 0.87:
+        ts = [2.0, 1.0]                       # not ascending
+    elif q < 0.94:
+        ts = np.array([1.0, 1.0, 2.0])        # ndarray with a repeated element
+    else:
+        ts = np.array([0.5, 1.5])
+    q = r()
+    if q < 0.08:
+        Pin = None
+    elif q < 0.12:
+        Pin = P[None]                         # wrong rank
+    else:
+        Pin = P
+    Vin = V[0] if r() < 0.04 else V
+    return Pin, Vin, ts, outval, kw
+
+
+def _run(fn, Pin, Vin, ts, outval, kw):
+    cp = lambda v: v.copy() if isinstance(v, np.ndarray) else v  # noqa: E731
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        try:
+            res = fn(cp(Pin), cp(Vin), cp(ts), outval, **{k: cp(v) for k, v in kw.items()})
+            err = None
+        except Exception as e:  # noqa: BLE001
+            res, err = None, (type(e).__name__, str(e))
+    deprecations = sorted(str(x.message) for x in w if "D_prev" in str(x.message))
+    return res, err, deprecations
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_extrapolate_host_logic_matches_reference(seed):
+    import pysteps_b200
+    ref, live = _reference()
+    rng = np.random.default_rng(100 + seed)
+    n_err = n_ok = 0
+    with cpu_abi.emulated():
+        for it in range(120):
+            Pin, Vin, ts, outval, kw = _random_call(rng)
+            want, werr, wdep = _run(ref, Pin, Vin, ts, outval, kw)
+            got, gerr, gdep = _run(pysteps_b200.extrapolation.semilagrangian.extrapolate, Pin, Vin, ts, outval, kw)
+            ctx = f"seed {seed} case {it}: ts={ts!r} outval={outval!r} kw={ {k: (v.shape if isinstance(v, np.ndarray) else v) for k, v in kw.items()} }"
+            assert gerr == werr, ctx
+            assert gdep == wdep, ctx
+            if werr is not None:
+                n_err += 1
+                continue
+            n_ok += 1
+            assert isinstance(got, tuple) == isinstance(want, tuple), ctx
+            for a, b in zip(got if isinstance(got, tuple) else (got,), want if isinstance(want, tuple) else (want,)):
+                assert (a is None) == (b is None), ctx
+                if a is not None:
+                    assert isinstance(a, np.ndarray) and _bits_equal(a, b), ctx
+    assert n_err >= 10 and n_ok >= 40, (n_err, n_ok, live)
+
+
+def test_member_loop_with_handles_matches_reference_expression():
+    """nowcasts/utils.py:440-458 with lazy handles and resident displacements == the same loop
+    with materialised arrays (oracle perturbator + the reference / oracle extrapolator)."""
+    import pysteps_b200
+    from pysteps_b200 import _device
+    ref, _ = _reference()
+    rng = np.random.default_rng(5)
+    with cpu_abi.emulated():
+        init, gen = pysteps_b200.noise.get_method("bps")
+        extrap = pysteps_b200.extrapolation.get_method("semilagrangian")
+        for vd in (np.float64, np.float32):
+            V = (3 * rng.standard_normal((2, 19, 23))).astype(vd)
+            V[:, 4:7, 5:9] = 0
+            P = rng.standard_normal((19, 23))
+            P[2, 3] = np.nan
+            pg = init(V, 0.5, 5.0, randstate=np.random.RandomState(9))
+            po = ora_bps.initialize_bps(V, 0.5, 5.0, randstate=np.random.RandomState(9))
+            assert pg["eps_par"] == po["eps_par"] and pg["eps_perp"] == po["eps_perp"]
+            assert _bits_equal(pg["V_par"], po["V_par"]) and _bits_equal(pg["V_perp"], po["V_perp"])
+            dg = dr = None
+            for step in range(1, 4):
+                h = V + gen(pg, step * 5.0)
+                assert isinstance(h, pysteps_b200.noise.motion.PerturbedVelocity)
+                out_g, dg = extrap(P, h, [1.0], displacement_prev=dg, return_displacement=True,
+                                   allow_nonfinite_values=True, b200_resident=True)
+                assert isinstance(dg, _device.DeviceField) and dg.shape == (2, 19, 23)
+                out_r, dr = ref(P, V + ora_bps.generate_bps(po, step * 5.0), [1.0], displacement_prev=dr,
+                                return_displacement=True, allow_nonfinite_values=True)
+                assert _bits_equal(out_g, out_r) and _bits_equal(np.asarray(dg), dr)
+            assert _bits_equal(np.asarray(V + gen(pg, 7.0)), V + ora_bps.generate_bps(po, 7.0))
+        # non-finite perturbed field: the extrapolator's own check fires (semilagrangian.py:118-123)
+        v = np.ones((2, 4, 4))
+        pert = init(v, 1, 1, p_par=(1e308, 1.0, 0.0), seed=1)
+        with pytest.raises(ValueError, match="velocity contains non-finite values"):
+            extrap(np.ones((4, 4)), v + gen(pert, 100.0), 1)
+        with pytest.raises(ValueError, match="velocity contains only non-finite values"):
+            extrap(np.ones((4, 4)), v + gen(pert, 100.0), 1, allow_nonfinite_values=True)
+        bad = v.copy()
+        bad[0, 0, 0] = np.inf
+        with pytest.raises(ValueError, match="infs or NaNs"):
+            init(bad, 1, 1)

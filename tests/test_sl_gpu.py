@@ -97,6 +97,9 @@ def test_errors(sl):
         sl.extrapolate(P, V, 1, D_prev=None)
     out = sl.extrapolate(P, V, 1, some_unknown_kwarg=5)  # unknown kwargs ignored (:29,129-134)
     assert out.shape == (1, 8, 8)
+    # outval is only looked at when there is a field to warp (:171-172): "min" without precip is fine
+    none, disp = sl.extrapolate(None, V, 2, "min", return_displacement=True)
+    assert none is None and disp.shape == (2, 8, 8)
 
 
 @pytest.mark.parametrize("shape,kind,T", [((257, 301), "smooth", 6), ((300, 200), "rotation", 12),
