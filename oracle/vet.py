@@ -110,8 +110,14 @@ def get_padding(dimension_size, sectors):
 def vet(input_images, sectors=((32, 16, 4, 2), (32, 16, 4, 2)), smooth_gain=1e6, first_guess=None,
         intermediate_steps=False, verbose=False, indexing="yx", padding=0, options=None):
     """pysteps/motion/vet.py:302-648."""
+    # decorators.check_input_frames(2, 3), pysteps/decorators.py:121-146
     if input_images.ndim != 3:
-        raise ValueError("input_images dimension mismatch.")
+        raise ValueError("input_images dimension mismatch.\n"
+                         f"input_images.shape: {str(input_images.shape)}\n"
+                         "(t, x, y ) dimensions expected")
+    if 2 < input_images.shape[0] > 3:
+        raise ValueError(f"input_images frames {input_images.shape[0]} mismatch.\n"
+                         "Minimum frames: 2\nMaximum frames: 3\n")
     options = dict() if options is None else dict(options)
     options.setdefault("eps", 0.1)
     options.setdefault("gtol", 0.1)
@@ -119,7 +125,8 @@ def vet(input_images, sectors=((32, 16, 4, 2), (32, 16, 4, 2)), smooth_gain=1e6,
     options.setdefault("disp", False)
     method = options.pop("method", "CG")
     if indexing not in ["yx", "xy", "ij"]:
-        raise ValueError("Invalid indexing values: {0}\n".format(indexing))
+        raise ValueError("Invalid indexing values: {0}\n".format(indexing)
+                         + "Supported values: {0}".format(str(["yx", "xy", "ij"])))
     if not isinstance(input_images, MaskedArray):
         input_images = numpy.ma.masked_invalid(input_images)
     else:
@@ -137,11 +144,21 @@ def vet(input_images, sectors=((32, 16, 4, 2), (32, 16, 4, 2)), smooth_gain=1e6,
     if sectors.ndim == 1:
         sectors = numpy.zeros((2,) + sectors.shape, dtype="int", order="C") + sectors.reshape(
             (1, sectors.shape[0]))
+    elif sectors.ndim > 2 or sectors.ndim < 1:  # vet.py:513-519
+        raise ValueError("Incorrect sectors dimensions.\n"
+                         + "Only 1D or 2D arrays are supported to define"
+                         + "the number of sectors used in"
+                         + "the scaling procedure")
     sectors[0, :].sort()
     sectors[1, :].sort()
     fgs = (2, int(sectors[0, 0]), int(sectors[1, 0]))
     if first_guess is None:
         first_guess = numpy.zeros(fgs, order="C")
+    elif first_guess.shape != fgs:  # vet.py:531-537
+        raise ValueError("The shape of the initial guess do not match the number of "
+                         + "sectors of the first scaling guess\n"
+                         + "first_guess.shape={}\n".format(str(first_guess.shape))
+                         + "Expected shape={}".format(str(fgs)))
     else:
         first_guess = numpy.asarray(first_guess, order="C", dtype="float64")
     scaling_guesses = []

@@ -19,7 +19,7 @@ from oracle import noise_motion as ora_bps
 from pysteps_b200 import _device, _lib
 
 _NP = {_lib.F32: np.float32, _lib.F64: np.float64}
-_C = {np.float32: ctypes.c_float, np.float64: ctypes.c_double}
+_C = {np.float32: ctypes.c_float, np.float64: ctypes.c_double, np.int8: ctypes.c_int8}
 
 
 def _addr(p):
@@ -103,7 +103,35 @@ def _bps(velocity, code, m, n, a, b, vsf, what, out, nnf, stream):
         _view(nnf, (1,))[0] = float(np.count_nonzero(~np.isfinite(res)))
 
 
-_TABLE = {"b200_field_stats": _field_stats, "b200_sl_extrapolate_rows": _sl_rows,
+def _vet_cost(sd, templ, inp, mask, xs, ys, nx, ny, smooth_gain, gradient, out, stream):
+    from oracle import vet as ora_vet
+    r = ora_vet.cost_function(_view(sd, (2, xs, ys)).copy(), _view(templ, (nx, ny)).copy(),
+                              _view(inp, (nx, ny)).copy(), _view(mask, (nx, ny), np.int8).copy(),
+                              smooth_gain, gradient=bool(gradient))
+    if gradient:
+        _view(out, (2, xs, ys))[...] = r
+    else:
+        _view(out, (2,))[...] = r
+
+
+def _vet_warp(image, mask, disp, nx, ny, out, omask, grad, stream):
+    from oracle import vet as ora_vet
+    g = _addr(grad) is not None
+    r = ora_vet.warp(_view(image, (nx, ny)).copy(), _view(mask, (nx, ny), np.int8).copy(),
+                     _view(disp, (2, nx, ny)).copy(), gradient=g)
+    _view(out, (nx, ny))[...] = r[0]
+    _view(omask, (nx, ny), np.int8)[...] = r[1]
+    if g:
+        _view(grad, (2, nx, ny))[...] = r[2]
+
+
+def _zoom(a, c, h, w, oh, ow, out, stream):
+    from oracle import vet as ora_vet
+    _view(out, (c, oh, ow))[...] = ora_vet.zoom_o1(_view(a, (c, h, w)).copy(), oh, ow)
+
+
+_TABLE = {"b200_vet_cost": _vet_cost, "b200_vet_warp": _vet_warp, "b200_zoom_bilinear": _zoom,
+          "b200_field_stats": _field_stats, "b200_sl_extrapolate_rows": _sl_rows,
           "b200_bps_perturb_velocity": _bps}
 
 
@@ -141,9 +169,11 @@ def emulated():
     with contextlib.ExitStack() as st:
         st.enter_context(mock.patch.object(_device, "require_cuda", lambda: None))
         st.enter_context(mock.patch.object(_device, "to_device", _to_device))
-        st.enter_context(mock.patch.object(_device, "to_host", lambda t: t.numpy()))
+        st.enter_context(mock.patch.object(_device, "to_host", lambda t: t.clone().numpy()))
         st.enter_context(mock.patch.object(_device, "stream_ptr", lambda: 0))
         st.enter_context(mock.patch.object(_lib, "call", _call))
         st.enter_context(mock.patch.object(torch, "empty", empty))
         st.enter_context(mock.patch.object(torch.cuda, "current_stream", lambda *a: _Stream()))
+        # a device tensor's .cpu() is a fresh host copy; keep that property for the stand-ins
+        st.enter_context(mock.patch.object(torch.Tensor, "cpu", lambda self, *a, **k: self.clone()))
         yield
