@@ -2,8 +2,9 @@
 
 TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  Host-side argument
 handling restates pysteps/extrapolation/semilagrangian.py:106-179,260-266 line
-by line; the array arithmetic runs in ``sl_oracle.c``.  ``interp_order > 1`` is
-not restated.
+by line; the array arithmetic runs in ``sl_oracle.c`` / ``spline_oracle.c``.
+``interp_order`` 0, 1 and 3 are restated (2, 4 and 5 are not: nothing in the reference tree
+uses them).
 """
 import ctypes
 import warnings
@@ -18,6 +19,34 @@ _dp = ctypes.POINTER(ctypes.c_double)
 
 def _p(a):
     return None if a is None else a.ctypes.data_as(_dp)
+
+
+def spline_filter3(a, mode="constant"):
+    """scipy.ndimage.spline_filter(a, 3, output=float64, mode=mode) for the two boundary
+    treatments map_coordinates uses: "constant" (mirror) and "nearest" (reflect)."""
+    f = np.array(a, dtype=np.float64, order="C")
+    L = lib()
+    L.ora_spline_filter3.restype = None
+    L.ora_spline_filter3.argtypes = [_dp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int]
+    L.ora_spline_filter3(_p(f), f.shape[0], f.shape[1], int(_MODES[mode] == 1))
+    return f
+
+
+def map_coordinates_spline(a, coords, order, mode="constant", cval=0.0):
+    """scipy.ndimage.map_coordinates(a, coords, order=0|3, mode, cval, prefilter=True)."""
+    a64 = np.ascontiguousarray(a, dtype=np.float64)
+    cy = np.ascontiguousarray(coords[0], dtype=np.float64)
+    cx = np.ascontiguousarray(coords[1], dtype=np.float64)
+    out = np.empty(cy.shape, dtype=np.float64)
+    L = lib()
+    L.ora_map_coordinates_spline.restype = ctypes.c_int
+    L.ora_map_coordinates_spline.argtypes = [_dp, ctypes.c_int64, ctypes.c_int64, _dp, _dp, ctypes.c_int64,
+                                             ctypes.c_int, ctypes.c_int, ctypes.c_double, _dp]
+    rc = L.ora_map_coordinates_spline(_p(a64), a64.shape[0], a64.shape[1], _p(cy), _p(cx), cy.size,
+                                      int(order), _MODES[mode], float(cval), _p(out))
+    if rc != 0:
+        raise MemoryError("oracle allocation failed")
+    return out.astype(a.dtype) if a.dtype == np.float32 else out
 
 
 def map_coordinates_o1(a, coords, mode="constant", cval=0.0):
@@ -63,8 +92,21 @@ def extrapolate(precip, velocity, timesteps, outval=np.nan, xy_coords=None,
         raise ValueError("precip is None but return_displacement is False")
     if "D_prev" in kwargs.keys():
         warnings.warn("deprecated argument D_prev is ignored, use displacement_prev instead")
-    if interp_order != 1:
-        raise NotImplementedError("oracle restates interp_order=1 only")
+    if interp_order not in (0, 1, 3):
+        raise NotImplementedError("oracle restates interp_order 0, 1 and 3 only")
+    # :144-157 separate masks preserve NaN and no-precipitation values under the spline
+    mask_min = mask_finite = None
+    minval = 0.0
+    if precip is not None and interp_order > 1:
+        minval = np.nanmin(precip)
+        mask_min = (precip > minval).astype(float)
+        if allow_nonfinite_values:
+            mask_finite = np.isfinite(precip)
+            precip = precip.copy()
+            precip[~mask_finite] = 0.0
+            mask_finite = mask_finite.astype(float)
+        else:
+            mask_finite = np.ones(precip.shape)
     # :159-165
     if isinstance(timesteps, int):
         timesteps = np.arange(1, timesteps + 1)
@@ -85,16 +127,20 @@ def extrapolate(precip, velocity, timesteps, outval=np.nan, xy_coords=None,
     T = timestep_diff.size
     out = None if precip is None else np.empty((T, m, n), dtype=np.float64)
     disp = np.empty((2, m, n), dtype=np.float64)
+    MM = None if mask_min is None else np.ascontiguousarray(mask_min, dtype=np.float64)
+    MF = None if mask_finite is None else np.ascontiguousarray(mask_finite, dtype=np.float64)
     L = lib()
-    L.ora_sl_extrapolate.restype = ctypes.c_int
-    L.ora_sl_extrapolate.argtypes = [_dp, _dp, ctypes.c_int64, ctypes.c_int64, _dp, _dp,
-                                     ctypes.c_int64, ctypes.c_double, ctypes.c_int, _dp,
-                                     ctypes.c_double, ctypes.c_int, ctypes.c_int, _dp, _dp]
-    rc = L.ora_sl_extrapolate(_p(P), _p(V), m, n, _p(XY), _p(timestep_diff), T,
-                              float(vel_timestep), int(n_iter), _p(DP),
-                              float(outval) if precip is not None else 0.0,  # cval unused without precip
-                              _MODES[map_coordinates_mode],
-                              int(velocity.dtype == np.float32), _p(out), _p(disp))
+    L.ora_sl_extrapolate_order.restype = ctypes.c_int
+    L.ora_sl_extrapolate_order.argtypes = [_dp, _dp, ctypes.c_int64, ctypes.c_int64, _dp, _dp,
+                                           ctypes.c_int64, ctypes.c_double, ctypes.c_int, _dp,
+                                           ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                           _dp, _dp, ctypes.c_double, _dp, _dp]
+    rc = L.ora_sl_extrapolate_order(_p(P), _p(V), m, n, _p(XY), _p(timestep_diff), T,
+                                    float(vel_timestep), int(n_iter), _p(DP),
+                                    float(outval) if precip is not None else 0.0,  # cval unused without precip
+                                    _MODES[map_coordinates_mode],
+                                    int(velocity.dtype == np.float32), int(interp_order), _p(MM), _p(MF),
+                                    float(minval), _p(out), _p(disp))
     if rc != 0:
         raise MemoryError("oracle allocation failed")
     # :260-266 ; scipy returns the input array dtype

@@ -157,11 +157,43 @@ static void interpolate_motion(const double *V, const double *xy, int64_t m,
  *   disp_out   (2,m,n) (always written)
  * returns 0, or -1 on allocation failure.
  */
+/* spline_oracle.c */
+double *ora_spline_prepare(const double *a, int64_t m, int64_t n, int order, int mode,
+                           int64_t *M, int64_t *N, int64_t *npad);
+double ora_sample_spline(const double *f, int64_t M, int64_t N, double cy, double cx, int order,
+                         int mode, double cval, int64_t npad);
+
+/* As ora_sl_extrapolate, plus semilagrangian.py:144-157,224-253: interp_order 0 or 3 for the
+ * precipitation field (the motion field is always sampled with order 1), with the two
+ * auxiliary order-1 mask warps.  For interp_order > 1 the caller passes precip with non-finite
+ * values already zeroed (:150-152), mask_min = (precip > minval) and mask_finite as float64
+ * 0/1 arrays (:147-155). */
+int ora_sl_extrapolate_order(const double *precip, const double *V, int64_t m,
+                             int64_t n, const double *xy_in, const double *tdiff,
+                             int64_t T, double vel_timestep, int n_iter,
+                             const double *disp_prev, double outval, int mode,
+                             int vel_f32, int interp_order, const double *mask_min,
+                             const double *mask_finite, double minval,
+                             double *out, double *disp_out);
+
 int ora_sl_extrapolate(const double *precip, const double *V, int64_t m,
                        int64_t n, const double *xy_in, const double *tdiff,
                        int64_t T, double vel_timestep, int n_iter,
                        const double *disp_prev, double outval, int mode,
                        int vel_f32, double *out, double *disp_out)
+{
+    return ora_sl_extrapolate_order(precip, V, m, n, xy_in, tdiff, T, vel_timestep, n_iter,
+                                    disp_prev, outval, mode, vel_f32, 1, NULL, NULL, 0.0, out,
+                                    disp_out);
+}
+
+int ora_sl_extrapolate_order(const double *precip, const double *V, int64_t m,
+                             int64_t n, const double *xy_in, const double *tdiff,
+                             int64_t T, double vel_timestep, int n_iter,
+                             const double *disp_prev, double outval, int mode,
+                             int vel_f32, int interp_order, const double *mask_min,
+                             const double *mask_finite, double minval,
+                             double *out, double *disp_out)
 {
     const int64_t N = m * n;
     double *xy = (double *)malloc(sizeof(double) * 2 * N);
@@ -171,6 +203,17 @@ int ora_sl_extrapolate(const double *precip, const double *V, int64_t m,
     if (!xy || !vinc || !tmp) {
         free(xy); free(vinc); free(tmp);
         return -1;
+    }
+    /* spline coefficients of the field: the prefilter of every map_coordinates call of the
+     * leadtime loop sees the same input, so it is evaluated once */
+    double *filt = NULL;
+    int64_t FM = 0, FN = 0, fpad = 0;
+    if (precip && interp_order != 1) {
+        filt = ora_spline_prepare(precip, m, n, interp_order, mode, &FM, &FN, &fpad);
+        if (!filt) {
+            free(xy); free(vinc); free(tmp);
+            return -1;
+        }
     }
     if (xy_in) {
         memcpy(xy, xy_in, sizeof(double) * 2 * N);
@@ -218,10 +261,19 @@ int ora_sl_extrapolate(const double *precip, const double *V, int64_t m,
             for (int64_t i = 0; i < N; i++) {
                 double cx = xy[i] + disp[i];
                 double cy = xy[N + i] + disp[N + i];
-                o[i] = sample_o1(precip, m, n, cy, cx, mode, outval);
+                if (interp_order == 1) {
+                    o[i] = sample_o1(precip, m, n, cy, cx, mode, outval);
+                    continue;
+                }
+                double v = ora_sample_spline(filt, FM, FN, cy, cx, interp_order, mode, outval, fpad);
+                if (interp_order > 1) { /* :234-253 */
+                    if (sample_o1(mask_min, m, n, cy, cx, mode, 0.0) < 0.5) v = minval;
+                    if (sample_o1(mask_finite, m, n, cy, cx, mode, 0.0) < 0.5) v = NAN;
+                }
+                o[i] = v;
             }
         }
     }
-    free(xy); free(vinc); free(tmp);
+    free(xy); free(vinc); free(tmp); free(filt);
     return 0;
 }

@@ -17,13 +17,13 @@ sys.path.insert(0, HERE)
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
 from _refimport import ref_module  # noqa: E402
-from sl_cases import CASES, build_case  # noqa: E402
+from sl_cases import CASES, SPLINE_CASES, build_case  # noqa: E402
 
 
 def main():
     ref = ref_module("pysteps.extrapolation.semilagrangian")
     out = {}
-    for name in CASES:
+    for name in CASES + SPLINE_CASES:
         args, kwargs = build_case(name)
         res = ref.extrapolate(*args, **kwargs)
         if isinstance(res, tuple):

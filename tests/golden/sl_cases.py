@@ -59,10 +59,28 @@ def build_case(name):
     if name == "noisy_velocity":
         rng = np.random.default_rng(11)
         return (P, V + rng.normal(size=V.shape), 3), {}
+    # ---- spline orders (semilagrangian.py:144-157,224-253); oracle only so far ----------------
+    if name == "order3_constant":
+        return (P, V * 2.0, 3), {"interp_order": 3}
+    if name == "order3_nearest_nan":
+        # the call of examples/ens_kalman_filter_blended_forecast.py:258 (order 3, "nearest")
+        return (syn.nan_disc(P), V * 3.0, 3), {"interp_order": 3, "map_coordinates_mode": "nearest",
+                                               "allow_nonfinite_values": True}
+    if name == "order3_float32_min":
+        return (P.astype(np.float32) - 2.0, V * 3.0, 2, "min"), {"interp_order": 3, "return_displacement": True}
+    if name == "order0_nearest":
+        return (P, V * 3.0, 2), {"interp_order": 0, "map_coordinates_mode": "nearest"}
+    if name == "order0_constant":
+        return (P, V * 3.0, 2, -15.0), {"interp_order": 0}
     raise KeyError(name)
 
 
+# cases the CUDA path implements (interp_order 1)
 CASES = ["default_T4", "rotation_T5", "list_timesteps", "n_iter3", "n_iter0", "n_iter0_prev",
          "nearest_mode", "outval_min", "outval_const", "return_disp", "disp_prev", "precip_none",
          "nan_disc", "float32_precip", "float32_both", "custom_xy", "default_xy_given",
          "long_T40", "noisy_velocity"]
+
+# cases only the oracle restates so far (the CUDA path raises NotImplementedError for them)
+SPLINE_CASES = ["order3_constant", "order3_nearest_nan", "order3_float32_min", "order0_nearest",
+                "order0_constant"]
