@@ -398,7 +398,85 @@ int sl_run(const void *precip, const void *velocity, const double *xy, const dou
     return 0;
 }
 
+// Displacement field after EVERY leadtime (for samplers other than the built-in order-1 warp):
+// the trajectory kernel run one leadtime per launch through the same resume mechanism that
+// chunks long sequences, so the arithmetic is that of the fused loop.
+template <typename FV>
+int sl_trajectories(const void *velocity, const double *xy, const double *disp_prev, const double *tdiff,
+                    int T, double vts, int n_iter, int layout, int m, int n, int row0, int rows,
+                    double *disp_steps, cudaStream_t stream) {
+    const size_t N = (size_t)m * n, NB = (size_t)rows * n;
+    b200::Scratch vi, st_vinc;
+    const int sblocks = (int)std::min<size_t>((N + 255) / 256, (size_t)b200::num_sms() * 16);
+    const void *vi_ptr = velocity;
+    if (!(sizeof(FV) == 8 && layout == B200_LAYOUT_INTERLEAVED)) {
+        B200_CUDA(vi.alloc(N * sizeof(double2), stream));
+        vi_ptr = vi.p;
+        widen_velocity_kernel<FV><<<sblocks, 256, 0, stream>>>(
+            (const FV *)velocity, (double2 *)vi.p, N, layout == B200_LAYOUT_INTERLEAVED);
+        B200_LAUNCH_CHECK();
+    }
+    B200_CUDA(st_vinc.alloc(2 * NB * sizeof(double), stream));
+    dim3 block(SL_BX, SL_BY);
+    dim3 grid(b200::ceil_div(n, SL_BX), b200::ceil_div(rows, SL_BY));
+    for (int c = 0; c < T; c++) {
+        SLParams p;
+        memset(&p, 0, sizeof(p));
+        p.Vi = vi_ptr;
+        p.xy = xy;
+        p.m = m; p.n = n;
+        p.row0 = row0; p.rows = rows;
+        p.n_iter = n_iter;
+        p.mode = B200_MODE_CONSTANT;
+        p.vts = vts;
+        p.td0 = tdiff[0];
+        p.has_prev = disp_prev != nullptr;
+        p.vel_f32 = sizeof(FV) == 4;
+        p.ti_offset = c;
+        p.T = 1;
+        p.scale[0] = tdiff[c] / vts;
+        if (c == 0) {
+            p.init_mode = disp_prev ? SL_INIT_PREV : SL_INIT_FRESH;
+            p.disp_in = disp_prev;
+        } else {
+            p.init_mode = SL_INIT_RESUME;
+            p.disp_in = disp_steps + (size_t)(c - 1) * 2 * NB;
+            p.vinc_in = (const double *)st_vinc.p;
+        }
+        p.disp_out = disp_steps + (size_t)c * 2 * NB;
+        p.vinc_out = (double *)st_vinc.p;
+        if (n_iter == 1)
+            sl_multistep_kernel<double, true, SL_BY><<<grid, block, 0, stream>>>(p);
+        else
+            sl_multistep_kernel<double, false, SL_BY><<<grid, block, 0, stream>>>(p);
+        B200_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
 }  // namespace
+
+extern "C" int b200_sl_trajectories(const void *velocity, const double *xy_coords, const double *disp_prev,
+                                    const double *tdiff, int T, double vel_timestep, int n_iter,
+                                    int velocity_dtype, int velocity_layout, int m, int n, int row_begin,
+                                    int row_count, double *disp_steps, void *stream) {
+    B200_REQUIRE(row_begin >= 0 && row_count >= 1 && row_begin + row_count <= m, "row band out of range");
+    B200_REQUIRE(velocity_layout == B200_LAYOUT_PLANAR || velocity_layout == B200_LAYOUT_INTERLEAVED,
+                 "unknown velocity layout");
+    B200_REQUIRE(velocity != nullptr && disp_steps != nullptr, "velocity / disp_steps is NULL");
+    B200_REQUIRE(tdiff != nullptr && T >= 1, "need at least one timestep");
+    B200_REQUIRE(m >= 1 && n >= 1 && (int64_t)m * n < ((int64_t)1 << 30), "grid must have 1 .. 2^30 pixels");
+    B200_REQUIRE(n_iter >= 0, "n_iter must be >= 0");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (velocity_dtype == B200_F32)
+        return sl_trajectories<float>(velocity, xy_coords, disp_prev, tdiff, T, vel_timestep, n_iter,
+                                      velocity_layout, m, n, row_begin, row_count, disp_steps, s);
+    if (velocity_dtype == B200_F64)
+        return sl_trajectories<double>(velocity, xy_coords, disp_prev, tdiff, T, vel_timestep, n_iter,
+                                       velocity_layout, m, n, row_begin, row_count, disp_steps, s);
+    b200::set_error("unknown velocity dtype %d", velocity_dtype);
+    return B200_EINVAL;
+}
 
 extern "C" int b200_sl_extrapolate_rows(const void *precip, const void *velocity,
                                         const double *xy_coords, const double *disp_prev,

@@ -13,6 +13,8 @@ device as well (``b200_field_stats``).
 Inputs may be NumPy arrays (results are NumPy arrays, one H2D per input and one
 D2H per output) or CUDA ``torch`` tensors (results stay on the device).
 """
+import math
+import os
 import time
 import warnings
 import weakref
@@ -89,8 +91,10 @@ def extrapolate(precip, velocity, timesteps, outval=np.nan, xy_coords=None,
                 allow_nonfinite_values=False, vel_timestep=1, **kwargs):
     """Semi-Lagrangian backward extrapolation; same contract as the reference
     (see its docstring, semilagrangian.py:30-104).  Differences: ``interp_order``
-    must be 1 and ``map_coordinates_mode`` one of "constant"/"nearest"
-    (anything else raises NotImplementedError instead of silently using a CPU path).
+    must be 1 (0 and 3 are built -- csrc/spline.cu -- but stay behind
+    ``PYSTEPS_B200_ENABLE_SPLINE=1`` until they have been verified on hardware) and
+    ``map_coordinates_mode`` one of "constant"/"nearest" (anything else raises
+    NotImplementedError instead of silently using a CPU path).
     """
     if precip is not None and precip.ndim != 2:
         raise ValueError("precip must be a two-dimensional array")
@@ -137,7 +141,8 @@ def extrapolate(precip, velocity, timesteps, outval=np.nan, xy_coords=None,
     deferred = []
     try:
         result = _extrapolate_checked(precip, velocity, d_precip, d_vel, stats, on_device, timesteps,
-                                      outval, xy_coords, vel_timestep, kwargs, deferred)
+                                      outval, xy_coords, vel_timestep, kwargs, deferred,
+                                      allow_nonfinite_values)
     except Exception:
         finiteness_errors()  # raises first if the reference would have
         for msg in deferred:
@@ -149,8 +154,18 @@ def extrapolate(precip, velocity, timesteps, outval=np.nan, xy_coords=None,
     return result
 
 
+# pole of the cubic B-spline prefilter: the double nearest to sqrt(3) - 2 (a decimal literal in
+# scipy's ni_splines.c; sqrt(3.0) - 2.0 evaluated in double is 2 ulp away)
+_POLE3 = -0.267949192431122706472553658494127633
+_SPLINE_PAD = 12  # scipy.ndimage._prepad_for_spline_filter, mode "nearest"
+
+
+def _spline_enabled():
+    return os.environ.get("PYSTEPS_B200_ENABLE_SPLINE", "") == "1"
+
+
 def _extrapolate_checked(precip, velocity, d_precip, d_vel, stats, on_device, timesteps, outval,
-                         xy_coords, vel_timestep, kwargs, deferred_warnings):
+                         xy_coords, vel_timestep, kwargs, deferred_warnings, allow_nonfinite_values=False):
     """semilagrangian.py:125-266 (everything after the finiteness checks)."""
     if isinstance(timesteps, list) and not sorted(timesteps) == timesteps:
         raise ValueError("timesteps is not in ascending order")
@@ -173,10 +188,12 @@ def _extrapolate_checked(precip, velocity, d_precip, d_vel, stats, on_device, ti
     if "D_prev" in kwargs.keys():
         deferred_warnings.append("deprecated argument D_prev is ignored, use displacement_prev instead")
 
-    if interp_order != 1:
+    if interp_order not in (0, 1, 3) or (interp_order != 1 and not _spline_enabled()):
         raise NotImplementedError(
             "pysteps_b200 semilagrangian: only interp_order=1 is implemented on the GPU "
-            f"(got {interp_order}); no CPU fallback is provided")
+            f"(got {interp_order}); no CPU fallback is provided"
+            + (" -- orders 0 and 3 are built but not yet verified on hardware; "
+               "PYSTEPS_B200_ENABLE_SPLINE=1 enables them" if interp_order in (0, 3) else ""))
     if map_coordinates_mode not in _MODES:
         raise NotImplementedError(
             "pysteps_b200 semilagrangian: map_coordinates_mode must be 'constant' or "
@@ -195,8 +212,19 @@ def _extrapolate_checked(precip, velocity, d_precip, d_vel, stats, on_device, ti
         print("Computing the advection with the semi-lagrangian scheme.")
         t0 = time.time()
 
+    # interp_order > 1 (:144-157): the spline runs on a copy whose non-finite values are zeroed
+    # (only when they are allowed at all); two order-1 mask warps restore them afterwards
+    zero_fill = False
+    if precip is not None and interp_order > 1:
+        st_p = stats.get()[0]
+        if st_p[0] != st_p[3]:
+            raise NotImplementedError("pysteps_b200 semilagrangian: interp_order > 1 with +-inf in precip")
+        zero_fill = bool(allow_nonfinite_values)
+
     if precip is not None and isinstance(outval, str) and outval == "min":
         outval = stats.get()[0][1]  # np.nanmin(precip), :171-172
+        if zero_fill and stats.get()[0][0] > 0:
+            outval = min(outval, 0.0)  # the reference takes it from the zero-filled copy (:150-152)
 
     m, n = int(velocity.shape[1]), int(velocity.shape[2])
     interleaved = isinstance(velocity, _bps.PerturbedVelocity)
@@ -239,15 +267,45 @@ def _extrapolate_checked(precip, velocity, d_precip, d_vel, stats, on_device, ti
         _lib.call("b200_sl_interleave_velocity", d_vel.data_ptr(), _device.dtype_code(d_vel.dtype),
                   m, n, d_v.data_ptr(), _device.stream_ptr())
         layout = _lib.LAYOUT_INTERLEAVED
-    _lib.call("b200_sl_extrapolate_rows",
-              _device.ptr(d_precip), d_v.data_ptr(), _device.ptr(d_xy), _device.ptr(d_prev),
-              timestep_diff.ctypes.data_as(_lib.c_dp), T, float(vel_timestep),
-              max(int(n_iter), 0),
-              float(outval) if d_precip is not None else 0.0,  # cval is unused without precip (:171-172)
-              _MODES[map_coordinates_mode],
-              _device.dtype_code(d_vel.dtype), layout,
-              _device.dtype_code(d_precip.dtype) if d_precip is not None else _lib.F64,
-              m, n, r0, mb, _device.ptr(d_out), _device.ptr(d_disp), _device.stream_ptr())
+    if d_precip is None or interp_order == 1:
+        _lib.call("b200_sl_extrapolate_rows",
+                  _device.ptr(d_precip), d_v.data_ptr(), _device.ptr(d_xy), _device.ptr(d_prev),
+                  timestep_diff.ctypes.data_as(_lib.c_dp), T, float(vel_timestep),
+                  max(int(n_iter), 0),
+                  float(outval) if d_precip is not None else 0.0,  # cval is unused without precip (:171-172)
+                  _MODES[map_coordinates_mode],
+                  _device.dtype_code(d_vel.dtype), layout,
+                  _device.dtype_code(d_precip.dtype) if d_precip is not None else _lib.F64,
+                  m, n, r0, mb, _device.ptr(d_out), _device.ptr(d_disp), _device.stream_ptr())
+    else:
+        # spline orders (:224-253): displacement after every leadtime from the trajectory kernel,
+        # spline coefficients of the field once (the prefilter sees the same input at every
+        # leadtime), then one sampling launch for all leadtimes
+        mode = _MODES[map_coordinates_mode]
+        pad = _SPLINE_PAD if (interp_order > 1 and map_coordinates_mode == "nearest") else 0
+        M, N = m + 2 * pad, n + 2 * pad
+        reflect = map_coordinates_mode == "nearest"
+        d_steps = torch.empty((T, 2, mb, n), dtype=torch.float64, device="cuda")
+        _lib.call("b200_sl_trajectories", d_v.data_ptr(), _device.ptr(d_xy), _device.ptr(d_prev),
+                  timestep_diff.ctypes.data_as(_lib.c_dp), T, float(vel_timestep), max(int(n_iter), 0),
+                  _device.dtype_code(d_vel.dtype), layout, m, n, r0, mb, d_steps.data_ptr(),
+                  _device.stream_ptr())
+        d_coeffs = torch.empty((M, N), dtype=torch.float64, device="cuda")
+        d_mmin = d_mfin = None
+        if interp_order > 1:
+            d_mmin = torch.empty((m, n), dtype=torch.float64, device="cuda")
+            d_mfin = torch.empty((m, n), dtype=torch.float64, device="cuda")
+        d_stats = stats.buf[0]
+        _lib.call("b200_spline_prepare", d_precip.data_ptr(), _device.dtype_code(d_precip.dtype), m, n,
+                  int(interp_order), mode, d_stats.data_ptr(), int(zero_fill), _POLE3,
+                  math.pow(_POLE3, M if reflect else M - 1), math.pow(_POLE3, N if reflect else N - 1),
+                  d_coeffs.data_ptr(), _device.ptr(d_mmin), _device.ptr(d_mfin), _device.stream_ptr())
+        _lib.call("b200_spline_sample", d_coeffs.data_ptr(), m, n, int(interp_order), mode, _device.ptr(d_xy),
+                  d_steps.data_ptr(), T, r0, mb, float(outval), _device.ptr(d_mmin), _device.ptr(d_mfin),
+                  d_stats.data_ptr(), _device.dtype_code(d_precip.dtype), d_out.data_ptr(),
+                  _device.stream_ptr())
+        if d_disp is not None:
+            d_disp.copy_(d_steps[T - 1])
 
     if on_device:
         out, disp = d_out, d_disp

@@ -83,6 +83,43 @@ def _sl_rows(precip, velocity, xy, disp_prev, tdiff, T, vts, n_iter, outval, mod
         _view(disp_out, (2, rows, n))[...] = disp[:, r0:r0 + rows]
 
 
+def _sl_trajectories(velocity, xy, disp_prev, tdiff, T, vts, n_iter, vdt, layout, m, n, r0, rows, steps,
+                     stream):
+    """disp_steps[t] = the displacement after leadtime t: prefix runs of the oracle trajectory"""
+    out = _view(steps, (T, 2, rows, n))
+    tmp = np.empty((2, rows, n))
+    for t in range(T):
+        _sl_rows(None, velocity, xy, disp_prev, tdiff, t + 1, vts, n_iter, 0.0, 0, vdt, layout, _lib.F64,
+                 m, n, r0, rows, None, tmp.ctypes.data, stream)
+        out[t] = tmp
+
+
+def _spline_prepare(precip, pdt, m, n, order, mode, stats, zero_fill, pole, zp0, zp1, coeffs, mmin, mfin,
+                    stream):
+    import host_kernels
+    L = host_kernels.lib()
+    L.host_spline_prepare.restype = None
+    L.host_spline_prepare.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_double,
+                                      ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p,
+                                      ctypes.c_void_p]
+    L.host_spline_prepare(_addr(precip), pdt, m, n, order, mode, _addr(stats), zero_fill, pole, zp0, zp1,
+                          _addr(coeffs), _addr(mmin), _addr(mfin))
+
+
+def _spline_sample(coeffs, m, n, order, mode, xy, steps, T, r0, rows, outval, mmin, mfin, stats, odt, out,
+                   stream):
+    import host_kernels
+    L = host_kernels.lib()
+    L.host_spline_sample.restype = None
+    L.host_spline_sample.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                     ctypes.c_int, ctypes.c_void_p]
+    L.host_spline_sample(_addr(coeffs), m, n, order, mode, _addr(xy), _addr(steps), T, r0, rows, outval,
+                         _addr(mmin), _addr(mfin), _addr(stats), odt, _addr(out))
+
+
 def _bps(velocity, code, m, n, a, b, vsf, what, out, nnf, stream):
     V = _view(velocity, (2, m, n), _NP[code])
     unit = np.zeros((2, m, n))
@@ -131,7 +168,8 @@ def _zoom(a, c, h, w, oh, ow, out, stream):
 
 
 _TABLE = {"b200_vet_cost": _vet_cost, "b200_vet_warp": _vet_warp, "b200_zoom_bilinear": _zoom,
-          "b200_field_stats": _field_stats, "b200_sl_extrapolate_rows": _sl_rows,
+          "b200_sl_trajectories": _sl_trajectories, "b200_spline_prepare": _spline_prepare,
+          "b200_spline_sample": _spline_sample, "b200_field_stats": _field_stats, "b200_sl_extrapolate_rows": _sl_rows,
           "b200_bps_perturb_velocity": _bps}
 
 

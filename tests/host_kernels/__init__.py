@@ -1,0 +1,21 @@
+"""TEST INFRASTRUCTURE: host builds of CUDA kernel bodies (see spline_host.cpp)."""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "libhost_kernels.so")
+        srcs = [os.path.join(_HERE, "spline_host.cpp"),
+                os.path.join(_HERE, "..", "..", "pysteps_b200", "csrc", "spline_body.cuh")]
+        if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+            cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+            subprocess.check_call([cxx, "-O2", "-fPIC", "-shared", "-std=c++17", "-ffp-contract=off",
+                                   "-fno-fast-math", "-Wall", "-o", so, srcs[0]])
+        _LIB = ctypes.CDLL(so)
+    return _LIB

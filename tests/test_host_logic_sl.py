@@ -169,3 +169,45 @@ def test_member_loop_with_handles_matches_reference_expression():
         bad[0, 0, 0] = np.inf
         with pytest.raises(ValueError, match="infs or NaNs"):
             init(bad, 1, 1)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_spline_orders_host_logic_and_kernel_bodies(seed, monkeypatch):
+    """interp_order 0 / 3 (behind PYSTEPS_B200_ENABLE_SPLINE=1 until verified on hardware): the
+    shim's branch -- trajectories per leadtime, prefilter, sampling, mask warps, outval="min" on
+    the zero-filled copy, bands -- driven through the emulated C ABI, whose spline entry points
+    are the CUDA kernels' own bodies compiled for the host (tests/host_kernels)."""
+    import pysteps_b200
+    extrap = pysteps_b200.extrapolation.semilagrangian.extrapolate
+    ref, live = _reference()
+    rng = np.random.default_rng(300 + seed)
+    with cpu_abi.emulated():
+        with pytest.raises(NotImplementedError, match="PYSTEPS_B200_ENABLE_SPLINE"):
+            extrap(np.ones((4, 4)), np.ones((2, 4, 4)), 1, interp_order=3)
+        monkeypatch.setenv("PYSTEPS_B200_ENABLE_SPLINE", "1")
+        with pytest.raises(NotImplementedError):
+            extrap(np.ones((4, 4)), np.ones((2, 4, 4)), 1, interp_order=2)
+        n_ok = 0
+        for it in range(60):
+            Pin, Vin, ts, outval, kw = _random_call(rng)
+            kw["interp_order"] = int(rng.choice([0, 3, 3]))
+            want, werr, wdep = _run(ref, Pin, Vin, ts, outval, kw)
+            got, gerr, gdep = _run(extrap, Pin, Vin, ts, outval, kw)
+            ctx = f"seed {seed} case {it}: ts={ts!r} outval={outval!r} kw={ {k: (v.shape if isinstance(v, np.ndarray) else v) for k, v in kw.items()} }"
+            if gerr is not None and "inf in precip" in gerr[1]:
+                continue
+            assert gerr == werr and gdep == wdep, ctx
+            if werr is not None:
+                continue
+            n_ok += 1
+            for a, b in zip(got if isinstance(got, tuple) else (got,), want if isinstance(want, tuple) else (want,)):
+                assert (a is None) == (b is None), ctx
+                if a is not None:
+                    assert _bits_equal(a, b), ctx
+        assert n_ok >= 15
+        # a band of output rows equals the rows of the full result
+        P = rng.standard_normal((17, 21)).astype(np.float32)
+        V = rng.standard_normal((2, 17, 21)) * 2
+        full = extrap(P, V, 3, interp_order=3, map_coordinates_mode="nearest")
+        band = extrap(P, V, 3, interp_order=3, map_coordinates_mode="nearest", b200_rows=(5, 11))
+        assert _bits_equal(band, full[:, 5:11])

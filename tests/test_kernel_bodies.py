@@ -1,0 +1,118 @@
+"""CPU execution of CUDA kernel bodies: the per-thread code of pysteps_b200/csrc/spline.cu
+(spline_body.cuh, shared verbatim between the device build and tests/host_kernels/) is compiled
+as host C++ and run over the whole "grid" against the oracle, bit for bit.  This pins the
+arithmetic and index logic of the spline kernels without a GPU; the device build differs only
+in spelling every float64 operation as a round-to-nearest intrinsic."""
+import ctypes
+import math
+
+import numpy as np
+import pytest
+from conftest import assert_bits_equal
+
+import host_kernels
+from oracle import semilagrangian as ora
+
+POLE3 = -0.267949192431122706472553658494127633
+F32, F64 = 0, 1
+MODES = {"constant": 0, "nearest": 1}
+_dp = ctypes.POINTER(ctypes.c_double)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _stats(P):
+    fin = np.isfinite(P)
+    nn = P[~np.isnan(P)].astype(np.float64)
+    return np.array([np.count_nonzero(~fin), nn.min() if nn.size else np.nan,
+                     nn.max() if nn.size else np.nan, np.count_nonzero(np.isnan(P))], dtype=np.float64)
+
+
+def _prepare(P, order, mode, zero_fill):
+    L = host_kernels.lib()
+    m, n = P.shape
+    pad = L.host_spline_pad(order, MODES[mode])
+    M, N = m + 2 * pad, n + 2 * pad
+    reflect = mode == "nearest"
+    coeffs = np.empty((M, N))
+    mmin, mfin = np.full((m, n), -1.0), np.full((m, n), -1.0)
+    stats = _stats(P)
+    L.host_spline_prepare.restype = None
+    L.host_spline_prepare.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_double,
+                                      ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p,
+                                      ctypes.c_void_p]
+    L.host_spline_prepare(_p(P), F32 if P.dtype == np.float32 else F64, m, n, order, MODES[mode], _p(stats),
+                          int(zero_fill), POLE3, math.pow(POLE3, M if reflect else M - 1),
+                          math.pow(POLE3, N if reflect else N - 1), _p(coeffs), _p(mmin), _p(mfin))
+    return coeffs, mmin, mfin, stats, pad
+
+
+@pytest.mark.parametrize("shape", [(9, 13), (1, 7), (5, 1), (2, 2), (1, 1), (40, 33)])
+@pytest.mark.parametrize("mode", ["constant", "nearest"])
+def test_prepare_and_prefilter_bodies(shape, mode):
+    from scipy import ndimage as ndi
+    rng = np.random.default_rng(shape[0] * 31 + shape[1])
+    for dtype in (np.float64, np.float32):
+        P = (rng.standard_normal(shape) * 5).astype(dtype)
+        P[rng.random(shape) < 0.15] = np.nan
+        for zero_fill in (False, True):
+            if not zero_fill:
+                P = np.nan_to_num(P, nan=1.5)
+            coeffs, mmin, mfin, stats, pad = _prepare(P, 3, mode, zero_fill)
+            src = np.where(np.isfinite(P), P, 0.0).astype(np.float64) if zero_fill else P.astype(np.float64)
+            padded = np.pad(src, pad, mode="edge") if pad else src
+            assert_bits_equal(coeffs, ndi.spline_filter(padded, 3, output=np.float64, mode=mode), "coefficients")
+            assert_bits_equal(coeffs, ora.spline_filter3(padded, mode), "coefficients vs oracle")
+            minval = np.nanmin(P)
+            assert_bits_equal(mmin, (P > minval).astype(float), "mask_min")      # semilagrangian.py:148
+            assert_bits_equal(mfin, np.isfinite(P).astype(float) if zero_fill else np.ones(shape), "mask_finite")
+    # order 0: a plain float64 copy, no masks touched
+    coeffs, mmin, mfin, _, pad = _prepare(P, 0, mode, False)
+    assert pad == 0 and np.array_equal(coeffs, P.astype(np.float64), equal_nan=True) and np.all(mmin == -1.0)
+
+
+@pytest.mark.parametrize("order", [0, 3])
+@pytest.mark.parametrize("mode", ["constant", "nearest"])
+def test_sample_body_reproduces_the_oracle_extrapolator(mode, order):
+    """prepare + sample bodies, fed with per-leadtime displacements, == the oracle's (reference-
+    pinned) extrapolate() with interp_order 0 / 3, incl. NaN handling, float32, bands, xy_coords."""
+    L = host_kernels.lib()
+    L.host_spline_sample.restype = None
+    L.host_spline_sample.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                     ctypes.c_int, ctypes.c_void_p]
+    rng = np.random.default_rng(10 * order + MODES[mode])
+    for case in range(12):
+        m, n = int(rng.integers(1, 28)), int(rng.integers(1, 28))
+        dtype = rng.choice([np.float64, np.float32])
+        P = (rng.standard_normal((m, n)) * 5).astype(dtype)
+        allow = bool(rng.random() < 0.5)
+        if allow:
+            P[rng.random((m, n)) < 0.2] = np.nan
+            if np.all(np.isnan(P)):
+                P[0, 0] = 1.0
+        V = rng.standard_normal((2, m, n)) * rng.choice([0.5, 3.0, 30.0])
+        T = int(rng.integers(1, 4))
+        outval = float(rng.choice([np.nan, 0.0, -15.0]))
+        xy = None
+        if rng.random() < 0.3:
+            xx, yy = np.meshgrid(np.arange(n) + 0.25, np.arange(m) * 0.5)
+            xy = np.stack([xx, yy])
+        kw = dict(interp_order=order, map_coordinates_mode=mode, allow_nonfinite_values=allow, xy_coords=xy)
+        want = ora.extrapolate(P, V, T, outval, **kw)
+        # displacement after every leadtime: single-step calls carrying the displacement give the
+        # same trajectory for equal time steps (what b200_sl_trajectories delivers in one go)
+        disp = np.empty((T, 2, m, n))
+        for t in range(T):
+            disp[t] = ora.extrapolate(None, V, t + 1, xy_coords=xy, return_displacement=True)[1]
+        coeffs, mmin, mfin, stats, _ = _prepare(P, order, mode, allow and order > 1)
+        r0, r1 = (0, m) if case % 3 else (m // 3, max(m // 3 + 1, 2 * m // 3))
+        band = np.ascontiguousarray(disp[:, :, r0:r1])
+        out = np.empty((T, r1 - r0, n), dtype=dtype)
+        L.host_spline_sample(_p(coeffs), m, n, order, MODES[mode], _p(xy), _p(band), T, r0, r1 - r0, outval,
+                             _p(mmin), _p(mfin), _p(stats), F32 if dtype == np.float32 else F64, _p(out))
+        assert_bits_equal(out, want[:, r0:r1], f"case {case} {(m, n)} {np.dtype(dtype).name} allow={allow}")
