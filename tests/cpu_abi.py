@@ -19,7 +19,8 @@ from oracle import noise_motion as ora_bps
 from pysteps_b200 import _device, _lib
 
 _NP = {_lib.F32: np.float32, _lib.F64: np.float64}
-_C = {np.float32: ctypes.c_float, np.float64: ctypes.c_double, np.int8: ctypes.c_int8}
+_C = {np.float32: ctypes.c_float, np.float64: ctypes.c_double, np.int8: ctypes.c_int8, np.uint8: ctypes.c_uint8,
+      np.int32: ctypes.c_int32}
 
 
 def _addr(p):
@@ -167,6 +168,162 @@ def _zoom(a, c, h, w, oh, ow, out, stream):
     _view(out, (c, oh, ow))[...] = ora_vet.zoom_o1(_view(a, (c, h, w)).copy(), oh, ow)
 
 
+# ---- dense Lucas-Kanade: the entry points emulated with the oracle's stage functions -------------
+# Device buffers carry their meaning between calls through this side table (pointer -> object):
+# the eigenvalue map remembers the uint8 image it came from, a pyramid the image it was built of.
+_side = {}
+
+
+def _masked(img, mask, m, n):
+    return np.ma.MaskedArray(_view(img, (m, n)).copy(), mask=_view(mask, (m, n), np.uint8).astype(bool))
+
+
+def _lk_mask_invalid(img, user_mask, m, n, mask_out, stats, stream):
+    a = _view(img, (m, n))
+    mk = ~np.isfinite(a)
+    if _addr(user_mask) is not None:
+        mk |= _view(user_mask, (m, n), np.uint8).astype(bool)
+    _view(mask_out, (m, n), np.uint8)[...] = mk
+    good = a[~mk]
+    _view(stats, (3,))[...] = [good.min() if good.size else np.nan, good.max() if good.size else np.nan, good.size]
+
+
+def _lk_morph_opening(img, mask, m, n, size, thr, minv, out, stream):
+    from oracle import lucaskanade as ora_lk
+    ma = _masked(img, mask, m, n)
+    np.ma.set_fill_value(ma, _view(minv, (1,))[0])
+    r = ora_lk.morph_opening(ma, _view(thr, (1,))[0], size)
+    _view(out, (m, n))[...] = np.ma.getdata(r)
+
+
+def _lk_masked_minmax(img, mask, m, n, dilate, stats0, stats, stream):
+    from oracle import lucaskanade as ora_lk
+    a = _view(img, (m, n))
+    mk = _view(mask, (m, n), np.uint8).astype(bool)
+    st = _view(stats, (12,))
+    st[...] = np.nan
+    for s0, r0 in ((0, 0), (3, 1), (6, 2)):
+        good = a[r0:][~mk[r0:]]
+        st[s0:s0 + 3] = [good.min() if good.size else np.inf, good.max() if good.size else -np.inf, good.size]
+    buffered = ora_lk.dilate_rect(mk.astype(np.uint8), int(dilate)) if dilate > 0 else mk.astype(np.uint8)
+    st[11] = np.count_nonzero(buffered == 0)
+
+
+def _lk_quantise(img, mask, m, n, mode, dilate, stats, fill, out, valid, stream):
+    from oracle import lucaskanade as ora_lk
+    ma = _masked(img, mask, m, n)
+    if mode == 0:
+        q = ora_lk.tracking_image(ma)
+    else:
+        q, v = ora_lk.detection_image(ma, dilate)
+        _view(valid, (m, n), np.uint8)[...] = v
+    _view(out, (m, n), np.uint8)[...] = q
+
+
+def _lk_min_eig(q, m, n, eig, stream):
+    from oracle import lucaskanade as ora_lk
+    img = _view(q, (m, n), np.uint8).copy()
+    _view(eig, (m, n), np.float32)[...] = ora_lk.corner_min_eigen_val(img)
+    _side[_addr(eig)] = img
+
+
+def _lk_good_features(eig, valid, m, n, max_corners, quality, min_distance, out_xy, out_count, stream):
+    from oracle import lucaskanade as ora_lk
+    pts = ora_lk.good_features_to_track(_side[_addr(eig)], _view(valid, (m, n), np.uint8).copy(), max_corners,
+                                        quality, min_distance)
+    pts = np.asarray(pts, dtype=np.float32).reshape(-1, 2)
+    _view(out_xy, (max_corners, 2), np.float32)[:len(pts)] = pts
+    _view(out_count, (1,), np.int32)[0] = len(pts)
+
+
+def _lk_build_pyramid(img, h, w, win_w, win_h, max_level, pyr, deriv, stream):
+    if _addr(img) is not None:
+        _side[_addr(pyr)] = _view(img, (h, w), np.uint8).copy()
+
+
+def _lk_track(pyrI, pyrJ, derivI, h, w, win_w, win_h, max_level, max_count, eps, min_eig_thr, prev, npts, npts_dev,
+              nxt, status, stream):
+    from oracle import lucaskanade as ora_lk
+    cnt = npts if _addr(npts_dev) is None else min(int(_view(npts_dev, (1,), np.int32)[0]), npts)
+    if cnt == 0:
+        return
+    p0 = _view(prev, (npts, 2), np.float32)[:cnt].copy()
+    p1, st = ora_lk.calc_optical_flow_pyr_lk(_side[_addr(pyrI)], _side[_addr(pyrJ)], p0, (win_w, win_h), max_level,
+                                             (3, max_count, eps), min_eig_thr)
+    _view(nxt, (npts, 2), np.float32)[:cnt] = p1
+    _view(status, (npts,), np.uint8)[:cnt] = np.atleast_1d(np.asarray(st).squeeze())
+
+
+def _lk_compact_tracks(p0, p1, status, npts_dev, cap, pool_xy, pool_uv, pool_count, pool_cap, stream):
+    cnt = cap if _addr(npts_dev) is None else min(int(_view(npts_dev, (1,), np.int32)[0]), cap)
+    a, b = _view(p0, (cap, 2), np.float32)[:cnt], _view(p1, (cap, 2), np.float32)[:cnt]
+    keep = _view(status, (cap,), np.uint8)[:cnt] == 1
+    pc = _view(pool_count, (1,), np.int32)
+    k = int(keep.sum())
+    _view(pool_xy, (pool_cap, 2))[pc[0]:pc[0] + k] = a[keep]
+    _view(pool_uv, (pool_cap, 2))[pc[0]:pc[0] + k] = b[keep] - a[keep]   # float32 arithmetic, widened
+    pc[0] += k
+
+
+def _count(n_dev, cap):
+    return cap if _addr(n_dev) is None else min(int(_view(n_dev, (1,), np.int32)[0]), cap)
+
+
+def _lk_detect_outliers(uv, xy, n_dev, cap, thr, k, out, stream):
+    from oracle import lucaskanade as ora_lk
+    cnt = _count(n_dev, cap)
+    if cnt:
+        _view(out, (cap,), np.uint8)[:cnt] = ora_lk.detect_outliers(_view(uv, (cap, 2))[:cnt].copy(), thr,
+                                                                    _view(xy, (cap, 2))[:cnt].copy(), k)
+
+
+def _lk_compact_rows(xy, uv, drop, n_dev, cap, oxy, ouv, ocount, stream):
+    cnt = _count(n_dev, cap)
+    keep = _view(drop, (cap,), np.uint8)[:cnt] == 0
+    k = int(keep.sum())
+    _view(oxy, (cap, 2))[:k] = _view(xy, (cap, 2))[:cnt][keep]
+    _view(ouv, (cap, 2))[:k] = _view(uv, (cap, 2))[:cnt][keep]
+    _view(ocount, (1,), np.int32)[0] = k
+
+
+def _lk_decluster(xy, uv, n_dev, cap, scale, min_samples, oxy, ouv, ocount, stream):
+    from oracle import lucaskanade as ora_lk
+    cnt = _count(n_dev, cap)
+    k = 0
+    if cnt:
+        dxy, duv = ora_lk.decluster(_view(xy, (cap, 2))[:cnt].copy(), _view(uv, (cap, 2))[:cnt].copy(), scale,
+                                    min_samples)
+        k = len(dxy)
+        _view(oxy, (cap, 2))[:k] = dxy
+        _view(ouv, (cap, 2))[:k] = duv
+    _view(ocount, (1,), np.int32)[0] = k
+
+
+def _lk_idw_fill(xy, vals, n_dev, cap, nvar, k, power, offset, mean_res, xg, nx, yg, ny, on_grid, out, stream):
+    from oracle import lucaskanade as ora_lk
+    cnt = _count(n_dev, cap)
+    gx, gy = _view(xg, (nx,)).copy(), _view(yg, (ny,)).copy()
+    # the oracle derives the resolution from the grids (np.gradient needs two samples per axis);
+    # the entry point is handed it (mean_res), so a one-row band is emulated on two rows
+    ex = np.append(gx, gx[-1] + mean_res) if nx == 1 else gx
+    ey = np.append(gy, gy[-1] + mean_res) if ny == 1 else gy
+    r = ora_lk.idwinterp2d(_view(xy, (cap, 2))[:cnt].copy(), _view(vals, (cap, nvar))[:cnt].copy(),
+                           ex, ey, power=power, k=k, dist_offset=offset)
+    _view(out, (nvar, ny, nx))[...] = np.asarray(r).reshape(nvar, ey.size, ex.size)[:, :ny, :nx]
+
+
+def _fill_f64(ptr, count, value, stream):
+    _view(ptr, (count,))[...] = value
+
+
+_TABLE_LK = {"b200_mask_invalid": _lk_mask_invalid, "b200_morph_opening": _lk_morph_opening,
+             "b200_masked_minmax": _lk_masked_minmax, "b200_quantise_u8": _lk_quantise,
+             "b200_min_eig": _lk_min_eig, "b200_good_features": _lk_good_features,
+             "b200_lk_build_pyramid": _lk_build_pyramid, "b200_lk_track": _lk_track,
+             "b200_lk_compact_tracks": _lk_compact_tracks, "b200_detect_outliers": _lk_detect_outliers,
+             "b200_compact_rows": _lk_compact_rows, "b200_decluster": _lk_decluster,
+             "b200_idw_fill": _lk_idw_fill, "b200_fill_f64": _fill_f64}
+
 _TABLE = {"b200_vet_cost": _vet_cost, "b200_vet_warp": _vet_warp, "b200_zoom_bilinear": _zoom,
           "b200_sl_trajectories": _sl_trajectories, "b200_spline_prepare": _spline_prepare,
           "b200_spline_sample": _spline_sample, "b200_field_stats": _field_stats, "b200_sl_extrapolate_rows": _sl_rows,
@@ -174,6 +331,8 @@ _TABLE = {"b200_vet_cost": _vet_cost, "b200_vet_warp": _vet_warp, "b200_zoom_bil
 
 
 def _call(name, *args):
+    if name in _TABLE_LK:
+        return _TABLE_LK[name](*args)
     if name not in _TABLE:
         raise NotImplementedError(f"cpu_abi: {name} is not emulated")
     _TABLE[name](*args)
@@ -191,7 +350,24 @@ def _to_device(a, dtype=None):
 class _Stream:
     cuda_stream = 0
 
+    def __init__(self, *a, **k):
+        pass
+
     def synchronize(self):
+        pass
+
+    def wait_event(self, e):
+        pass
+
+    def wait_stream(self, s):
+        pass
+
+
+class _Event:
+    def __init__(self, *a, **k):
+        pass
+
+    def record(self, *a):
         pass
 
 
@@ -211,6 +387,25 @@ def emulated():
         st.enter_context(mock.patch.object(_device, "stream_ptr", lambda: 0))
         st.enter_context(mock.patch.object(_lib, "call", _call))
         st.enter_context(mock.patch.object(torch, "empty", empty))
+        real_zeros = torch.zeros
+
+        def zeros(*a, **k):
+            k.pop("device", None)
+            return real_zeros(*a, **k)
+
+        st.enter_context(mock.patch.object(torch, "zeros", zeros))
+        real_tensor = torch.tensor
+
+        def tensor(*a, **k):
+            k.pop("device", None)
+            return real_tensor(*a, **k)
+
+        st.enter_context(mock.patch.object(torch, "tensor", tensor))
+        st.enter_context(mock.patch.object(torch.cuda, "Stream", _Stream))
+        st.enter_context(mock.patch.object(torch.cuda, "Event", _Event))
+        st.enter_context(mock.patch.object(torch.cuda, "stream", lambda s: contextlib.nullcontext()))
+        st.enter_context(mock.patch.object(torch.cuda, "current_device", lambda: 0))
+        _side.clear()
         st.enter_context(mock.patch.object(torch.cuda, "current_stream", lambda *a: _Stream()))
         # a device tensor's .cpu() is a fresh host copy; keep that property for the stand-ins
         st.enter_context(mock.patch.object(torch.Tensor, "cpu", lambda self, *a, **k: self.clone()))

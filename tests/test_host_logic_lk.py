@@ -1,0 +1,139 @@
+"""CPU test of the HOST logic of pysteps_b200.motion.lucaskanade.dense_lucaskanade (kwargs
+plumbing, frame pairing and pooling, early-outs, masked-array handling, return conventions, the
+b200_rows extension) over randomised frames and argument combinations.  The C-ABI entry points are
+emulated with the oracle's stage functions (tests/cpu_abi.py), so the shim must reproduce the
+oracle's dense_lucaskanade -- itself pinned to the reference -- bit for bit; errors are compared
+with the live reference when /root/reference exists."""
+import warnings
+
+import numpy as np
+import pytest
+
+import cpu_abi
+from oracle import lucaskanade as ora
+from pysteps_b200 import _synthetic as syn
+
+
+def _live():
+    from _refimport import available, ref_module
+    if not available():
+        return None
+    try:
+        import cv2  # noqa: F401
+    except ImportError:
+        return None
+    return ref_module("pysteps.motion.lucaskanade").dense_lucaskanade
+
+
+def _random_call(rng):
+    m, n, T = int(rng.integers(40, 150)), int(rng.integers(40, 150)), int(rng.choice([1, 2, 2, 3]))
+    fr = syn.rain_frames(m, n, T, int(rng.integers(0, 1000)), dx=int(rng.integers(-4, 5)), dy=int(rng.integers(-4, 5)))
+    q = rng.random()
+    if q < 0.25:
+        fr = np.where(fr > 0.1, 10.0 * np.log10(np.maximum(fr, 0.1)), -15.0)
+    elif q < 0.32:
+        fr = np.zeros_like(fr)                       # nothing to track
+    elif q < 0.38:
+        fr = np.full_like(fr, np.nan)
+    if rng.random() < 0.3:
+        fr = np.stack([syn.nan_disc(f, float(rng.uniform(0.05, 0.3))) for f in fr])
+    kw = {}
+    if rng.random() < 0.3:
+        kw["dense"] = False
+    if rng.random() < 0.3:
+        kw["lk_kwargs"] = dict(winsize=(int(rng.choice([15, 21, 50])),) * 2, nr_levels=int(rng.integers(0, 4)))
+    if rng.random() < 0.3:
+        kw["fd_kwargs"] = dict(max_corners=int(rng.choice([20, 200, 1000])), quality_level=float(rng.choice([0.01, 0.2])),
+                               min_distance=int(rng.choice([3, 10, 25])), buffer_mask=int(rng.choice([0, 5, 12])))
+    if rng.random() < 0.15:
+        kw["fd_kwargs"] = dict(max_num_features=int(rng.choice([5, 50])))
+    if rng.random() < 0.3:
+        kw["interp_kwargs"] = dict(k=int(rng.choice([1, 4, 20, 30])), power=float(rng.choice([0.5, 1.0, 2.0])))
+    if rng.random() < 0.2:
+        kw["size_opening"] = 0
+    if rng.random() < 0.2:
+        kw["decl_scale"] = int(rng.choice([1, 5, 40]))
+    if rng.random() < 0.2:
+        kw["k_outlier"] = int(rng.choice([5, 30, 100]))
+        kw["nr_std_outlier"] = float(rng.choice([1, 2, 3]))
+    inp = fr
+    q = rng.random()
+    if q < 0.15 and np.isfinite(fr).any():
+        inp = np.ma.masked_array(np.nan_to_num(fr, nan=0.0), mask=np.isnan(fr) | (rng.random(fr.shape) < 0.01))
+    elif q < 0.2:
+        inp = fr[0]                                  # wrong rank
+    return inp, kw
+
+
+def _run(fn, inp, kw):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        try:
+            return fn(inp.copy(), **kw), None
+        except Exception as e:  # noqa: BLE001
+            return None, (type(e).__name__, str(e))
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_dense_lucaskanade_host_logic(seed):
+    from pysteps_b200.motion.lucaskanade import dense_lucaskanade
+    live = _live()
+    rng = np.random.default_rng(500 + seed)
+    n_ok = n_err = n_empty = 0
+    with cpu_abi.emulated():
+        for it in range(40):
+            inp, kw = _random_call(rng)
+            got, gerr = _run(dense_lucaskanade, inp, kw)
+            want, werr = _run(ora.dense_lucaskanade, inp, kw)
+            ctx = f"seed {seed} case {it}: shape={inp.shape} masked={isinstance(inp, np.ma.MaskedArray)} kw={kw}"
+            assert gerr == werr, ctx
+            if live is not None:
+                _, rerr = _run(live, inp, kw)
+                assert gerr == rerr, ctx
+            if gerr is not None:
+                n_err += 1
+                continue
+            n_ok += 1
+            if kw.get("dense", True):
+                assert isinstance(got, np.ndarray) and got.shape == want.shape and got.dtype == want.dtype, ctx
+                assert np.array_equal(got, want), ctx
+                n_empty += not got.any()
+            else:
+                assert isinstance(got, tuple) and len(got) == 2, ctx
+                for a, b in zip(got, want):
+                    assert a.shape == b.shape and a.dtype == b.dtype and np.array_equal(a, b), ctx
+                n_empty += got[0].shape[0] == 0
+    assert n_ok >= 25 and n_empty >= 1, (n_ok, n_err, n_empty)
+
+
+def test_row_band_fill_and_stage_mirrors():
+    from pysteps_b200 import stages
+    from pysteps_b200.motion.lucaskanade import dense_lucaskanade
+    fr = syn.rain_frames(120, 96, 3, 5, dx=2, dy=-1)
+    with cpu_abi.emulated():
+        full = dense_lucaskanade(fr)
+        for r0, r1 in ((0, 120), (0, 41), (41, 90), (77, 78)):
+            band = dense_lucaskanade(fr, interp_kwargs={"b200_rows": (r0, r1)})
+            assert band.shape == (2, r1 - r0, 96) and np.array_equal(band, full[:, r0:r1])
+        with pytest.raises(ValueError):
+            dense_lucaskanade(fr, interp_kwargs={"b200_rows": (5, 5)})
+        assert dense_lucaskanade(fr[:1], interp_kwargs={"b200_rows": (5, 9)}).shape == (2, 4, 96)
+        # the stand-alone mirrors of the helper functions (pysteps_b200.stages)
+        a = np.ma.masked_invalid(fr[0]); np.ma.set_fill_value(a, a.min())
+        b = np.ma.masked_invalid(fr[1]); np.ma.set_fill_value(b, b.min())
+        oa, ob = ora.morph_opening(a, a.min(), 3), ora.morph_opening(b, b.min(), 3)
+        ga = stages.morph_opening(a, a.min(), 3)
+        assert np.array_equal(np.ma.getmaskarray(ga), np.ma.getmaskarray(oa)) and np.array_equal(ga.filled(), oa.filled())
+        pts = stages.detection(oa)
+        assert np.array_equal(pts, ora.detection(oa))
+        xy, uv = stages.track_features(oa, ob, pts)
+        oxy, ouv = ora.track_features(oa, ob, pts.astype(np.float32))
+        assert np.array_equal(xy, oxy) and np.array_equal(uv, ouv)
+        flags = stages.detect_outliers(uv, 3, xy, 30)
+        assert np.array_equal(flags, ora.detect_outliers(uv, 3, xy, 30))
+        dxy, duv = stages.decluster(xy[~flags], uv[~flags], 20, 1)
+        o = ora.decluster(xy[~flags], uv[~flags], 20, 1)
+        assert np.array_equal(dxy, o[0]) and np.array_equal(duv, o[1])
+        g = stages.idwinterp2d(dxy, duv, np.arange(96), np.arange(120))
+        assert np.array_equal(g, ora.idwinterp2d(dxy, duv, np.arange(96), np.arange(120)))
+        assert np.array_equal(stages.idwinterp2d(dxy, duv, np.arange(96), np.arange(30, 70)), g[:, 30:70])
