@@ -93,28 +93,29 @@ int b200_sl_extrapolate_rows(const void *precip, const void *velocity,
 
 /* Displacement field after EVERY leadtime, disp_steps (T, 2, row_count, n) float64: the
  * trajectory part of b200_sl_extrapolate_rows alone (semilagrangian.py:201-219), for samplers
- * other than the built-in order-1 warp (interp_order 0 / 3 below).  Same arithmetic as the fused
+ * other than the built-in order-1 warp (interp_order 0 and 2..5 below).  Same arithmetic as the fused
  * loop: the kernel is resumed once per leadtime. */
 int b200_sl_trajectories(const void *velocity, const double *xy_coords, const double *disp_prev,
                          const double *tdiff, int T, double vel_timestep, int n_iter,
                          int velocity_dtype, int velocity_layout, int m, int n, int row_begin,
                          int row_count, double *disp_steps, void *stream);
 
-/* interp_order 0 / 3 (semilagrangian.py:144-157,224-253; scipy.ndimage.map_coordinates with
- * prefilter).  b200_spline_prepare: coeffs (m+2p, n+2p) float64, p = 12 for order 3 with
+/* interp_order 0 and 2..5 (semilagrangian.py:144-157,224-253; scipy.ndimage.map_coordinates with
+ * prefilter).  b200_spline_prepare: coeffs (m+2p, n+2p) float64, p = 12 for order >= 2 with
  * B200_MODE_NEAREST and 0 otherwise = the field (non-finite values zeroed when zero_fill) edge
- * padded and, for order 3, run through scipy's cubic B-spline prefilter (pole = double nearest to
- * sqrt(3)-2; zpow_axis0/1 = pole^(L-1) for MODE_CONSTANT ("mirror" boundary) or pole^L for
- * MODE_NEAREST ("reflect"), L the padded length of the axis, evaluated by the caller with the
- * host's pow so that it is the libm value scipy uses); for order 3 also mask_min = (precip >
- * nanmin) and mask_finite as float64 0/1 (m, n).  stats = b200_field_stats of precip.
+ * padded and, for order >= 2, run through scipy's B-spline prefilter.  poles (HOST array, order/2
+ * entries) are the filter poles -- the doubles nearest to the exact values, e.g. sqrt(3)-2 for
+ * order 3 -- and zpow_axis0/1 (HOST arrays) pole^(L-1) for MODE_CONSTANT ("mirror" boundary) or
+ * pole^L for MODE_NEAREST ("reflect"), L the padded length of the axis, evaluated by the caller
+ * with the host's pow so that it is the libm value scipy uses.  For order >= 2 also mask_min =
+ * (precip > nanmin) and mask_finite as float64 0/1 (m, n).  stats = b200_field_stats of precip.
  * b200_spline_sample: out (T, row_count, n) of out_dtype, pixel (y, x) of leadtime t sampled at
- * xy + disp_steps[t] -- 4x4 cubic taps (mirrored / clamped) or the nearest tap (order 0) -- then,
- * for order 3, reset to nanmin / NaN where the order-1 warps of the masks fall below 0.5. */
+ * xy + disp_steps[t] -- (order+1)^2 taps (mirrored / clamped) or the nearest tap (order 0) -- then,
+ * for order >= 2, reset to nanmin / NaN where the order-1 warps of the masks fall below 0.5. */
 int b200_spline_prepare(const void *precip, int precip_dtype, int m, int n, int order, int mode,
-                        const double *stats, int zero_fill, double pole, double zpow_axis0,
-                        double zpow_axis1, double *coeffs, double *mask_min, double *mask_finite,
-                        void *stream);
+                        const double *stats, int zero_fill, const double *poles,
+                        const double *zpow_axis0, const double *zpow_axis1, double *coeffs,
+                        double *mask_min, double *mask_finite, void *stream);
 int b200_spline_sample(const double *coeffs, int m, int n, int order, int mode,
                        const double *xy_coords, const double *disp_steps, int T, int row_begin,
                        int row_count, double outval, const double *mask_min,

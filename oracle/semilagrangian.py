@@ -3,8 +3,7 @@
 TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  Host-side argument
 handling restates pysteps/extrapolation/semilagrangian.py:106-179,260-266 line
 by line; the array arithmetic runs in ``sl_oracle.c`` / ``spline_oracle.c``.
-``interp_order`` 0, 1 and 3 are restated (2, 4 and 5 are not: nothing in the reference tree
-uses them).
+Every ``interp_order`` scipy accepts (0 .. 5) is restated.
 """
 import ctypes
 import warnings
@@ -21,19 +20,23 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(_dp)
 
 
-def spline_filter3(a, mode="constant"):
-    """scipy.ndimage.spline_filter(a, 3, output=float64, mode=mode) for the two boundary
+def spline_filter(a, order, mode="constant"):
+    """scipy.ndimage.spline_filter(a, order, output=float64, mode=mode) for the two boundary
     treatments map_coordinates uses: "constant" (mirror) and "nearest" (reflect)."""
     f = np.array(a, dtype=np.float64, order="C")
     L = lib()
-    L.ora_spline_filter3.restype = None
-    L.ora_spline_filter3.argtypes = [_dp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int]
-    L.ora_spline_filter3(_p(f), f.shape[0], f.shape[1], int(_MODES[mode] == 1))
+    L.ora_spline_filter.restype = None
+    L.ora_spline_filter.argtypes = [_dp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int]
+    L.ora_spline_filter(_p(f), f.shape[0], f.shape[1], int(order), int(_MODES[mode] == 1))
     return f
 
 
+def spline_filter3(a, mode="constant"):
+    return spline_filter(a, 3, mode)
+
+
 def map_coordinates_spline(a, coords, order, mode="constant", cval=0.0):
-    """scipy.ndimage.map_coordinates(a, coords, order=0|3, mode, cval, prefilter=True)."""
+    """scipy.ndimage.map_coordinates(a, coords, order=0|2|3|4|5, mode, cval, prefilter=True)."""
     a64 = np.ascontiguousarray(a, dtype=np.float64)
     cy = np.ascontiguousarray(coords[0], dtype=np.float64)
     cx = np.ascontiguousarray(coords[1], dtype=np.float64)
@@ -92,8 +95,8 @@ def extrapolate(precip, velocity, timesteps, outval=np.nan, xy_coords=None,
         raise ValueError("precip is None but return_displacement is False")
     if "D_prev" in kwargs.keys():
         warnings.warn("deprecated argument D_prev is ignored, use displacement_prev instead")
-    if interp_order not in (0, 1, 3):
-        raise NotImplementedError("oracle restates interp_order 0, 1 and 3 only")
+    if interp_order not in (0, 1, 2, 3, 4, 5):
+        raise RuntimeError("spline order not supported")  # scipy.ndimage._ni_support
     # :144-157 separate masks preserve NaN and no-precipitation values under the spline
     mask_min = mask_finite = None
     minval = 0.0

@@ -35,14 +35,19 @@
 #define ORA_MODE_NEAREST 1
 #define ORA_NPAD 12
 
-static const double POLE3 = -0.267949192431122706472553658494127633;
+/* poles of the B-spline prefilters: the doubles nearest to the exact values (decimal literals in
+ * scipy's ni_splines.c); orders 2..5 have order/2 poles */
+static const double POLES[6][2] = {
+    {0.0, 0.0}, {0.0, 0.0},
+    {-0.171572875253809902396622551580603843, 0.0},                                      /* sqrt(8) - 3 */
+    {-0.267949192431122706472553658494127633, 0.0},                                      /* sqrt(3) - 2 */
+    {-0.361341225900220177092212841325675255, -0.013725429297339121360331226939128204},
+    {-0.430575347099973791851434783493520110, -0.043096288203264653822712376822550182},
+};
 
-/* one line of n samples with stride s, in place */
-static void filter_line(double *c, int64_t n, int64_t s, double z, int reflect)
+/* one pole of one line of n samples with stride s, in place (the gain has been applied) */
+static void filter_pole(double *c, int64_t n, int64_t s, double z, int reflect)
 {
-    if (n <= 1) return;
-    const double gain = (1.0 - z) * (1.0 - 1.0 / z);
-    for (int64_t i = 0; i < n; i++) c[i * s] *= gain;
     if (!reflect) {
         double z_i = z;
         const double z_n_1 = pow(z, (double)(n - 1));
@@ -72,13 +77,33 @@ static void filter_line(double *c, int64_t n, int64_t s, double z, int reflect)
     for (int64_t i = n - 2; i >= 0; i--) c[i * s] = z * (c[(i + 1) * s] - c[i * s]);
 }
 
-/* scipy.ndimage.spline_filter(a, 3, mode="mirror"|"reflect") of an (m, n) array, in place */
+/* one line: gain of all poles first, then pole after pole */
+static void filter_line(double *c, int64_t n, int64_t s, int order, int reflect)
+{
+    if (n <= 1) return;
+    const int npoles = order / 2;
+    double gain = 1.0;
+    for (int k = 0; k < npoles; k++) {
+        const double z = POLES[order][k];
+        gain *= (1.0 - z) * (1.0 - 1.0 / z);
+    }
+    for (int64_t i = 0; i < n; i++) c[i * s] *= gain;
+    for (int k = 0; k < npoles; k++) filter_pole(c, n, s, POLES[order][k], reflect);
+}
+
+/* scipy.ndimage.spline_filter(a, order, mode="mirror"|"reflect") of an (m, n) array, in place */
+void ora_spline_filter(double *a, int64_t m, int64_t n, int order, int reflect)
+{
+    if (order < 2) return;
+#pragma omp parallel for schedule(static)
+    for (int64_t j = 0; j < n; j++) filter_line(a + j, m, n, order, reflect);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < m; i++) filter_line(a + i * n, n, 1, order, reflect);
+}
+
 void ora_spline_filter3(double *a, int64_t m, int64_t n, int reflect)
 {
-#pragma omp parallel for schedule(static)
-    for (int64_t j = 0; j < n; j++) filter_line(a + j, m, n, POLE3, reflect);
-#pragma omp parallel for schedule(static)
-    for (int64_t i = 0; i < m; i++) filter_line(a + i * n, n, 1, POLE3, reflect);
+    ora_spline_filter(a, m, n, 3, reflect);
 }
 
 static inline int64_t mirror_index(int64_t idx, int64_t len)
@@ -113,18 +138,58 @@ static inline int64_t tap(int64_t base, int64_t off, int64_t len, int mode)
     return i < 0 ? 0 : (i >= len ? len - 1 : i);
 }
 
-static inline void weights3(double x, double *w)
+/* get_spline_interpolation_weights of scipy's ni_splines.c: x becomes the offset from the middle
+ * knot (odd orders: c - floor(c), even orders: c - floor(c + 0.5)); the last weight is one minus
+ * the others */
+static inline void spline_weights(double x, int order, double *w)
 {
-    x -= floor(x);
-    const double y = x, z = 1.0 - x;
-    w[1] = (y * y * (y - 2.0) * 3.0 + 4.0) / 6.0;
-    w[2] = (z * z * (z - 2.0) * 3.0 + 4.0) / 6.0;
-    w[0] = z * z * z / 6.0;
-    w[3] = 1.0;
-    for (int i = 0; i < 3; i++) w[3] -= w[i];
+    double y, z, t;
+    if (order & 1) x -= floor(x); else x -= floor(x + 0.5);
+    y = x;
+    z = 1.0 - x;
+    switch (order) {
+    case 1:
+        w[0] = 1.0 - x;
+        break;
+    case 2:
+        w[1] = 0.75 - x * x;
+        y = 0.5 - x;
+        w[0] = 0.5 * y * y;
+        break;
+    case 3:
+        w[1] = (y * y * (y - 2.0) * 3.0 + 4.0) / 6.0;
+        w[2] = (z * z * (z - 2.0) * 3.0 + 4.0) / 6.0;
+        w[0] = z * z * z / 6.0;
+        break;
+    case 4:
+        t = x * x;
+        w[2] = t * (t * 0.25 - 0.625) + 115.0 / 192.0;
+        y = 1.0 + x;
+        w[1] = y * (y * (y * (5.0 - y) / 6.0 - 1.25) + 5.0 / 24.0) + 55.0 / 96.0;
+        w[3] = z * (z * (z * (5.0 - z) / 6.0 - 1.25) + 5.0 / 24.0) + 55.0 / 96.0;
+        t = 0.5 - x;
+        t *= t;
+        w[0] = t * t / 24.0;
+        break;
+    case 5:
+        t = y * y;
+        w[2] = t * (t * (0.25 - y / 12.0) - 0.5) + 0.55;
+        t = z * z;
+        w[3] = t * (t * (0.25 - z / 12.0) - 0.5) + 0.55;
+        y += 1.0;
+        w[1] = y * (y * (y * (y * (y / 24.0 - 0.375) + 1.25) - 1.75) + 0.625) + 0.425;
+        z += 1.0;
+        w[4] = z * (z * (z * (z * (z / 24.0 - 0.375) + 1.25) - 1.75) + 0.625) + 0.425;
+        z = 1.0 - x;
+        t = z * z;
+        w[0] = z * t * t / 120.0;
+        break;
+    }
+    w[order] = 1.0;
+    for (int i = 0; i < order; i++) w[order] -= w[i];
 }
 
-/* one sample of order 0 or 3 from the (already filtered and, for mode nearest, padded) array f
+/* one sample of order 0 or 2..5 from the (already filtered and, for mode nearest, padded) array f
  * of shape (M, N); cy/cx are coordinates in the ORIGINAL frame, npad the padding of f */
 double ora_sample_spline(const double *f, int64_t M, int64_t N, double cy, double cx, int order,
                          int mode, double cval, int64_t npad)
@@ -143,18 +208,19 @@ double ora_sample_spline(const double *f, int64_t M, int64_t N, double cy, doubl
         t += f[iy * N + ix];
         return t;
     }
-    const int64_t by = cast_floor(floor(cy)), bx = cast_floor(floor(cx));
-    int64_t ys[4], xs[4];
-    for (int l = 0; l < 4; l++) {
-        ys[l] = tap(by, l - 1, M, mode);
-        xs[l] = tap(bx, l - 1, N, mode);
+    const int64_t by = cast_floor((order & 1) ? floor(cy) : floor(cy + 0.5));
+    const int64_t bx = cast_floor((order & 1) ? floor(cx) : floor(cx + 0.5));
+    int64_t ys[6], xs[6];
+    for (int l = 0; l <= order; l++) {
+        ys[l] = tap(by, l - order / 2, M, mode);
+        xs[l] = tap(bx, l - order / 2, N, mode);
     }
-    double wy[4], wx[4];
-    weights3(cy, wy);
-    weights3(cx, wx);
+    double wy[6], wx[6];
+    spline_weights(cy, order, wy);
+    spline_weights(cx, order, wx);
     double t = 0.0;
-    for (int j = 0; j < 4; j++)
-        for (int k = 0; k < 4; k++) {
+    for (int j = 0; j <= order; j++)
+        for (int k = 0; k <= order; k++) {
             double c = f[ys[j] * N + xs[k]];
             c *= wy[j];
             c *= wx[k];
@@ -183,11 +249,11 @@ double *ora_spline_prepare(const double *a, int64_t m, int64_t n, int order, int
             f[i * (*N) + j] = a[si * n + sj];
         }
     }
-    if (order > 1) ora_spline_filter3(f, *M, *N, mode == ORA_MODE_NEAREST);
+    if (order > 1) ora_spline_filter(f, *M, *N, order, mode == ORA_MODE_NEAREST);
     return f;
 }
 
-/* scipy.ndimage.map_coordinates(a, [cy, cx], order in {0, 3}, mode, cval, prefilter=True) */
+/* scipy.ndimage.map_coordinates(a, [cy, cx], order in {0, 2, 3, 4, 5}, mode, cval, prefilter=True) */
 int ora_map_coordinates_spline(const double *a, int64_t m, int64_t n, const double *cy,
                                const double *cx, int64_t npts, int order, int mode, double cval,
                                double *out)

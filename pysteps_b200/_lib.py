@@ -39,8 +39,8 @@ _SIGNATURES = {
     "b200_sl_interleave_velocity": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "b200_sl_trajectories": (c_int, [c_void_p, c_void_p, c_void_p, c_dp, c_int, c_double, c_int, c_int, c_int,
                                      c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
-    "b200_spline_prepare": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_double,
-                                    c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200_spline_prepare": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_dp,
+                                    c_dp, c_dp, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200_spline_sample": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
                                    c_int, c_double, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "b200_bps_perturb_velocity": (c_int, [c_void_p, c_int, c_int, c_int, c_double, c_double, c_double,

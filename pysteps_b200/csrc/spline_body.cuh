@@ -54,29 +54,30 @@ SPL_FN void prepare_element(size_t e, const F *precip, int m, int n, int pad, co
     }
 }
 
-// ---- one line of the prefilter: L samples with stride S, in place --------------------------------
-// reflect == 0: scipy's "mirror" initialisation, zpow = z^(L-1); reflect != 0: "reflect", zpow = z^L
-SPL_FN void filter_line(double *c, int L, size_t S, double z, double gain, double zpow, int reflect) {
-    if (L <= 1) return;
-#define SPL_G(i) mul(c[(size_t)(i) * S], gain) /* the gained sample */
+// ---- one line of the prefilter: L samples with stride S, in place -------------------------------
+// scipy's apply_filter: the gain of all poles first, then for every pole z the causal
+// initialisation, the causal recursion, the anti-causal initialisation and recursion.
+// reflect == 0: "mirror" initialisation, zpow = z^(L-1); reflect != 0: "reflect", zpow = z^L
+SPL_FN void filter_pole(double *c, int L, size_t S, double z, double zpow, int reflect) {
+#define SPL_C(i) c[(size_t)(i) * S]
     double s;
     if (!reflect) {
         double z_i = z;
-        s = add(SPL_G(0), mul(zpow, SPL_G(L - 1)));
+        s = add(SPL_C(0), mul(zpow, SPL_C(L - 1)));
         for (int i = 1; i < L - 1; i++) {
-            s = add(s, mul(z_i, add(SPL_G(i), mul(zpow, SPL_G(L - 1 - i)))));
+            s = add(s, mul(z_i, add(SPL_C(i), mul(zpow, SPL_C(L - 1 - i)))));
             z_i = mul(z_i, z);
         }
         s = dvd(s, sub(1.0, mul(zpow, zpow)));
     } else {
         double z_i = z;
-        const double c0 = SPL_G(0);
-        s = add(c0, mul(zpow, SPL_G(L - 1)));
+        const double c0 = SPL_C(0);
+        s = add(c0, mul(zpow, SPL_C(L - 1)));
         for (int i = 1; i < L; i++) {
             // scipy accumulates into c[0] in place, so the last term (i == L-1) pairs c[L-1]
             // with the PARTIAL SUM standing in c[0], not with the original first sample
-            const double partner = (i == L - 1) ? s : SPL_G(L - 1 - i);
-            s = add(s, mul(z_i, add(SPL_G(i), mul(zpow, partner))));
+            const double partner = (i == L - 1) ? s : SPL_C(L - 1 - i);
+            s = add(s, mul(z_i, add(SPL_C(i), mul(zpow, partner))));
             z_i = mul(z_i, z);
         }
         s = mul(s, dvd(z, sub(1.0, mul(zpow, zpow))));
@@ -85,28 +86,40 @@ SPL_FN void filter_line(double *c, int L, size_t S, double z, double gain, doubl
     // causal recursion c[i] += z * c[i-1]
     double prev = s;
     double before = s;  // c[L-2] after the causal pass
+    SPL_C(0) = s;
     for (int i = 1; i < L; i++) {
-        const double cur = add(SPL_G(i), mul(z, prev));
-        c[(size_t)i * S] = cur;
+        const double cur = add(SPL_C(i), mul(z, prev));
+        SPL_C(i) = cur;
         before = prev;
         prev = cur;
     }
-    c[0] = s;
-#undef SPL_G
     // anti-causal initialisation
     double last;
     if (!reflect)
         last = dvd(mul(add(mul(z, before), prev), z), sub(mul(z, z), 1.0));
     else
         last = mul(prev, dvd(z, sub(z, 1.0)));
-    c[(size_t)(L - 1) * S] = last;
+    SPL_C(L - 1) = last;
     // anti-causal recursion c[i] = z * (c[i+1] - c[i])
     double next = last;
     for (int i = L - 2; i >= 0; i--) {
-        const double cur = mul(z, sub(next, c[(size_t)i * S]));
-        c[(size_t)i * S] = cur;
+        const double cur = mul(z, sub(next, SPL_C(i)));
+        SPL_C(i) = cur;
         next = cur;
     }
+#undef SPL_C
+}
+
+struct FilterParams {
+    int npoles, reflect;
+    double gain;        // prod over poles of (1 - z)(1 - 1/z), evaluated on the host
+    double z[2], zpow[2];
+};
+
+SPL_FN void filter_line(double *c, int L, size_t S, const FilterParams &fp) {
+    if (L <= 1) return;
+    for (int i = 0; i < L; i++) c[(size_t)i * S] = mul(c[(size_t)i * S], fp.gain);
+    for (int k = 0; k < fp.npoles; k++) filter_pole(c, L, S, fp.z[k], fp.zpow[k], fp.reflect);
 }
 
 // ---- (R, C) -> (C, R) through a 32x32 tile: the two phases of one thread (tx < 32, ty < 8) of a
@@ -151,13 +164,51 @@ SPL_FN long long tap_index(long long base, long long off, long long len, int mod
     return i < 0 ? 0 : (i >= len ? len - 1 : i);
 }
 
-SPL_FN void cubic_weights(double x, double *w) {
-    x = sub(x, floor(x));
-    const double y = x, z = sub(1.0, x);
-    w[1] = dvd(add(mul(mul(mul(y, y), sub(y, 2.0)), 3.0), 4.0), 6.0);
-    w[2] = dvd(add(mul(mul(mul(z, z), sub(z, 2.0)), 3.0), 4.0), 6.0);
-    w[0] = dvd(mul(mul(z, z), z), 6.0);
-    w[3] = sub(sub(sub(1.0, w[0]), w[1]), w[2]);
+// get_spline_interpolation_weights of scipy's ni_splines.c (orders 2..5): x becomes the offset from
+// the middle knot, the last weight is one minus the others
+SPL_FN void spline_weights(double x, int order, double *w) {
+    x = (order & 1) ? sub(x, floor(x)) : sub(x, floor(add(x, 0.5)));
+    double y = x, z = sub(1.0, x), t;
+    switch (order) {
+    case 2:
+        w[1] = sub(0.75, mul(x, x));
+        y = sub(0.5, x);
+        w[0] = mul(mul(0.5, y), y);
+        break;
+    case 3:
+        w[1] = dvd(add(mul(mul(mul(y, y), sub(y, 2.0)), 3.0), 4.0), 6.0);
+        w[2] = dvd(add(mul(mul(mul(z, z), sub(z, 2.0)), 3.0), 4.0), 6.0);
+        w[0] = dvd(mul(mul(z, z), z), 6.0);
+        break;
+    case 4:
+        t = mul(x, x);
+        w[2] = add(mul(t, sub(mul(t, 0.25), 0.625)), 115.0 / 192.0);
+        y = add(1.0, x);
+        w[1] = add(mul(y, add(mul(y, sub(dvd(mul(y, sub(5.0, y)), 6.0), 1.25)), 5.0 / 24.0)), 55.0 / 96.0);
+        w[3] = add(mul(z, add(mul(z, sub(dvd(mul(z, sub(5.0, z)), 6.0), 1.25)), 5.0 / 24.0)), 55.0 / 96.0);
+        t = sub(0.5, x);
+        t = mul(t, t);
+        w[0] = dvd(mul(t, t), 24.0);
+        break;
+    case 5:
+        t = mul(y, y);
+        w[2] = add(mul(t, sub(mul(t, sub(0.25, dvd(y, 12.0))), 0.5)), 0.55);
+        t = mul(z, z);
+        w[3] = add(mul(t, sub(mul(t, sub(0.25, dvd(z, 12.0))), 0.5)), 0.55);
+        y = add(y, 1.0);
+        w[1] = add(mul(y, add(mul(y, sub(mul(y, add(mul(y, sub(dvd(y, 24.0), 0.375)), 1.25)), 1.75)), 0.625)), 0.425);
+        z = add(z, 1.0);
+        w[4] = add(mul(z, add(mul(z, sub(mul(z, add(mul(z, sub(dvd(z, 24.0), 0.375)), 1.25)), 1.75)), 0.625)), 0.425);
+        z = sub(1.0, x);
+        t = mul(z, z);
+        w[0] = dvd(mul(mul(z, t), t), 120.0);
+        break;
+    default:
+        break;
+    }
+    double last = 1.0;
+    for (int i = 0; i < order; i++) last = sub(last, w[i]);
+    w[order] = last;
 }
 
 // scipy map_coordinates(order=1, prefilter=False) of a float64 (m, n) array, generic path
@@ -223,18 +274,20 @@ SPL_FN double sample_pixel(const SampleParams &p, int x, int yl, int t) {
         const long long ix = tap_index(cast_floor(floor(add(cx, 0.5))), 0, N, p.mode);
         v = add(0.0, ld(p.coeffs + iy * N + ix));
     } else {
-        const long long by = cast_floor(floor(cy)), bx = cast_floor(floor(cx));
-        long long ys[4], xs[4];
-        for (int l = 0; l < 4; l++) {
-            ys[l] = tap_index(by, l - 1, M, p.mode);
-            xs[l] = tap_index(bx, l - 1, N, p.mode);
+        const int order = p.order, half = p.order / 2;
+        const long long by = cast_floor((order & 1) ? floor(cy) : floor(add(cy, 0.5)));
+        const long long bx = cast_floor((order & 1) ? floor(cx) : floor(add(cx, 0.5)));
+        long long ys[6], xs[6];
+        for (int l = 0; l <= order; l++) {
+            ys[l] = tap_index(by, l - half, M, p.mode);
+            xs[l] = tap_index(bx, l - half, N, p.mode);
         }
-        double wy[4], wx[4];
-        cubic_weights(cy, wy);
-        cubic_weights(cx, wx);
+        double wy[6], wx[6];
+        spline_weights(cy, order, wy);
+        spline_weights(cx, order, wx);
         v = 0.0;
-        for (int j = 0; j < 4; j++)
-            for (int k = 0; k < 4; k++) v = add(v, mul(mul(ld(p.coeffs + ys[j] * N + xs[k]), wy[j]), wx[k]));
+        for (int j = 0; j <= order; j++)
+            for (int k = 0; k <= order; k++) v = add(v, mul(mul(ld(p.coeffs + ys[j] * N + xs[k]), wy[j]), wx[k]));
     }
     if (p.order > 1) {  // :234-253
         if (sample_order1(p.mask_min, p.m, p.n, cy0, cx0, p.mode, 0.0) < 0.5) v = p.stats[1];

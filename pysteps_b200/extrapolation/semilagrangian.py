@@ -91,7 +91,7 @@ def extrapolate(precip, velocity, timesteps, outval=np.nan, xy_coords=None,
                 allow_nonfinite_values=False, vel_timestep=1, **kwargs):
     """Semi-Lagrangian backward extrapolation; same contract as the reference
     (see its docstring, semilagrangian.py:30-104).  Differences: ``interp_order``
-    must be 1 (0 and 3 are built -- csrc/spline.cu -- but stay behind
+    must be 1 (0 and 2..5 are built -- csrc/spline.cu -- but stay behind
     ``PYSTEPS_B200_ENABLE_SPLINE=1`` until they have been verified on hardware) and
     ``map_coordinates_mode`` one of "constant"/"nearest" (anything else raises
     NotImplementedError instead of silently using a CPU path).
@@ -154,9 +154,15 @@ def extrapolate(precip, velocity, timesteps, outval=np.nan, xy_coords=None,
     return result
 
 
-# pole of the cubic B-spline prefilter: the double nearest to sqrt(3) - 2 (a decimal literal in
-# scipy's ni_splines.c; sqrt(3.0) - 2.0 evaluated in double is 2 ulp away)
-_POLE3 = -0.267949192431122706472553658494127633
+# poles of the B-spline prefilters: the doubles nearest to the exact values (decimal literals in
+# scipy's ni_splines.c; e.g. sqrt(3.0) - 2.0 evaluated in double is 2 ulp away from the first one)
+_POLES = {
+    0: (),
+    2: (-0.171572875253809902396622551580603843,),                                        # sqrt(8) - 3
+    3: (-0.267949192431122706472553658494127633,),                                        # sqrt(3) - 2
+    4: (-0.361341225900220177092212841325675255, -0.013725429297339121360331226939128204),
+    5: (-0.430575347099973791851434783493520110, -0.043096288203264653822712376822550182),
+}
 _SPLINE_PAD = 12  # scipy.ndimage._prepad_for_spline_filter, mode "nearest"
 
 
@@ -188,12 +194,13 @@ def _extrapolate_checked(precip, velocity, d_precip, d_vel, stats, on_device, ti
     if "D_prev" in kwargs.keys():
         deferred_warnings.append("deprecated argument D_prev is ignored, use displacement_prev instead")
 
-    if interp_order not in (0, 1, 3) or (interp_order != 1 and not _spline_enabled()):
+    if interp_order not in (0, 1, 2, 3, 4, 5):
+        raise RuntimeError("spline order not supported")  # scipy.ndimage._ni_support._check_order
+    if interp_order != 1 and not _spline_enabled():
         raise NotImplementedError(
             "pysteps_b200 semilagrangian: only interp_order=1 is implemented on the GPU "
-            f"(got {interp_order}); no CPU fallback is provided"
-            + (" -- orders 0 and 3 are built but not yet verified on hardware; "
-               "PYSTEPS_B200_ENABLE_SPLINE=1 enables them" if interp_order in (0, 3) else ""))
+            f"(got {interp_order}); no CPU fallback is provided -- orders 0 and 2..5 are built but "
+            "not yet verified on hardware; PYSTEPS_B200_ENABLE_SPLINE=1 enables them")
     if map_coordinates_mode not in _MODES:
         raise NotImplementedError(
             "pysteps_b200 semilagrangian: map_coordinates_mode must be 'constant' or "
@@ -296,9 +303,12 @@ def _extrapolate_checked(precip, velocity, d_precip, d_vel, stats, on_device, ti
             d_mmin = torch.empty((m, n), dtype=torch.float64, device="cuda")
             d_mfin = torch.empty((m, n), dtype=torch.float64, device="cuda")
         d_stats = stats.buf[0]
+        poles = np.array(_POLES[int(interp_order)] + (0.0,), dtype=np.float64)
+        zp0 = np.array([math.pow(z, M if reflect else M - 1) for z in poles], dtype=np.float64)
+        zp1 = np.array([math.pow(z, N if reflect else N - 1) for z in poles], dtype=np.float64)
         _lib.call("b200_spline_prepare", d_precip.data_ptr(), _device.dtype_code(d_precip.dtype), m, n,
-                  int(interp_order), mode, d_stats.data_ptr(), int(zero_fill), _POLE3,
-                  math.pow(_POLE3, M if reflect else M - 1), math.pow(_POLE3, N if reflect else N - 1),
+                  int(interp_order), mode, d_stats.data_ptr(), int(zero_fill),
+                  poles.ctypes.data_as(_lib.c_dp), zp0.ctypes.data_as(_lib.c_dp), zp1.ctypes.data_as(_lib.c_dp),
                   d_coeffs.data_ptr(), _device.ptr(d_mmin), _device.ptr(d_mfin), _device.stream_ptr())
         _lib.call("b200_spline_sample", d_coeffs.data_ptr(), m, n, int(interp_order), mode, _device.ptr(d_xy),
                   d_steps.data_ptr(), T, r0, mb, float(outval), _device.ptr(d_mmin), _device.ptr(d_mfin),

@@ -101,11 +101,11 @@ def _spline_prepare(precip, pdt, m, n, order, mode, stats, zero_fill, pole, zp0,
     L = host_kernels.lib()
     L.host_spline_prepare.restype = None
     L.host_spline_prepare.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                      ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_double,
-                                      ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p,
+                                      ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                       ctypes.c_void_p]
-    L.host_spline_prepare(_addr(precip), pdt, m, n, order, mode, _addr(stats), zero_fill, pole, zp0, zp1,
-                          _addr(coeffs), _addr(mmin), _addr(mfin))
+    L.host_spline_prepare(_addr(precip), pdt, m, n, order, mode, _addr(stats), zero_fill, _addr(pole),
+                          _addr(zp0), _addr(zp1), _addr(coeffs), _addr(mmin), _addr(mfin))
 
 
 def _spline_sample(coeffs, m, n, order, mode, xy, steps, T, r0, rows, outval, mmin, mfin, stats, odt, out,

@@ -28,8 +28,8 @@ void host_transpose(const double *in, double *out, int R, int C) {
 
 // == b200_spline_prepare
 void host_spline_prepare(const void *precip, int precip_dtype, int m, int n, int order, int mode,
-                         const double *stats, int zero_fill, double pole, double zpow_axis0, double zpow_axis1,
-                         double *coeffs, double *mask_min, double *mask_fin) {
+                         const double *stats, int zero_fill, const double *poles, const double *zpow_axis0,
+                         const double *zpow_axis1, double *coeffs, double *mask_min, double *mask_fin) {
     const int pad = host_spline_pad(order, mode);
     const int M = m + 2 * pad, N = n + 2 * pad;
     const size_t total = (size_t)M * N;
@@ -43,13 +43,25 @@ void host_spline_prepare(const void *precip, int precip_dtype, int m, int n, int
                                          mask_min, mask_fin);
     }
     if (order <= 1) return;
-    const int reflect = mode == B200_MODE_NEAREST;
-    const double gain = (1.0 - pole) * (1.0 - 1.0 / pole);
+    spl::FilterParams f0;
+    memset(&f0, 0, sizeof(f0));
+    f0.npoles = order / 2;
+    f0.reflect = mode == B200_MODE_NEAREST;
+    f0.gain = 1.0;
+    for (int k = 0; k < f0.npoles; k++) {
+        f0.z[k] = poles[k];
+        f0.gain *= (1.0 - poles[k]) * (1.0 - 1.0 / poles[k]);
+    }
+    spl::FilterParams f1 = f0;
+    for (int k = 0; k < f0.npoles; k++) {
+        f0.zpow[k] = zpow_axis0[k];
+        f1.zpow[k] = zpow_axis1[k];
+    }
     // the launch sequence of b200_spline_prepare: columns, transpose, columns, transpose back
-    for (int j = 0; j < N; j++) spl::filter_line(coeffs + j, M, (size_t)N, pole, gain, zpow_axis0, reflect);
+    for (int j = 0; j < N; j++) spl::filter_line(coeffs + j, M, (size_t)N, f0);
     double *tr = new double[total];
     host_transpose(coeffs, tr, M, N);
-    for (int j = 0; j < M; j++) spl::filter_line(tr + j, N, (size_t)M, pole, gain, zpow_axis1, reflect);
+    for (int j = 0; j < M; j++) spl::filter_line(tr + j, N, (size_t)M, f1);
     host_transpose(tr, coeffs, N, M);
     delete[] tr;
 }

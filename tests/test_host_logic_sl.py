@@ -185,12 +185,12 @@ def test_spline_orders_host_logic_and_kernel_bodies(seed, monkeypatch):
         with pytest.raises(NotImplementedError, match="PYSTEPS_B200_ENABLE_SPLINE"):
             extrap(np.ones((4, 4)), np.ones((2, 4, 4)), 1, interp_order=3)
         monkeypatch.setenv("PYSTEPS_B200_ENABLE_SPLINE", "1")
-        with pytest.raises(NotImplementedError):
-            extrap(np.ones((4, 4)), np.ones((2, 4, 4)), 1, interp_order=2)
+        with pytest.raises(RuntimeError, match="spline order not supported"):
+            extrap(np.ones((4, 4)), np.ones((2, 4, 4)), 1, interp_order=6)
         n_ok = 0
         for it in range(60):
             Pin, Vin, ts, outval, kw = _random_call(rng)
-            kw["interp_order"] = int(rng.choice([0, 3, 3]))
+            kw["interp_order"] = int(rng.choice([0, 2, 3, 3, 4, 5]))
             want, werr, wdep = _run(ref, Pin, Vin, ts, outval, kw)
             got, gerr, gdep = _run(extrap, Pin, Vin, ts, outval, kw)
             ctx = f"seed {seed} case {it}: ts={ts!r} outval={outval!r} kw={ {k: (v.shape if isinstance(v, np.ndarray) else v) for k, v in kw.items()} }"

@@ -13,7 +13,9 @@ from conftest import assert_bits_equal
 import host_kernels
 from oracle import semilagrangian as ora
 
-POLE3 = -0.267949192431122706472553658494127633
+POLES = {0: (), 2: (-0.171572875253809902396622551580603843,), 3: (-0.267949192431122706472553658494127633,),
+         4: (-0.361341225900220177092212841325675255, -0.013725429297339121360331226939128204),
+         5: (-0.430575347099973791851434783493520110, -0.043096288203264653822712376822550182)}
 F32, F64 = 0, 1
 MODES = {"constant": 0, "nearest": 1}
 _dp = ctypes.POINTER(ctypes.c_double)
@@ -41,18 +43,21 @@ def _prepare(P, order, mode, zero_fill):
     stats = _stats(P)
     L.host_spline_prepare.restype = None
     L.host_spline_prepare.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                      ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_double,
-                                      ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p,
+                                      ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                       ctypes.c_void_p]
+    poles = np.array(POLES[order] + (0.0,))
+    zp0 = np.array([math.pow(z, M if reflect else M - 1) for z in poles])
+    zp1 = np.array([math.pow(z, N if reflect else N - 1) for z in poles])
     L.host_spline_prepare(_p(P), F32 if P.dtype == np.float32 else F64, m, n, order, MODES[mode], _p(stats),
-                          int(zero_fill), POLE3, math.pow(POLE3, M if reflect else M - 1),
-                          math.pow(POLE3, N if reflect else N - 1), _p(coeffs), _p(mmin), _p(mfin))
+                          int(zero_fill), _p(poles), _p(zp0), _p(zp1), _p(coeffs), _p(mmin), _p(mfin))
     return coeffs, mmin, mfin, stats, pad
 
 
+@pytest.mark.parametrize("order", [2, 3, 4, 5])
 @pytest.mark.parametrize("shape", [(9, 13), (1, 7), (5, 1), (2, 2), (1, 1), (40, 33)])
 @pytest.mark.parametrize("mode", ["constant", "nearest"])
-def test_prepare_and_prefilter_bodies(shape, mode):
+def test_prepare_and_prefilter_bodies(shape, mode, order):
     from scipy import ndimage as ndi
     rng = np.random.default_rng(shape[0] * 31 + shape[1])
     for dtype in (np.float64, np.float32):
@@ -61,11 +66,11 @@ def test_prepare_and_prefilter_bodies(shape, mode):
         for zero_fill in (False, True):
             if not zero_fill:
                 P = np.nan_to_num(P, nan=1.5)
-            coeffs, mmin, mfin, stats, pad = _prepare(P, 3, mode, zero_fill)
+            coeffs, mmin, mfin, stats, pad = _prepare(P, order, mode, zero_fill)
             src = np.where(np.isfinite(P), P, 0.0).astype(np.float64) if zero_fill else P.astype(np.float64)
             padded = np.pad(src, pad, mode="edge") if pad else src
-            assert_bits_equal(coeffs, ndi.spline_filter(padded, 3, output=np.float64, mode=mode), "coefficients")
-            assert_bits_equal(coeffs, ora.spline_filter3(padded, mode), "coefficients vs oracle")
+            assert_bits_equal(coeffs, ndi.spline_filter(padded, order, output=np.float64, mode=mode), "coefficients")
+            assert_bits_equal(coeffs, ora.spline_filter(padded, order, mode), "coefficients vs oracle")
             minval = np.nanmin(P)
             assert_bits_equal(mmin, (P > minval).astype(float), "mask_min")      # semilagrangian.py:148
             assert_bits_equal(mfin, np.isfinite(P).astype(float) if zero_fill else np.ones(shape), "mask_finite")
@@ -74,7 +79,7 @@ def test_prepare_and_prefilter_bodies(shape, mode):
     assert pad == 0 and np.array_equal(coeffs, P.astype(np.float64), equal_nan=True) and np.all(mmin == -1.0)
 
 
-@pytest.mark.parametrize("order", [0, 3])
+@pytest.mark.parametrize("order", [0, 2, 3, 4, 5])
 @pytest.mark.parametrize("mode", ["constant", "nearest"])
 def test_sample_body_reproduces_the_oracle_extrapolator(mode, order):
     """prepare + sample bodies, fed with per-leadtime displacements, == the oracle's (reference-

@@ -1,5 +1,5 @@
 """CPU tests: the spline part of the semi-Lagrangian oracle (oracle/spline_oracle.c --
-scipy.ndimage.map_coordinates for orders 0 and 3 with prefilter) is pinned bit for bit against
+scipy.ndimage.map_coordinates for orders 0 and 2..5 with prefilter) is pinned bit for bit against
 the scipy binary; the extrapolator with interp_order 0 / 3 against the reference's stored
 outputs (tests/test_oracle_sl.py, SPLINE_CASES) and, when /root/reference exists, the live
 reference."""
@@ -15,19 +15,20 @@ from oracle import semilagrangian as ora
 SHAPES = [(9, 13), (1, 7), (5, 1), (2, 2), (1, 1), (3, 40), (64, 80)]
 
 
+@pytest.mark.parametrize("order", [2, 3, 4, 5])
 @pytest.mark.parametrize("shape", SHAPES)
-def test_prefilter_matches_scipy_bitwise(shape):
+def test_prefilter_matches_scipy_bitwise(shape, order):
     rng = np.random.default_rng(shape[0] * 100 + shape[1])
     a = rng.standard_normal(shape) * 10
-    assert_bits_equal(ora.spline_filter3(a, "constant"),
-                      ndi.spline_filter(a, 3, output=np.float64, mode="constant"), "mirror")
+    assert_bits_equal(ora.spline_filter(a, order, "constant"),
+                      ndi.spline_filter(a, order, output=np.float64, mode="constant"), "mirror")
     # mode "nearest": 12-sample edge padding + the reflect boundary (ndimage._prepad_for_spline_filter)
     p = np.pad(a, 12, mode="edge")
-    assert_bits_equal(ora.spline_filter3(p, "nearest"),
-                      ndi.spline_filter(p, 3, output=np.float64, mode="nearest"), "reflect")
+    assert_bits_equal(ora.spline_filter(p, order, "nearest"),
+                      ndi.spline_filter(p, order, output=np.float64, mode="nearest"), "reflect")
 
 
-@pytest.mark.parametrize("order", [0, 3])
+@pytest.mark.parametrize("order", [0, 2, 3, 4, 5])
 @pytest.mark.parametrize("mode", ["constant", "nearest"])
 @pytest.mark.parametrize("shape", SHAPES)
 def test_samples_match_scipy_bitwise(shape, mode, order):
@@ -73,7 +74,7 @@ def test_extrapolate_spline_orders_against_live_reference():
         m, n = int(rng.integers(1, 30)), int(rng.integers(1, 30))
         P = (rng.standard_normal((m, n)) * 5).astype(rng.choice([np.float64, np.float32]))
         V = (rng.standard_normal((2, m, n)) * rng.choice([0.5, 3.0, 20.0])).astype(rng.choice([np.float64, np.float32]))
-        kw = {"interp_order": int(rng.choice([0, 3, 3])), "map_coordinates_mode": str(rng.choice(["constant", "nearest"]))}
+        kw = {"interp_order": int(rng.choice([0, 2, 3, 3, 4, 5])), "map_coordinates_mode": str(rng.choice(["constant", "nearest"]))}
         if rng.random() < 0.4:
             P[rng.random((m, n)) < 0.2] = np.nan
             kw["allow_nonfinite_values"] = True
@@ -95,5 +96,8 @@ def test_extrapolate_spline_orders_against_live_reference():
         if werr is None:
             for a, b in zip(got if isinstance(got, tuple) else (got,), want if isinstance(want, tuple) else (want,)):
                 assert_bits_equal(a, b, f"case {it} {kw}")
-    with pytest.raises(NotImplementedError):
-        ora.extrapolate(np.ones((4, 4)), np.ones((2, 4, 4)), 1, interp_order=2)
+    with pytest.raises(RuntimeError) as e_ora:
+        ora.extrapolate(np.ones((4, 4)), np.ones((2, 4, 4)), 1, interp_order=6)
+    with pytest.raises(RuntimeError) as e_ref:
+        ref(np.ones((4, 4)), np.ones((2, 4, 4)), 1, interp_order=6)
+    assert str(e_ora.value) == str(e_ref.value)

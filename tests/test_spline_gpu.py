@@ -1,4 +1,4 @@
-"""GPU parity tests of interp_order 0 / 3 (csrc/spline.cu).  The path is built and its kernel
+"""GPU parity tests of interp_order 0 and 2..5 (csrc/spline.cu).  The path is built and its kernel
 bodies and host logic are verified on the CPU (tests/test_kernel_bodies.py,
 tests/test_host_logic_sl.py) but it has not run on hardware yet, so it stays behind
 PYSTEPS_B200_ENABLE_SPLINE=1 and these tests are skipped unless that variable is set:
@@ -36,7 +36,7 @@ def test_reference_goldens(extrap):
             assert_bits_equal(disp, golden[name + "/disp"], name + " displacement")
 
 
-@pytest.mark.parametrize("order", [0, 3])
+@pytest.mark.parametrize("order", [0, 2, 3, 4, 5])
 @pytest.mark.parametrize("mode", ["constant", "nearest"])
 def test_randomised_vs_oracle(extrap, order, mode):
     from oracle import semilagrangian as ora
