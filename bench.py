@@ -524,7 +524,8 @@ def run_ours(args):
             stages = stage_rooflines(tr, args.steps, M, N_, peak, alg_bytes)
         except Exception as exc:  # supplementary table only
             stages = [{"error": repr(exc)}]
-        cpu = cpu_baseline(frames_h, precip_h, V_h, have_lk_oracle()) if not args.no_cpu else None
+        # the CPU leg is a property of the host, measured once: rank 0 of the single-GPU run only
+        cpu = cpu_baseline(frames_h, precip_h, V_h, have_lk_oracle()) if (not args.no_cpu and world == 1) else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
                 "higher_is_better": True, "scaling": SCALING, "vs_baseline": None,
