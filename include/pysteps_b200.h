@@ -287,6 +287,22 @@ int b200_vet_warp(const double *image, const int8_t *mask, const double *displac
 int b200_zoom_bilinear(const double *a, int c, int h, int w, int oh, int ow, double *out,
                        void *stream);
 
+/* ------------------------------------------------------------------------
+ * Proesmans et al. (1994) optical flow -- replaces the other native extension of the reference,
+ * pysteps/motion/_proesmans.pyx (called from pysteps/motion/proesmans.py:88).
+ * ---------------------------------------------------------------------- */
+
+/* pysteps/motion/proesmans.py:79-83: out = (frames - im_min) / (im_max - im_min) * 255.0 when
+ * do_scale, else a float64 copy. */
+int b200_proesmans_scale(const void *frames, int dtype, int64_t count, double im_min, double im_max,
+                         int do_scale, double *out, void *stream);
+/* _proesmans.pyx:19-44 _compute_advection_field(R, lam, num_iter, n_levels): frames (2,m,n)
+ * float64 -> advfield (2,2,m,n) (forward / backward flow, x / y component) and quality (2,m,n)
+ * (the consistency maps).  The relaxation sweep keeps the reference's raster-order Gauss-Seidel
+ * update order (wavefronts t = x + 2y inside one CTA per flow field). */
+int b200_proesmans_field(const double *frames, int m, int n, double lam, int num_iter, int num_levels,
+                         double *advfield, double *quality, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

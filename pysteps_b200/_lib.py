@@ -43,6 +43,8 @@ _SIGNATURES = {
                                     c_dp, c_dp, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200_spline_sample": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
                                    c_int, c_double, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "b200_proesmans_scale": (c_int, [c_void_p, c_int, ctypes.c_int64, c_double, c_double, c_int, c_void_p, c_void_p]),
+    "b200_proesmans_field": (c_int, [c_void_p, c_int, c_int, c_double, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "b200_bps_perturb_velocity": (c_int, [c_void_p, c_int, c_int, c_int, c_double, c_double, c_double,
                                           c_int, c_void_p, c_void_p, c_void_p]),
     "b200_sl_extrapolate_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_dp, c_int,

@@ -31,6 +31,8 @@ def methods():
         out["motion"]["vet_b200"] = vet.vet
     except ImportError:
         pass
+    from .motion import proesmans
+    out["motion"]["proesmans_b200"] = proesmans.proesmans
     return out
 
 

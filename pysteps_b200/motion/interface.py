@@ -2,8 +2,8 @@
 
 Same ``get_method(name)`` contract: case-insensitive names, ``None`` -> a callable that
 returns a zero field, unknown names -> ValueError, "brox"/"clg" -> NotImplementedError
-(pysteps/motion/interface.py:97-111).  Methods of the reference that are outside the
-advection hot path (darts, proesmans, farneback, constant) are not provided.
+(pysteps/motion/interface.py:97-111).  "proesmans" is built but opt-in until verified on
+hardware (see motion/proesmans.py); darts, farneback and constant are not provided.
 """
 import numpy as np
 
@@ -20,6 +20,12 @@ try:
     _methods["vet_b200"] = vet
 except ImportError:  # VET not built yet
     pass
+
+
+from .proesmans import proesmans  # noqa: E402
+
+_methods["proesmans"] = proesmans
+_methods["proesmans_b200"] = proesmans
 
 
 def get_method(name):

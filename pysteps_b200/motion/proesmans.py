@@ -1,0 +1,87 @@
+"""B200 Proesmans et al. (1994) optical flow -- drop-in for ``pysteps.motion.proesmans.proesmans``
+(pysteps/motion/proesmans.py:20-94) with the reference's native extension
+(pysteps/motion/_proesmans.pyx) replaced by ``csrc/proesmans.cu``.
+
+Built and verified on the CPU (the kernels' per-thread bodies and their wavefront schedule are
+executed on the host against the oracle and the reference extension: tests/test_kernel_bodies.py,
+tests/test_host_logic_proesmans.py) but NOT yet run on hardware, so it is opt-in:
+``PYSTEPS_B200_ENABLE_PROESMANS=1``; without it the call raises NotImplementedError.
+"""
+import os
+
+import numpy as np
+import torch
+
+from .. import _device, _lib
+
+
+def _enabled():
+    return os.environ.get("PYSTEPS_B200_ENABLE_PROESMANS", "") == "1"
+
+
+def proesmans(input_images, lam=50.0, num_iter=100, num_levels=6, filter_std=0.0, verbose=True,
+              full_output=False):
+    """Same contract as the reference (see its docstring, proesmans.py:29-71).  NumPy input ->
+    NumPy results; CUDA tensor input -> results stay on the device.  ``filter_std > 0`` (a
+    scipy.ndimage.gaussian_filter pre-smoothing) is not implemented."""
+    # decorators.check_input_frames(2, 2): decorators.py:121-146
+    if input_images.ndim != 3:
+        raise ValueError(
+            "input_images dimension mismatch.\n"
+            f"input_images.shape: {str(tuple(input_images.shape))}\n"
+            "(t, x, y ) dimensions expected"
+        )
+    if 2 < input_images.shape[0] > 2:
+        raise ValueError(
+            f"input_images frames {input_images.shape[0]} mismatch.\n"
+            "Minimum frames: 2\n"
+            "Maximum frames: 2\n"
+        )
+    if not _enabled():
+        raise NotImplementedError(
+            "pysteps_b200 proesmans is built but not yet verified on hardware; "
+            "PYSTEPS_B200_ENABLE_PROESMANS=1 enables it (there is no CPU fallback)")
+    if filter_std > 0.0:
+        raise NotImplementedError("pysteps_b200 proesmans: filter_std > 0 is not implemented")
+    del verbose  # Not used
+
+    _device.require_cuda()
+    on_device = _device.is_device_tensor(input_images)
+    m, n = int(input_images.shape[1]), int(input_images.shape[2])
+    if m >> (int(num_levels) - 1) < 1 or n >> (int(num_levels) - 1) < 1:
+        raise NotImplementedError("pysteps_b200 proesmans: num_levels leaves an empty pyramid level")
+
+    frames = input_images[-2:]
+    if isinstance(frames, torch.Tensor):
+        d_in = _device.to_device(frames if frames.dtype in (torch.float32, torch.float64) else frames.to(torch.float64))
+    else:
+        a = np.asarray(frames)
+        d_in = _device.to_device(a if a.dtype in (np.float32, np.float64) else a.astype(np.float64))
+
+    # proesmans.py:79-83 min / max scaling to 0..255 (np.min / np.max propagate NaN: no scaling then)
+    st = torch.empty(4, dtype=torch.float64, device="cuda")
+    _lib.call("b200_field_stats", d_in.data_ptr(), _device.dtype_code(d_in.dtype), d_in.numel(), st.data_ptr(),
+              _device.stream_ptr())
+    n_nonfinite, lo, hi, n_nan = st.cpu().tolist()
+    if n_nan > 0:
+        lo = hi = float("nan")
+    if d_in.dtype == torch.float32:
+        # the reference hands the (still float32) stack to a float64 Cython memoryview
+        # (_proesmans.pyx:19), which rejects it
+        raise ValueError("Buffer dtype mismatch, expected 'float64' but got 'float'")
+    do_scale = bool(hi - lo > 1e-8)
+    d_im = torch.empty((2, m, n), dtype=torch.float64, device="cuda")
+    _lib.call("b200_proesmans_scale", d_in.data_ptr(), _device.dtype_code(d_in.dtype), 2 * m * n, float(lo),
+              float(hi), int(do_scale), d_im.data_ptr(), _device.stream_ptr())
+
+    d_adv = torch.empty((2, 2, m, n), dtype=torch.float64, device="cuda")
+    d_q = torch.empty((2, m, n), dtype=torch.float64, device="cuda")
+    _lib.call("b200_proesmans_field", d_im.data_ptr(), m, n, float(lam), int(num_iter), int(num_levels),
+              d_adv.data_ptr(), d_q.data_ptr(), _device.stream_ptr())
+
+    if not full_output:
+        out = d_adv[0]
+        return out if on_device else _device.to_host(out.contiguous())
+    if on_device:
+        return d_adv, d_q
+    return _device.to_host(d_adv), _device.to_host(d_q)

@@ -121,6 +121,24 @@ def _spline_sample(coeffs, m, n, order, mode, xy, steps, T, r0, rows, outval, mm
                          _addr(mmin), _addr(mfin), _addr(stats), odt, _addr(out))
 
 
+def _proesmans_scale(frames, code, count, lo, hi, do_scale, out, stream):
+    import host_kernels
+    L = host_kernels.lib()
+    src = np.ascontiguousarray(_view(frames, (count,), _NP[code]), dtype=np.float64)
+    L.host_proesmans_scale.restype = None
+    L.host_proesmans_scale(src.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(count), ctypes.c_double(lo),
+                           ctypes.c_double(hi), int(do_scale), ctypes.c_void_p(_addr(out)))
+
+
+def _proesmans_field(frames, m, n, lam, num_iter, num_levels, adv, quality, stream):
+    import host_kernels
+    L = host_kernels.lib()
+    L.host_proesmans_field.restype = ctypes.c_int
+    rc = L.host_proesmans_field(ctypes.c_void_p(_addr(frames)), m, n, ctypes.c_double(lam), num_iter, num_levels,
+                                ctypes.c_void_p(_addr(adv)), ctypes.c_void_p(_addr(quality)))
+    assert rc == 0
+
+
 def _bps(velocity, code, m, n, a, b, vsf, what, out, nnf, stream):
     V = _view(velocity, (2, m, n), _NP[code])
     unit = np.zeros((2, m, n))
@@ -325,6 +343,7 @@ _TABLE_LK = {"b200_mask_invalid": _lk_mask_invalid, "b200_morph_opening": _lk_mo
              "b200_idw_fill": _lk_idw_fill, "b200_fill_f64": _fill_f64}
 
 _TABLE = {"b200_vet_cost": _vet_cost, "b200_vet_warp": _vet_warp, "b200_zoom_bilinear": _zoom,
+          "b200_proesmans_scale": _proesmans_scale, "b200_proesmans_field": _proesmans_field,
           "b200_sl_trajectories": _sl_trajectories, "b200_spline_prepare": _spline_prepare,
           "b200_spline_sample": _spline_sample, "b200_field_stats": _field_stats, "b200_sl_extrapolate_rows": _sl_rows,
           "b200_bps_perturb_velocity": _bps}

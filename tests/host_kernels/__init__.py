@@ -11,11 +11,12 @@ def lib():
     global _LIB
     if _LIB is None:
         so = os.path.join(_HERE, "libhost_kernels.so")
-        srcs = [os.path.join(_HERE, "spline_host.cpp"),
-                os.path.join(_HERE, "..", "..", "pysteps_b200", "csrc", "spline_body.cuh")]
+        csrc = os.path.join(_HERE, "..", "..", "pysteps_b200", "csrc")
+        units = [os.path.join(_HERE, "spline_host.cpp"), os.path.join(_HERE, "proesmans_host.cpp")]
+        srcs = units + [os.path.join(csrc, "spline_body.cuh"), os.path.join(csrc, "proesmans_body.cuh")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
             subprocess.check_call([cxx, "-O2", "-fPIC", "-shared", "-std=c++17", "-ffp-contract=off",
-                                   "-fno-fast-math", "-Wall", "-o", so, srcs[0]])
+                                   "-fno-fast-math", "-Wall", "-o", so] + units)
         _LIB = ctypes.CDLL(so)
     return _LIB

@@ -121,3 +121,34 @@ def test_sample_body_reproduces_the_oracle_extrapolator(mode, order):
         L.host_spline_sample(_p(coeffs), m, n, order, MODES[mode], _p(xy), _p(band), T, r0, r1 - r0, outval,
                              _p(mmin), _p(mfin), _p(stats), F32 if dtype == np.float32 else F64, _p(out))
         assert_bits_equal(out, want[:, r0:r1], f"case {case} {(m, n)} {np.dtype(dtype).name} allow={allow}")
+
+
+# ---- Proesmans (pysteps_b200/csrc/proesmans.cu / proesmans_body.cuh) -----------------------------
+@pytest.mark.parametrize("case", [(64, 80, 3, 40, 50.0), (37, 53, 2, 20, 50.0), (130, 97, 4, 30, 10.0),
+                                  (40, 40, 6, 10, 50.0), (5, 4, 1, 3, 50.0), (63, 95, 1, 100, 1000.0),
+                                  (3, 3, 1, 5, 50.0), (2, 9, 1, 2, 50.0)])
+def test_proesmans_bodies_and_wavefront_schedule(case):
+    """The whole b200_proesmans_field launch sequence on the CPU: pyramid, gradients, consistency
+    maps (row-wise mean), the Gauss-Seidel sweep run wavefront by wavefront (t = x + 2y) with the
+    rows of a wavefront in REVERSE order and the two flow fields swapped, border fill, prolongation
+    -- bit-identical to the oracle's raster-order sweep, ill-conditioned settings included."""
+    from oracle import proesmans as ora_p
+    from pysteps_b200 import _synthetic as syn
+    m, n, levels, num_iter, lam = case
+    L = host_kernels.lib()
+    L.host_proesmans_field.restype = ctypes.c_int
+    L.host_proesmans_scale.restype = None
+    fr = syn.rain_frames(m, n, 2, 3, dx=2, dy=-1)
+    lo, hi = float(fr.min()), float(fr.max())
+    im = np.empty_like(fr)
+    L.host_proesmans_scale(_p(np.ascontiguousarray(fr)), ctypes.c_int64(fr.size), ctypes.c_double(lo),
+                           ctypes.c_double(hi), int(hi - lo > 1e-8), _p(im))
+    assert_bits_equal(im, (fr - lo) / (hi - lo) * 255.0 if hi - lo > 1e-8 else fr, "scaling")
+    adv, q = np.empty((2, 2, m, n)), np.empty((2, m, n))
+    rc = L.host_proesmans_field(_p(im), m, n, ctypes.c_double(lam), num_iter, levels, _p(adv), _p(q))
+    assert rc == 0
+    want_adv, want_q = ora_p.compute_advection_field(im, lam, num_iter, levels)
+    assert_bits_equal(adv, want_adv, f"{case} advection fields")
+    assert_bits_equal(q, want_q, f"{case} consistency maps")
+    # an empty pyramid level is refused (the reference reads out of bounds there)
+    assert L.host_proesmans_field(_p(im), m, n, ctypes.c_double(lam), 1, 12, _p(adv), _p(q)) == -1
