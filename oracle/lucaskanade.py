@@ -286,6 +286,31 @@ def track_features(prvs_image, next_image, points, winsize=(50, 50), nr_levels=3
     return xy, uv
 
 
+# How equidistant / coincident neighbours are chosen and ordered by the two k-NN users
+# (detect_outliers, idwinterp2d):
+#   "lower_index" (default) -- ascending distance, ties by lower index: the rule of the CUDA path;
+#   "ckdtree"               -- exactly as scipy.spatial.cKDTree returns them (oracle/ckdtree.py):
+#                              with it the whole of dense_lucaskanade is bit-identical to the
+#                              reference (tests/test_oracle_lk.py), which isolates the tie rule as
+#                              the only difference between the CUDA path and the reference.
+_KNN_MODE = ["lower_index"]
+
+
+class knn_mode:
+    """with knn_mode("ckdtree"): ..."""
+
+    def __init__(self, mode):
+        assert mode in ("lower_index", "ckdtree")
+        self.mode = mode
+
+    def __enter__(self):
+        self.prev = _KNN_MODE[0]
+        _KNN_MODE[0] = self.mode
+
+    def __exit__(self, *exc):
+        _KNN_MODE[0] = self.prev
+
+
 def _knn_bruteforce(coord, k):
     """scipy.spatial.cKDTree(coord).query(coord, k)[1]: exhaustive, ascending distance,
     ties by lower index."""
@@ -324,7 +349,12 @@ def detect_outliers(input_array, thr, coord=None, k=None, verbose=False):
         except np.linalg.LinAlgError:
             MD = np.zeros(nsamples)
         return MD > thr
-    inds = _knn_bruteforce(coord.astype(np.float64), k)
+    if _KNN_MODE[0] == "ckdtree":
+        from .ckdtree import KDTree
+        __, inds = KDTree(coord).query(coord, k=int(k))       # cleansing.py:219-220
+        inds = inds.reshape(nsamples, -1)
+    else:
+        inds = _knn_bruteforce(coord.astype(np.float64), k)
     outliers = np.empty(nsamples, dtype=bool)
     for i in range(nsamples):
         thisdata = input_array[i, :]
@@ -386,6 +416,24 @@ def idwinterp2d(xy_coord, values, xgrid, ygrid, power=0.5, k=20, dist_offset=0.5
     if values.ndim == 1:
         values = values[:, None]
     npoints, nvar = values.shape
+    if _KNN_MODE[0] == "ckdtree" and k is not None and not return_ties:
+        # interpolate.py:67-114 verbatim, with the restated tree in place of scipy's
+        from .ckdtree import KDTree
+        xgridv, ygridv = np.meshgrid(xgrid, ygrid)
+        gridv = np.column_stack((xgridv.ravel(), ygridv.ravel()))
+        kk = int(np.min((k, npoints)))
+        dist, inds = KDTree(xy_coord).query(gridv, k=kk)
+        if dist.ndim == 1:
+            dist = dist[..., None]
+            inds = inds[..., None]
+        mean_res = np.mean(np.abs([np.gradient(xgrid).mean(), np.gradient(ygrid).mean()]))
+        dist /= mean_res
+        dist += dist_offset
+        weights = 1 / np.power(dist, power)
+        weights = weights / np.sum(weights, axis=1, keepdims=True)
+        output_array = np.sum(values[inds, :] * weights[..., None], axis=1)
+        output_array = output_array.reshape(ygrid.size, xgrid.size, nvar)
+        return np.moveaxis(output_array, -1, 0).squeeze()
     k = npoints if k is None else int(min(k, npoints))
     x_res = np.gradient(xgrid)
     y_res = np.gradient(ygrid)
