@@ -247,6 +247,12 @@ int b200_lk_compact_tracks(const float *p0, const float *p1, const uint8_t *stat
  * branch: out[i] = 1 where the Mahalanobis distance to the k nearest vectors exceeds thr. */
 int b200_detect_outliers(const double *uv, const double *xy, const int *n_dev, int n_cap,
                          double thr, int k, uint8_t *out, void *stream);
+/* The same test with the k+1 nearest vectors taken in scipy.spatial.cKDTree's own order, ties and
+ * coincident vectors included (the tree is built and queried on the device exactly as scipy does,
+ * csrc/knn_body.cuh): with integer corner coordinates that order decides outlier tests.  Reads one
+ * int back (the node count) and synchronises the stream. */
+int b200_detect_outliers_ckdtree(const double *uv, const double *xy, const int *n_dev, int n_cap,
+                                 double thr, int k, uint8_t *out, void *stream);
 /* rows with drop == 0, order preserved */
 int b200_compact_rows(const double *xy, const double *uv, const uint8_t *drop, const int *n_dev,
                       int n_cap, double *out_xy, double *out_uv, int *out_count, void *stream);

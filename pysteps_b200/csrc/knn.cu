@@ -1,0 +1,108 @@
+// knn.cu -- the local outlier test of dense_lucaskanade with scipy.spatial.cKDTree's exact
+// neighbour order (pysteps/utils/cleansing.py:216-245).
+//
+// The default kernel (sparse.cu) takes equidistant neighbours by lower index; cKDTree returns them
+// in an order that follows from its tree (knn_body.cuh restates tree and query bit for bit), and
+// with integer corner coordinates that order decides outlier tests.  Here
+// the tree is built ON THE DEVICE by one thread (<= 2000 vectors: ~50 k dependent steps, it is
+// sequential by definition of nth_element) and every vector then runs scipy's best-first query in
+// its own thread.
+#include "common.cuh"
+#include "knn_body.cuh"
+
+namespace {
+
+struct KnnParams {
+    const double *xy, *uv;
+    const int *n_dev;
+    int n_cap, k;
+    double thr;
+    int *idx;            // n_cap
+    kd::Node *nodes;     // max_nodes(n_cap)
+    int *meta;           // [0] = nnodes
+    double *bounds;      // maxes[2], mins[2]
+    int *inds;           // n_cap * (k+1)
+    kd::Item *nb;        // n_cap * (k+1)
+    kd::Item *q;         // n_cap * qcap
+    kd::NodeInfo *pool;  // n_cap * qcap
+    int qcap;
+    uint8_t *out;
+};
+
+__global__ void kd_build_kernel(const __grid_constant__ KnnParams p) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    const int n = p.n_dev ? min(*p.n_dev, p.n_cap) : p.n_cap;
+    int stack[128];
+    kd::Tree t;
+    t.data = p.xy;
+    t.n = n;
+    t.idx = p.idx;
+    t.nodes = p.nodes;
+    kd::build(t, stack);
+    p.meta[0] = t.nnodes;
+    for (int c = 0; c < 2; c++) {
+        p.bounds[c] = t.maxes[c];
+        p.bounds[2 + c] = t.mins[c];
+    }
+}
+
+__global__ void __launch_bounds__(64)
+outliers_ckdtree_kernel(const __grid_constant__ KnnParams p) {
+    const int n = p.n_dev ? min(*p.n_dev, p.n_cap) : p.n_cap;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (n < 2) {  // cleansing.py:178-179
+        p.out[i] = 0;
+        return;
+    }
+    const int kk = min(p.k + 1, n);  // :197
+    kd::Tree t;
+    t.data = p.xy;
+    t.n = n;
+    t.idx = p.idx;
+    t.nodes = p.nodes;
+    t.nnodes = p.meta[0];
+    for (int c = 0; c < 2; c++) {
+        t.maxes[c] = p.bounds[c];
+        t.mins[c] = p.bounds[2 + c];
+    }
+    int *inds = p.inds + (size_t)i * (p.k + 1);
+    kd::query(t, p.xy[2 * (size_t)i], p.xy[2 * (size_t)i + 1], kk, inds, p.nb + (size_t)i * (p.k + 1),
+              p.q + (size_t)i * p.qcap, p.pool + (size_t)i * p.qcap);
+    p.out[i] = kd::mahalanobis_outlier(p.uv, i, inds, kk - 1, p.thr) ? 1 : 0;
+}
+
+}  // namespace
+
+extern "C" int b200_detect_outliers_ckdtree(const double *uv, const double *xy, const int *n_dev, int n_cap,
+                                            double thr, int k, uint8_t *out, void *stream) {
+    B200_REQUIRE(uv != nullptr && xy != nullptr && out != nullptr && n_cap >= 1, "bad arguments");
+    B200_REQUIRE(k >= 1 && k <= 4096, "k out of range");
+    cudaStream_t s = (cudaStream_t)stream;
+    KnnParams p;
+    memset(&p, 0, sizeof(p));
+    p.xy = xy; p.uv = uv; p.n_dev = n_dev; p.n_cap = n_cap; p.k = k; p.thr = thr; p.out = out;
+    b200::Scratch idx, nodes, meta, bounds, inds, nb, q, pool;
+    B200_CUDA(idx.alloc(sizeof(int) * (size_t)n_cap, s));
+    B200_CUDA(nodes.alloc(sizeof(kd::Node) * (size_t)kd::max_nodes(n_cap), s));
+    B200_CUDA(meta.alloc(sizeof(int) * 4, s));
+    B200_CUDA(bounds.alloc(sizeof(double) * 4, s));
+    B200_CUDA(inds.alloc(sizeof(int) * (size_t)n_cap * (k + 1), s));
+    B200_CUDA(nb.alloc(sizeof(kd::Item) * (size_t)n_cap * (k + 1), s));
+    p.idx = (int *)idx.p; p.nodes = (kd::Node *)nodes.p; p.meta = (int *)meta.p; p.bounds = (double *)bounds.p;
+    p.inds = (int *)inds.p; p.nb = (kd::Item *)nb.p;
+    kd_build_kernel<<<1, 1, 0, s>>>(p);
+    B200_LAUNCH_CHECK();
+    // A query queues at most one far child per internal node it visits, so the node count bounds
+    // its queue; it is known only now (one small read-back; this entry point synchronises).
+    int nnodes = 0;
+    B200_CUDA(cudaMemcpyAsync(&nnodes, p.meta, sizeof(int), cudaMemcpyDeviceToHost, s));
+    B200_CUDA(cudaStreamSynchronize(s));
+    p.qcap = nnodes > 0 ? nnodes : 1;
+    B200_CUDA(q.alloc(sizeof(kd::Item) * (size_t)n_cap * p.qcap, s));
+    B200_CUDA(pool.alloc(sizeof(kd::NodeInfo) * (size_t)n_cap * p.qcap, s));
+    p.q = (kd::Item *)q.p; p.pool = (kd::NodeInfo *)pool.p;
+    outliers_ckdtree_kernel<<<b200::ceil_div(n_cap, 64), 64, 0, s>>>(p);
+    B200_LAUNCH_CHECK();
+    return 0;
+}

@@ -22,6 +22,7 @@ Sparse vectors stay on the device between stages; the host reads back only eleme
 counts (to size the next launch / take the reference's early-outs).
 """
 import ctypes
+import os
 import time
 
 import numpy as np
@@ -91,6 +92,10 @@ def _track_image(f, m, n, buffer_mask):
 
 _side_streams = {}
 _grids = {}
+
+
+def exact_ties():
+    return os.environ.get("PYSTEPS_B200_EXACT_TIES", "") == "1"
 
 
 def _pixel_grid(a, b):
@@ -297,7 +302,11 @@ def dense_lucaskanade(input_images, lk_kwargs=None, fd_method="shitomasi", fd_kw
     kept_uv = torch.empty((pool_cap, 2), dtype=torch.float64, device="cuda")
     if k_outlier is None:
         raise NotImplementedError("pysteps_b200 LK: k_outlier=None (global outlier test) is not implemented")
-    _call("b200_detect_outliers", pool_uv.data_ptr(), pool_xy.data_ptr(), counts[0:1].data_ptr(),
+    # PYSTEPS_B200_EXACT_TIES=1: equidistant / coincident neighbours in scipy.spatial.cKDTree's own
+    # order (csrc/knn.cu) instead of by lower index -- built and verified on the CPU, opt-in until it
+    # has run on hardware
+    _call("b200_detect_outliers_ckdtree" if exact_ties() else "b200_detect_outliers",
+          pool_uv.data_ptr(), pool_xy.data_ptr(), counts[0:1].data_ptr(),
           pool_cap, float(nr_std_outlier), int(k_outlier), flags.data_ptr(), _s())
     _call("b200_compact_rows", pool_xy.data_ptr(), pool_uv.data_ptr(), flags.data_ptr(),
           counts[0:1].data_ptr(), pool_cap, kept_xy.data_ptr(), kept_uv.data_ptr(),

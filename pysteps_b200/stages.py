@@ -154,8 +154,8 @@ def detect_outliers(input_array, thr, coord=None, k=None, verbose=False):
     duv = _device.to_device(np.ascontiguousarray(input_array, dtype=np.float64))
     dxy = _device.to_device(np.ascontiguousarray(coord, dtype=np.float64))
     flags = torch.empty(nsamples, dtype=torch.uint8, device="cuda")
-    _lib.call("b200_detect_outliers", duv.data_ptr(), dxy.data_ptr(), None, nsamples, float(thr), int(k),
-              flags.data_ptr(), _s())
+    _lib.call("b200_detect_outliers_ckdtree" if _lk.exact_ties() else "b200_detect_outliers",
+              duv.data_ptr(), dxy.data_ptr(), None, nsamples, float(thr), int(k), flags.data_ptr(), _s())
     out = flags.cpu().numpy().astype(bool)
     if verbose:
         print(f"--- {np.sum(out)} outliers detected ---")

@@ -295,6 +295,16 @@ def _lk_detect_outliers(uv, xy, n_dev, cap, thr, k, out, stream):
                                                                     _view(xy, (cap, 2))[:cnt].copy(), k)
 
 
+def _lk_detect_outliers_ckdtree(uv, xy, n_dev, cap, thr, k, out, stream):
+    """the kernel's own body (csrc/knn_body.cuh) compiled for the host"""
+    import host_kernels
+    cnt = _count(n_dev, cap)
+    L = host_kernels.lib()
+    L.host_detect_outliers_ckdtree.restype = None
+    L.host_detect_outliers_ckdtree(ctypes.c_void_p(_addr(uv)), ctypes.c_void_p(_addr(xy)), cnt, ctypes.c_double(thr),
+                                   int(k), ctypes.c_void_p(_addr(out)))
+
+
 def _lk_compact_rows(xy, uv, drop, n_dev, cap, oxy, ouv, ocount, stream):
     cnt = _count(n_dev, cap)
     keep = _view(drop, (cap,), np.uint8)[:cnt] == 0
@@ -339,6 +349,7 @@ _TABLE_LK = {"b200_mask_invalid": _lk_mask_invalid, "b200_morph_opening": _lk_mo
              "b200_min_eig": _lk_min_eig, "b200_good_features": _lk_good_features,
              "b200_lk_build_pyramid": _lk_build_pyramid, "b200_lk_track": _lk_track,
              "b200_lk_compact_tracks": _lk_compact_tracks, "b200_detect_outliers": _lk_detect_outliers,
+             "b200_detect_outliers_ckdtree": _lk_detect_outliers_ckdtree,
              "b200_compact_rows": _lk_compact_rows, "b200_decluster": _lk_decluster,
              "b200_idw_fill": _lk_idw_fill, "b200_fill_f64": _fill_f64}
 

@@ -12,8 +12,10 @@ def lib():
     if _LIB is None:
         so = os.path.join(_HERE, "libhost_kernels.so")
         csrc = os.path.join(_HERE, "..", "..", "pysteps_b200", "csrc")
-        units = [os.path.join(_HERE, "spline_host.cpp"), os.path.join(_HERE, "proesmans_host.cpp")]
-        srcs = units + [os.path.join(csrc, "spline_body.cuh"), os.path.join(csrc, "proesmans_body.cuh")]
+        units = [os.path.join(_HERE, "spline_host.cpp"), os.path.join(_HERE, "proesmans_host.cpp"),
+                 os.path.join(_HERE, "knn_host.cpp")]
+        srcs = units + [os.path.join(csrc, "spline_body.cuh"), os.path.join(csrc, "proesmans_body.cuh"),
+                        os.path.join(csrc, "knn_body.cuh")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
             subprocess.check_call([cxx, "-O2", "-fPIC", "-shared", "-std=c++17", "-ffp-contract=off",

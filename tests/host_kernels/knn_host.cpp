@@ -1,0 +1,40 @@
+// TEST INFRASTRUCTURE: pysteps_b200/csrc/knn_body.cuh compiled as host C++ (see spline_host.cpp).
+#include <stdint.h>
+
+#include <vector>
+
+#include "../../pysteps_b200/csrc/knn_body.cuh"
+
+extern "C" {
+
+// tree permutation (tree.indices) and the k nearest of every query, in cKDTree's order
+void host_kd_knn(const double *data, int n, const double *queries, int nq, int k, int *perm, int *out_idx) {
+    std::vector<int> idx(n > 0 ? n : 1), stack(256);
+    std::vector<kd::Node> nodes(kd::max_nodes(n));
+    kd::Tree t;
+    t.data = data;
+    t.n = n;
+    t.idx = idx.data();
+    t.nodes = nodes.data();
+    kd::build(t, stack.data());
+    for (int i = 0; i < n; i++) perm[i] = idx[i];
+    std::vector<kd::Item> nb(k), q(t.nnodes + 1);
+    std::vector<kd::NodeInfo> pool(t.nnodes + 1);
+    for (int i = 0; i < nq; i++)
+        kd::query(t, queries[2 * (size_t)i], queries[2 * (size_t)i + 1], k, out_idx + (size_t)i * k, nb.data(), q.data(),
+                  pool.data());
+}
+
+// == b200_detect_outliers_ckdtree
+void host_detect_outliers_ckdtree(const double *uv, const double *xy, int n, double thr, int k, uint8_t *out) {
+    if (n < 2) {
+        for (int i = 0; i < n; i++) out[i] = 0;
+        return;
+    }
+    const int kk = k + 1 < n ? k + 1 : n;  // cleansing.py:197
+    std::vector<int> perm(n), inds((size_t)n * kk);
+    host_kd_knn(xy, n, xy, n, kk, perm.data(), inds.data());
+    for (int i = 0; i < n; i++) out[i] = kd::mahalanobis_outlier(uv, i, inds.data() + (size_t)i * kk, kk - 1, thr) ? 1 : 0;
+}
+
+}  // extern "C"

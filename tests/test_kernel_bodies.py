@@ -152,3 +152,67 @@ def test_proesmans_bodies_and_wavefront_schedule(case):
     assert_bits_equal(q, want_q, f"{case} consistency maps")
     # an empty pyramid level is refused (the reference reads out of bounds there)
     assert L.host_proesmans_field(_p(im), m, n, ctypes.c_double(lam), 1, 12, _p(adv), _p(q)) == -1
+
+
+# ---- cKDTree-exact k-NN + outlier test (pysteps_b200/csrc/knn.cu / knn_body.cuh) -----------------
+@pytest.mark.parametrize("kind", ["int", "half", "dup", "few_values", "real"])
+@pytest.mark.parametrize("n", [1, 5, 17, 60, 400, 2000])
+def test_knn_body_matches_scipy_ckdtree(kind, n):
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(n * 13 + len(kind))
+    W = int(rng.choice([16, 64, 300]))
+    pts = np.floor(rng.uniform(0, W, (n, 2)))
+    if kind == "half":
+        pts = np.floor(rng.uniform(0, W, (n, 2)) * 2) / 2
+    elif kind == "dup" and n >= 8:
+        pts[: n // 4] = pts[n // 4: 2 * (n // 4)]
+    elif kind == "few_values":
+        pts = np.floor(rng.uniform(0, 4, (n, 2)))
+    elif kind == "real":
+        pts = rng.uniform(0, W, (n, 2))
+    pts = np.ascontiguousarray(pts)
+    L = host_kernels.lib()
+    ref = cKDTree(pts)
+    queries = np.ascontiguousarray(np.concatenate([pts[:200], np.floor(rng.uniform(-2, W + 2, (100, 2)))]))
+    for k in (2, 21, 31, 101):
+        k = min(k, n)
+        perm = np.empty(n, np.int32)
+        out = np.empty((len(queries), k), np.int32)
+        L.host_kd_knn(_p(pts), n, _p(queries), len(queries), k, _p(perm), _p(out))
+        assert np.array_equal(perm, ref.indices), (kind, n)
+        assert np.array_equal(out, ref.query(queries, k=k)[1].reshape(len(queries), -1)), (kind, n, k)
+
+
+def test_outlier_body_matches_the_reference_at_ties():
+    """detect_outliers of the reference (scipy cKDTree + np.cov + np.linalg.inv) on vector sets with
+    many equidistant and coincident positions: the body's flags equal the reference's (live when
+    /root/reference exists) and the oracle's in cKDTree mode."""
+    from oracle import lucaskanade as ora_lk
+    try:
+        from _refimport import available, ref_module
+        live = ref_module("pysteps.utils.cleansing").detect_outliers if available() else None
+    except Exception:  # noqa: BLE001
+        live = None
+    L = host_kernels.lib()
+    L.host_detect_outliers_ckdtree.restype = None
+    rng = np.random.default_rng(31)
+    for it in range(30):
+        n = int(rng.choice([2, 3, 10, 40, 300, 1500]))
+        xy = np.floor(rng.uniform(0, rng.choice([6, 30, 200]), (n, 2)))
+        if it % 3 == 0 and n >= 8:
+            xy[: n // 4] = xy[n // 4: 2 * (n // 4)]
+        uv = np.stack([2 + 0.3 * rng.standard_normal(n), -1 + 0.3 * rng.standard_normal(n)], 1)
+        uv[::7] += 2.0
+        k = int(rng.choice([5, 30, 100]))
+        thr = float(rng.choice([1, 2, 3]))
+        flags = np.empty(n, np.uint8)
+        L.host_detect_outliers_ckdtree(_p(np.ascontiguousarray(uv)), _p(np.ascontiguousarray(xy)), n,
+                                       ctypes.c_double(thr), k, _p(flags))
+        with ora_lk.knn_mode("ckdtree"):
+            want = ora_lk.detect_outliers(uv, thr, xy, k)
+        assert np.array_equal(flags.astype(bool), want), (it, n, k, thr)
+        if live is not None and n >= 3:
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                assert np.array_equal(flags.astype(bool), live(uv, thr, xy, k)), (it, n, k, thr)

@@ -411,3 +411,22 @@ def test_row_band_fill_equals_rows_of_full_field(env):
     with pytest.raises(ValueError):
         lk(frames, interp_kwargs={"b200_rows": (10, 10)})
     assert lk(frames[:1], interp_kwargs={"b200_rows": (5, 9)}).shape == (2, 4, 176)
+
+
+@pytest.mark.skipif(os.environ.get("PYSTEPS_B200_EXACT_TIES") != "1",
+                    reason="cKDTree-exact ties are not yet verified on hardware (opt-in)")
+def test_exact_ties_sparse_vectors_vs_oracle_ckdtree_mode(env):
+    """PYSTEPS_B200_EXACT_TIES=1: the outlier stage takes tied neighbours in cKDTree's order; the
+    sparse vectors then equal the oracle in cKDTree mode (which equals the reference bit for bit)."""
+    from oracle import lucaskanade as ora
+    from pysteps_b200 import _synthetic as syn
+    from pysteps_b200.motion.lucaskanade import dense_lucaskanade as lk
+    rng = np.random.default_rng(9)
+    for it in range(12):
+        m, n, T = int(rng.integers(60, 260)), int(rng.integers(60, 260)), int(rng.choice([2, 3, 3]))
+        fr = syn.rain_frames(m, n, T, int(rng.integers(0, 1000)), dx=int(rng.integers(-3, 4)), dy=int(rng.integers(-3, 4)))
+        kw = dict(dense=False, k_outlier=int(rng.choice([5, 30, 100])), nr_std_outlier=float(rng.choice([1, 2, 3])))
+        xy, uv = lk(fr, **kw)
+        with ora.knn_mode("ckdtree"):
+            oxy, ouv = ora.dense_lucaskanade(fr, **kw)
+        assert np.array_equal(xy, oxy) and np.array_equal(uv, ouv), (it, m, n, T, kw)
