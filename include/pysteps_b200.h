@@ -271,6 +271,16 @@ int b200_idw_fill(const double *xy, const double *vals, const int *npts_dev, int
                   const double *xgrid, int nx, const double *ygrid, int ny,
                   int coords_on_16th_grid, double *out, void *stream);
 
+/* idwinterp2d with the k nearest vectors of every grid point found, ordered and weighted exactly
+ * as the reference does it (scipy.spatial.cKDTree's query order, numpy's pairwise sum of the
+ * weights, values accumulated in neighbour order): equal to the reference at EVERY grid point to
+ * the last bits (np.power vs pow), ties included; much slower than b200_idw_fill (a tree search
+ * per grid point).  k <= 128.  Reads one int back and synchronises the stream. */
+int b200_idw_fill_ckdtree(const double *xy, const double *vals, const int *npts_dev, int npts_cap,
+                          int nvar, int k, double power, double dist_offset, double mean_res,
+                          const double *xgrid, int nx, const double *ygrid, int ny, double *out,
+                          void *stream);
+
 /* ------------------------------------------------------------------------
  * Variational Echo Tracking -- replaces the native extension of the reference,
  * pysteps/motion/_vet.pyx.  The CG optimiser (scipy.optimize.minimize, vet.py:593-600)

@@ -83,6 +83,8 @@ _SIGNATURES = {
                                c_void_p, c_void_p]),
     "b200_idw_fill": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_double,
                               c_double, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "b200_idw_fill_ckdtree": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_double,
+                                      c_double, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "b200_vet_cost": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                               ctypes.c_float, c_int, c_void_p, c_void_p]),
     "b200_vet_warp": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,

@@ -251,7 +251,7 @@ struct NodeInfo { int node; double side[2]; double min_distance; };
 // tree.query(x, k): the kmax nearest points in scipy's order (missing: index n).  Scratch per
 // query: nb (kmax items), q and pool (nnodes entries each).
 KD_FN_NOINLINE void query(const Tree &t, double x0, double x1, int kmax, int *out_idx, Item *nb, Item *q,
-                          NodeInfo *pool) {
+                          NodeInfo *pool, double *out_dist = nullptr) {
     const double x[2] = {x0, x1};
     int nbn = 0, qn = 0, pooln = 0;
     NodeInfo cur;
@@ -322,9 +322,53 @@ KD_FN_NOINLINE void query(const Tree &t, double x0, double x1, int kmax, int *ou
     const int found = nbn;
     for (int i = found - 1; i >= 0; i--) {
         out_idx[i] = nb[0].payload;
+        if (out_dist) out_dist[i] = sqrt(-nb[0].priority);
         heap_remove(nb, nbn);
     }
-    for (int i = found; i < kmax; i++) out_idx[i] = t.n;
+    for (int i = found; i < kmax; i++) {
+        out_idx[i] = t.n;
+        if (out_dist) out_dist[i] = (double)INFINITY;
+    }
+}
+
+// numpy's pairwise summation of n <= 128 contiguous doubles (DOUBLE_pairwise_sum): 8 running
+// sums for n >= 8, combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the tail
+KD_FN double numpy_sum(const double *a, int n) {
+    if (n < 8) {
+        double res = 0.0;  // numpy starts from the first element: res = a[0]; equal to 0.0 + a[0]
+        for (int i = 0; i < n; i++) res = (i == 0) ? a[0] : res + a[i];
+        return res;
+    }
+    double r[8];
+    for (int j = 0; j < 8; j++) r[j] = a[j];
+    int i;
+    for (i = 8; i < n - (n % 8); i += 8)
+        for (int j = 0; j < 8; j++) r[j] += a[i + j];
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; i++) res += a[i];
+    return res;
+}
+
+// pysteps/utils/interpolate.py:78-107 for one grid point: the k nearest vectors in cKDTree's order,
+// w = 1 / (d / mean_res + offset)^power normalised by numpy's sum, values accumulated in
+// neighbour order.  w holds the distances on entry (k <= 128).
+KD_FN void idw_point(const double *vals, int nvar, const int *inds, double *w, int k, double power, double offset,
+                     double mean_res, double *out, size_t out_stride) {
+    for (int j = 0; j < k; j++) {
+        double d = w[j] / mean_res;
+        d = d + offset;
+        w[j] = 1.0 / pow(d, power);
+    }
+    const double wsum = numpy_sum(w, k);
+    for (int j = 0; j < k; j++) w[j] = w[j] / wsum;
+    for (int c = 0; c < nvar; c++) {
+        double acc = 0.0;
+        for (int j = 0; j < k; j++) {
+            const double term = vals[(size_t)inds[j] * nvar + c] * w[j];
+            acc = (j == 0) ? term : acc + term;
+        }
+        out[(size_t)c * out_stride] = acc;
+    }
 }
 
 // cleansing.py:231-245 for vector i with its k+1 nearest (inds[0] is dropped as "the vector

@@ -362,9 +362,15 @@ def dense_lucaskanade(input_images, lk_kwargs=None, fd_method="shitomasi", fd_kw
         # of 1/2): squared distances are exact small multiples of 1/256 -> packed-key fast path
         on_grid = bool(np.all(xy_h * 16.0 == np.rint(xy_h * 16.0)) and np.abs(xy_h).max() < 16384.0
                        and max(m, n) < 16384)
-        _call("b200_idw_fill", dec_xy.data_ptr(), dec_uv.data_ptr(), None, n_dec, 2, int(min(int(k), n_dec)),
-              power, dist_offset, 1.0, xgrid.data_ptr(), n, ygrid.data_ptr(), mb, int(on_grid),
-              out.data_ptr(), _s())
+        if exact_ties():
+            # every grid point searched, ordered and weighted as the reference does (csrc/knn.cu)
+            _call("b200_idw_fill_ckdtree", dec_xy.data_ptr(), dec_uv.data_ptr(), None, n_dec, 2,
+                  int(min(int(k), n_dec)), power, dist_offset, 1.0, xgrid.data_ptr(), n, ygrid.data_ptr(), mb,
+                  out.data_ptr(), _s())
+        else:
+            _call("b200_idw_fill", dec_xy.data_ptr(), dec_uv.data_ptr(), None, n_dec, 2, int(min(int(k), n_dec)),
+                  power, dist_offset, 1.0, xgrid.data_ptr(), n, ygrid.data_ptr(), mb, int(on_grid),
+                  out.data_ptr(), _s())
 
     if verbose:
         torch.cuda.current_stream().synchronize()

@@ -340,6 +340,18 @@ def _lk_idw_fill(xy, vals, n_dev, cap, nvar, k, power, offset, mean_res, xg, nx,
     _view(out, (nvar, ny, nx))[...] = np.asarray(r).reshape(nvar, ey.size, ex.size)[:, :ny, :nx]
 
 
+def _lk_idw_fill_ckdtree(xy, vals, n_dev, cap, nvar, k, power, offset, mean_res, xg, nx, yg, ny, out, stream):
+    """the kernel's own body (csrc/knn_body.cuh) compiled for the host"""
+    import host_kernels
+    cnt = _count(n_dev, cap)
+    L = host_kernels.lib()
+    L.host_idw_fill_ckdtree.restype = None
+    vp = ctypes.c_void_p
+    L.host_idw_fill_ckdtree(vp(_addr(xy)), vp(_addr(vals)), cnt, nvar, min(k, cnt), ctypes.c_double(power),
+                            ctypes.c_double(offset), ctypes.c_double(mean_res), vp(_addr(xg)), nx, vp(_addr(yg)),
+                            ny, vp(_addr(out)))
+
+
 def _fill_f64(ptr, count, value, stream):
     _view(ptr, (count,))[...] = value
 
@@ -351,7 +363,7 @@ _TABLE_LK = {"b200_mask_invalid": _lk_mask_invalid, "b200_morph_opening": _lk_mo
              "b200_lk_compact_tracks": _lk_compact_tracks, "b200_detect_outliers": _lk_detect_outliers,
              "b200_detect_outliers_ckdtree": _lk_detect_outliers_ckdtree,
              "b200_compact_rows": _lk_compact_rows, "b200_decluster": _lk_decluster,
-             "b200_idw_fill": _lk_idw_fill, "b200_fill_f64": _fill_f64}
+             "b200_idw_fill": _lk_idw_fill, "b200_idw_fill_ckdtree": _lk_idw_fill_ckdtree, "b200_fill_f64": _fill_f64}
 
 _TABLE = {"b200_vet_cost": _vet_cost, "b200_vet_warp": _vet_warp, "b200_zoom_bilinear": _zoom,
           "b200_proesmans_scale": _proesmans_scale, "b200_proesmans_field": _proesmans_field,

@@ -37,4 +37,28 @@ void host_detect_outliers_ckdtree(const double *uv, const double *xy, int n, dou
     for (int i = 0; i < n; i++) out[i] = kd::mahalanobis_outlier(uv, i, inds.data() + (size_t)i * kk, kk - 1, thr) ? 1 : 0;
 }
 
+// == b200_idw_fill_ckdtree: out (nvar, ny, nx)
+void host_idw_fill_ckdtree(const double *xy, const double *vals, int npts, int nvar, int k, double power,
+                           double offset, double mean_res, const double *xgrid, int nx, const double *ygrid, int ny,
+                           double *out) {
+    std::vector<int> idx(npts > 0 ? npts : 1), stack(256);
+    std::vector<kd::Node> nodes(kd::max_nodes(npts));
+    kd::Tree t;
+    t.data = xy;
+    t.n = npts;
+    t.idx = idx.data();
+    t.nodes = nodes.data();
+    kd::build(t, stack.data());
+    std::vector<kd::Item> nb(k), q(t.nnodes + 1);
+    std::vector<kd::NodeInfo> pool(t.nnodes + 1);
+    std::vector<int> inds(k);
+    std::vector<double> w(k);
+    const size_t N = (size_t)ny * nx;
+    for (int i = ny - 1; i >= 0; i--)
+        for (int j = 0; j < nx; j++) {
+            kd::query(t, xgrid[j], ygrid[i], k, inds.data(), nb.data(), q.data(), pool.data(), w.data());
+            kd::idw_point(vals, nvar, inds.data(), w.data(), k, power, offset, mean_res, out + (size_t)i * nx + j, N);
+        }
+}
+
 }  // extern "C"

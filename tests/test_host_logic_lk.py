@@ -166,3 +166,27 @@ def test_exact_ties_mode_reproduces_the_reference_sparse_vectors(monkeypatch):
                     for a, b in zip(got, ref):
                         assert a.shape == b.shape and np.array_equal(a, b), (it, kw)
     assert n >= 40
+
+
+def test_exact_ties_mode_reproduces_the_reference_dense_field(monkeypatch):
+    """... and the dense field equals the live reference at EVERY pixel to the last bits (np.power
+    vs pow), where the default mode differs by a bounded amount on the ~0.3 % of pixels with a
+    k-NN tie."""
+    from pysteps_b200.motion.lucaskanade import dense_lucaskanade
+    live = _live()
+    if live is None:
+        pytest.skip("/root/reference or cv2 not present")
+    monkeypatch.setenv("PYSTEPS_B200_EXACT_TIES", "1")
+    rng = np.random.default_rng(2001)
+    n = 0
+    with cpu_abi.emulated():
+        for it in range(30):
+            inp, kw = _random_call(rng)
+            kw = dict(kw, dense=True)
+            got, gerr = _run(dense_lucaskanade, inp, kw)
+            ref, rerr = _run(live, inp, kw)
+            assert gerr == rerr, (it, kw)
+            if gerr is None:
+                n += 1
+                assert got.shape == ref.shape and np.abs(got - ref).max() <= 1e-13, (it, kw)
+    assert n >= 20

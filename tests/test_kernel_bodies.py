@@ -216,3 +216,37 @@ def test_outlier_body_matches_the_reference_at_ties():
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore")
                 assert np.array_equal(flags.astype(bool), live(uv, thr, xy, k)), (it, n, k, thr)
+
+
+def test_exact_idw_body_matches_the_reference_at_every_grid_point():
+    """idwinterp2d with cKDTree's neighbour order, numpy's pairwise weight sum and in-order
+    accumulation (knn_body.cuh: idw_point): equal to the reference at ALL grid points, ties and
+    coincident vectors included, to the last bits of np.power vs pow."""
+    from oracle import lucaskanade as ora_lk
+    try:
+        from _refimport import available, ref_module
+        live = ref_module("pysteps.utils.interpolate").idwinterp2d if available() else None
+    except Exception:  # noqa: BLE001
+        live = None
+    L = host_kernels.lib()
+    L.host_idw_fill_ckdtree.restype = None
+    rng = np.random.default_rng(2)
+    for it in range(14):
+        n = int(rng.choice([2, 30, 200, 800]))
+        W, H = int(rng.choice([40, 120])), int(rng.choice([30, 90]))
+        xy = np.floor(rng.uniform(0, max(W, H), (n, 2)) * 2) / 2
+        if it % 3 == 0 and n >= 8:
+            xy[: n // 4] = xy[n // 4: 2 * (n // 4)]
+        uv = np.ascontiguousarray(rng.standard_normal((n, 2)))
+        k = int(min(rng.choice([1, 4, 20, 30]), n))
+        power, off = float(rng.choice([0.5, 1.0, 2.0])), float(rng.choice([0.5, 1.0]))
+        xg, yg = np.arange(W, dtype=float), np.arange(H, dtype=float)
+        out = np.empty((2, H, W))
+        L.host_idw_fill_ckdtree(_p(np.ascontiguousarray(xy)), _p(uv), n, 2, k, ctypes.c_double(power),
+                                ctypes.c_double(off), ctypes.c_double(1.0), _p(xg), W, _p(yg), H, _p(out))
+        with ora_lk.knn_mode("ckdtree"):
+            want = ora_lk.idwinterp2d(xy, uv, np.arange(W), np.arange(H), power=power, k=k, dist_offset=off)
+        assert np.abs(out - want).max() <= 1e-14, (it, n, k, power)
+        if live is not None:
+            ref = live(xy, uv, np.arange(W), np.arange(H), power=power, k=k, dist_offset=off)
+            assert np.abs(out - ref).max() <= 1e-14, (it, n, k, power)
