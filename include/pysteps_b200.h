@@ -312,6 +312,11 @@ int b200_zoom_bilinear(const double *a, int c, int h, int w, int oh, int ow, dou
  * do_scale, else a float64 copy. */
 int b200_proesmans_scale(const void *frames, int dtype, int64_t count, double im_min, double im_max,
                          int do_scale, double *out, void *stream);
+/* scipy.ndimage.gaussian_filter(in, sigma) of a float64 (h,w) image (proesmans.py:85-87): weights
+ * (HOST array, 2*radius+1 entries) is scipy's normalised kernel exp(-0.5 x^2 / sigma^2), radius =
+ * int(4 sigma + 0.5) <= 64; axis 0 then axis 1, "reflect" boundary, scipy's accumulation order. */
+int b200_gaussian_filter(const double *in, int h, int w, const double *weights, int radius, double *out,
+                         void *stream);
 /* _proesmans.pyx:19-44 _compute_advection_field(R, lam, num_iter, n_levels): frames (2,m,n)
  * float64 -> advfield (2,2,m,n) (forward / backward flow, x / y component) and quality (2,m,n)
  * (the consistency maps).  The relaxation sweep keeps the reference's raster-order Gauss-Seidel

@@ -86,8 +86,10 @@ def proesmans(input_images, lam=50.0, num_iter=100, num_levels=6, filter_std=0.0
     im_min, im_max = np.min(im), np.max(im)
     if im_max - im_min > 1e-8:
         im = (im - im_min) / (im_max - im_min) * 255.0
-    if filter_std > 0.0:
-        raise NotImplementedError("oracle restates filter_std == 0 only")
+    if filter_std > 0.0:  # proesmans.py:85-87 (scipy itself: the reference's own dependency)
+        from scipy.ndimage import gaussian_filter
+        im[0, :, :] = gaussian_filter(im[0, :, :], filter_std)
+        im[1, :, :] = gaussian_filter(im[1, :, :], filter_std)
     advfield, quality = compute_advection_field(im, lam, num_iter, num_levels)
     if not full_output:
         return advfield[0]

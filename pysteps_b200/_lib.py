@@ -44,6 +44,7 @@ _SIGNATURES = {
     "b200_spline_sample": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
                                    c_int, c_double, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "b200_proesmans_scale": (c_int, [c_void_p, c_int, ctypes.c_int64, c_double, c_double, c_int, c_void_p, c_void_p]),
+    "b200_gaussian_filter": (c_int, [c_void_p, c_int, c_int, c_dp, c_int, c_void_p, c_void_p]),
     "b200_proesmans_field": (c_int, [c_void_p, c_int, c_int, c_double, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "b200_bps_perturb_velocity": (c_int, [c_void_p, c_int, c_int, c_int, c_double, c_double, c_double,
                                           c_int, c_void_p, c_void_p, c_void_p]),

@@ -28,6 +28,18 @@ scale_kernel(const F *__restrict__ in, double *__restrict__ out, size_t count, d
         out[e] = pro::scale_value((double)in[e], lo, hi, do_scale);
 }
 
+// one axis of the Gaussian pre-filter: axis 0 filters columns, axis 1 rows
+__global__ void __launch_bounds__(256)
+gauss_axis_kernel(const double *__restrict__ in, double *__restrict__ out, int h, int w, int axis,
+                  const __grid_constant__ pro::GaussKernel k) {
+    const size_t total = (size_t)h * w, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const int y = (int)(e / w), x = (int)(e % w);
+        out[e] = axis == 0 ? pro::gauss_line_value(in + x, h, (size_t)w, y, k)
+                           : pro::gauss_line_value(in + (size_t)y * w, w, 1, x, k);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 pyr_kernel(const double *__restrict__ src, int sw, double *__restrict__ dst, int dh, int dw) {
     const size_t total = (size_t)dh * dw, stride = (size_t)gridDim.x * blockDim.x;
@@ -157,6 +169,25 @@ extern "C" int b200_proesmans_scale(const void *frames, int dtype, int64_t count
         b200::set_error("unknown frame dtype %d", dtype);
         return B200_EINVAL;
     }
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int b200_gaussian_filter(const double *in, int h, int w, const double *weights, int radius, double *out,
+                                    void *stream) {
+    B200_REQUIRE(in != nullptr && out != nullptr && weights != nullptr && h >= 1 && w >= 1, "bad arguments");
+    B200_REQUIRE(radius >= 0 && radius <= pro::GAUSS_MAX_RADIUS, "kernel radius must be 0..64 (sigma <= 16)");
+    cudaStream_t s = (cudaStream_t)stream;
+    pro::GaussKernel k;
+    memset(&k, 0, sizeof(k));
+    k.lw = radius;
+    for (int i = 0; i < 2 * radius + 1; i++) k.w[i] = weights[i];
+    b200::Scratch tmp;
+    const size_t N = (size_t)h * w;
+    B200_CUDA(tmp.alloc(N * sizeof(double), s));
+    gauss_axis_kernel<<<grid_for(N), 256, 0, s>>>(in, (double *)tmp.p, h, w, 0, k);
+    B200_LAUNCH_CHECK();
+    gauss_axis_kernel<<<grid_for(N), 256, 0, s>>>((const double *)tmp.p, out, h, w, 1, k);
     B200_LAUNCH_CHECK();
     return 0;
 }

@@ -41,6 +41,32 @@ PRO_FN double scale_value(double v, double lo, double hi, int do_scale) {
     return do_scale ? (v - lo) / (hi - lo) * 255.0 : v;
 }
 
+// scipy.ndimage.gaussian_filter (pysteps/motion/proesmans.py:85-87), one axis: correlate1d with the
+// symmetric kernel w[0 .. 2 lw] (centre w[lw]) and mode "reflect" (d c b a | a b c d | d c b a);
+// terms are added from the farthest pair inwards, as scipy's symmetric branch does
+constexpr int GAUSS_MAX_RADIUS = 64;
+struct GaussKernel {
+    int lw;
+    double w[2 * GAUSS_MAX_RADIUS + 1];
+};
+
+PRO_FN double gauss_reflect_at(const double *line, int n, size_t stride, long long i) {
+    if (n == 1) return line[0];
+    const long long p = 2LL * n;
+    i %= p;
+    if (i < 0) i += p;
+    return i < n ? line[(size_t)i * stride] : line[(size_t)(p - 1 - i) * stride];
+}
+
+// value at position l of the line (n samples, given stride)
+PRO_FN double gauss_line_value(const double *line, int n, size_t stride, int l, const GaussKernel &k) {
+    double tmp = gauss_reflect_at(line, n, stride, l) * k.w[k.lw];
+    for (int ii = -k.lw; ii < 0; ii++)
+        tmp += (gauss_reflect_at(line, n, stride, (long long)l + ii) + gauss_reflect_at(line, n, stride, (long long)l - ii)) *
+               k.w[k.lw + ii];
+    return tmp;
+}
+
 // :46-58 destination pixel (y, x) of the next pyramid level, source (sh, sw)
 PRO_FN double pyr_pixel(const double *src, int sw, int y, int x) {
     return (src[(size_t)(2 * y) * sw + 2 * x] + src[(size_t)(2 * y) * sw + 2 * x + 1] +

@@ -22,8 +22,7 @@ def _enabled():
 def proesmans(input_images, lam=50.0, num_iter=100, num_levels=6, filter_std=0.0, verbose=True,
               full_output=False):
     """Same contract as the reference (see its docstring, proesmans.py:29-71).  NumPy input ->
-    NumPy results; CUDA tensor input -> results stay on the device.  ``filter_std > 0`` (a
-    scipy.ndimage.gaussian_filter pre-smoothing) is not implemented."""
+    NumPy results; CUDA tensor input -> results stay on the device."""
     # decorators.check_input_frames(2, 2): decorators.py:121-146
     if input_images.ndim != 3:
         raise ValueError(
@@ -41,8 +40,6 @@ def proesmans(input_images, lam=50.0, num_iter=100, num_levels=6, filter_std=0.0
         raise NotImplementedError(
             "pysteps_b200 proesmans is built but not yet verified on hardware; "
             "PYSTEPS_B200_ENABLE_PROESMANS=1 enables it (there is no CPU fallback)")
-    if filter_std > 0.0:
-        raise NotImplementedError("pysteps_b200 proesmans: filter_std > 0 is not implemented")
     del verbose  # Not used
 
     _device.require_cuda()
@@ -73,6 +70,21 @@ def proesmans(input_images, lam=50.0, num_iter=100, num_levels=6, filter_std=0.0
     d_im = torch.empty((2, m, n), dtype=torch.float64, device="cuda")
     _lib.call("b200_proesmans_scale", d_in.data_ptr(), _device.dtype_code(d_in.dtype), 2 * m * n, float(lo),
               float(hi), int(do_scale), d_im.data_ptr(), _device.stream_ptr())
+
+    if filter_std > 0.0:  # proesmans.py:85-87 scipy.ndimage.gaussian_filter on both frames
+        sd = float(filter_std)
+        radius = int(4.0 * sd + 0.5)
+        if radius > 64:
+            raise NotImplementedError("pysteps_b200 proesmans: filter_std > 16 is not implemented")
+        # scipy.ndimage._filters._gaussian_kernel1d(sigma, 0, radius)[::-1]
+        x = np.arange(-radius, radius + 1)
+        phi_x = np.exp(-0.5 / (filter_std * filter_std) * x ** 2)
+        weights = np.ascontiguousarray((phi_x / phi_x.sum())[::-1], dtype=np.float64)
+        d_f = torch.empty((2, m, n), dtype=torch.float64, device="cuda")
+        for t in range(2):
+            _lib.call("b200_gaussian_filter", d_im[t].data_ptr(), m, n, weights.ctypes.data_as(_lib.c_dp), radius,
+                      d_f[t].data_ptr(), _device.stream_ptr())
+        d_im = d_f
 
     d_adv = torch.empty((2, 2, m, n), dtype=torch.float64, device="cuda")
     d_q = torch.empty((2, m, n), dtype=torch.float64, device="cuda")

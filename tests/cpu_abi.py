@@ -130,6 +130,14 @@ def _proesmans_scale(frames, code, count, lo, hi, do_scale, out, stream):
                            ctypes.c_double(hi), int(do_scale), ctypes.c_void_p(_addr(out)))
 
 
+def _gaussian_filter(src, h, w, weights, radius, out, stream):
+    import host_kernels
+    L = host_kernels.lib()
+    L.host_gaussian_filter.restype = None
+    vp = ctypes.c_void_p
+    L.host_gaussian_filter(vp(_addr(src)), h, w, vp(_addr(weights)), radius, vp(_addr(out)))
+
+
 def _proesmans_field(frames, m, n, lam, num_iter, num_levels, adv, quality, stream):
     import host_kernels
     L = host_kernels.lib()
@@ -366,7 +374,7 @@ _TABLE_LK = {"b200_mask_invalid": _lk_mask_invalid, "b200_morph_opening": _lk_mo
              "b200_idw_fill": _lk_idw_fill, "b200_idw_fill_ckdtree": _lk_idw_fill_ckdtree, "b200_fill_f64": _fill_f64}
 
 _TABLE = {"b200_vet_cost": _vet_cost, "b200_vet_warp": _vet_warp, "b200_zoom_bilinear": _zoom,
-          "b200_proesmans_scale": _proesmans_scale, "b200_proesmans_field": _proesmans_field,
+          "b200_gaussian_filter": _gaussian_filter, "b200_proesmans_scale": _proesmans_scale, "b200_proesmans_field": _proesmans_field,
           "b200_sl_trajectories": _sl_trajectories, "b200_spline_prepare": _spline_prepare,
           "b200_spline_sample": _spline_sample, "b200_field_stats": _field_stats, "b200_sl_extrapolate_rows": _sl_rows,
           "b200_bps_perturb_velocity": _bps}

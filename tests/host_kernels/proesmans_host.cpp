@@ -53,6 +53,19 @@ void host_proesmans_scale(const double *in, int64_t count, double lo, double hi,
     for (int64_t e = 0; e < count; e++) out[e] = pro::scale_value(in[e], lo, hi, do_scale);
 }
 
+// == b200_gaussian_filter
+void host_gaussian_filter(const double *in, int h, int w, const double *weights, int radius, double *out) {
+    pro::GaussKernel k;
+    memset(&k, 0, sizeof(k));
+    k.lw = radius;
+    for (int i = 0; i < 2 * radius + 1; i++) k.w[i] = weights[i];
+    std::vector<double> tmp((size_t)h * w);
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) tmp[(size_t)y * w + x] = pro::gauss_line_value(in + x, h, (size_t)w, y, k);
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) out[(size_t)y * w + x] = pro::gauss_line_value(tmp.data() + (size_t)y * w, w, 1, x, k);
+}
+
 // == b200_proesmans_field
 int host_proesmans_field(const double *frames, int m, int n, double lam, int num_iter, int num_levels,
                          double *advfield, double *quality) {

@@ -66,7 +66,12 @@ def test_dtypes_nan_and_unsupported_options(enabled):
         got = proesmans(nan, num_iter=3, num_levels=2)
         want = ora.proesmans(nan, num_iter=3, num_levels=2)
         assert np.array_equal(got, want, equal_nan=True)
+        # Gaussian pre-filter (scipy.ndimage.gaussian_filter restated, bit for bit)
+        for std in (0.7, 2.0):
+            got = proesmans(fr, filter_std=std, num_iter=5, num_levels=3, full_output=True)
+            want = ora.proesmans(fr, filter_std=std, num_iter=5, num_levels=3, full_output=True)
+            assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
         with pytest.raises(NotImplementedError, match="filter_std"):
-            proesmans(fr, filter_std=1.0)
+            proesmans(fr, filter_std=20.0)
         with pytest.raises(NotImplementedError, match="empty pyramid level"):
             proesmans(fr, num_levels=9)

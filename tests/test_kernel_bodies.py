@@ -250,3 +250,20 @@ def test_exact_idw_body_matches_the_reference_at_every_grid_point():
         if live is not None:
             ref = live(xy, uv, np.arange(W), np.arange(H), power=power, k=k, dist_offset=off)
             assert np.abs(out - ref).max() <= 1e-14, (it, n, k, power)
+
+
+@pytest.mark.parametrize("shape", [(17, 23), (5, 40), (1, 9), (3, 3), (64, 80)])
+@pytest.mark.parametrize("sigma", [0.5, 1.0, 2.3, 6.0])
+def test_gaussian_filter_body_matches_scipy_bitwise(shape, sigma):
+    from scipy import ndimage as ndi
+    rng = np.random.default_rng(shape[0] + int(sigma * 10))
+    a = np.ascontiguousarray(rng.standard_normal(shape) * 20)
+    radius = int(4.0 * float(sigma) + 0.5)
+    x = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / (sigma * sigma) * x ** 2)
+    weights = np.ascontiguousarray((phi / phi.sum())[::-1])
+    out = np.empty_like(a)
+    L = host_kernels.lib()
+    L.host_gaussian_filter.restype = None
+    L.host_gaussian_filter(_p(a), shape[0], shape[1], _p(weights), radius, _p(out))
+    assert_bits_equal(out, ndi.gaussian_filter(a, sigma), f"{shape} sigma {sigma}")

@@ -61,6 +61,29 @@ def test_oracle_matches_the_fastmath_build_of_the_reference(name, golden):
         assert np.abs(ref_adv).max() > 0.3   # the cases do exercise the solver
 
 
+def test_gaussian_prefilter_against_live_reference():
+    from _refimport import available, ref_module
+    import glob
+    if not (available() and glob.glob("/tmp/proes_strict/pysteps/motion/_proesmans*.so")):
+        pytest.skip("reference extension (IEEE build) not present in this container")
+    try:
+        ref = ref_module("pysteps.motion.proesmans", "/tmp/proes_strict").proesmans
+        import pysteps.motion._proesmans as ext
+        if "proes_strict" not in ext.__file__:
+            pytest.skip("another build of the extension is already imported")
+    except ImportError:
+        pytest.skip("reference not importable")
+    frames, _ = build_case("default_96x128")
+    ora.raster_order_mean(True)
+    try:
+        for std in (0.8, 2.5):
+            a, qa = ref(frames, filter_std=std, num_iter=10, num_levels=3, full_output=True)
+            b, qb = ora.proesmans(frames, filter_std=std, num_iter=10, num_levels=3, full_output=True)
+            assert_bits_equal(b, a, f"filter_std {std}")
+    finally:
+        ora.raster_order_mean(False)
+
+
 def test_argument_errors():
     with pytest.raises(ValueError, match="dimension mismatch"):
         ora.proesmans(np.zeros((8, 8)))
