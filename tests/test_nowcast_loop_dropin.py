@@ -81,3 +81,33 @@ def test_deterministic_loop(ref):
     with cpu_abi.emulated():
         got = utils.nowcast_main_loop(precip, velocity, {"f": precip}, 4, "semilagrangian_b200", model)
     assert np.array_equal(np.asarray(got), np.asarray(want), equal_nan=True)
+
+
+def test_steps_forecast_end_to_end(ref):
+    """pysteps.nowcasts.steps.forecast itself (cascade decomposition, AR model, noise, BPS velocity
+    perturbations, AR pre-alignment through the extrapolator, the member loop): seeded, once with
+    the stock methods and once with extrap_method / vel_pert_method pointing at the B200 ones."""
+    import contextlib
+    import importlib
+    import io
+    import warnings
+    steps = importlib.import_module("pysteps.nowcasts.steps")
+    m, n = 64, 64
+    fr = syn.rain_frames(m, n, 3, 4, dx=2, dy=-1)
+    R = np.where(fr > 0.1, 10 * np.log10(np.maximum(fr, 0.1)), -15.0)
+    V = 2.0 * syn.velocity_field(m, n, 4)
+    kw = dict(timesteps=3, n_ens_members=3, n_cascade_levels=3, precip_thr=-10.0, kmperpixel=1.0, timestep=5.0,
+              noise_method="nonparametric", seed=42, num_workers=1)
+
+    def run(**extra):
+        with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+            warnings.simplefilter("ignore")
+            return steps.forecast(R, V, **kw, **extra)
+
+    want = run()
+    with cpu_abi.emulated():
+        got = run(extrap_method="semilagrangian_b200", vel_pert_method="bps_b200",
+                  extrap_kwargs={"b200_resident": True})
+    assert want.shape == got.shape == (3, 3, m, n)
+    assert np.array_equal(want, got, equal_nan=True)
+    assert np.isfinite(want).any()
