@@ -18,7 +18,9 @@ def lib():
                         os.path.join(csrc, "knn_body.cuh")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+            tmp = f"{so}.tmp.{os.getpid()}"
             subprocess.check_call([cxx, "-O2", "-fPIC", "-shared", "-std=c++17", "-ffp-contract=off",
-                                   "-fno-fast-math", "-Wall", "-o", so] + units)
+                                   "-fno-fast-math", "-Wall", "-o", tmp] + units)
+            os.replace(tmp, so)
         _LIB = ctypes.CDLL(so)
     return _LIB
