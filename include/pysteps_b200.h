@@ -204,7 +204,10 @@ int b200_masked_minmax(const double *img, const uint8_t *mask, int m, int n, int
 
 /* "scale between 0 and 255" + astype(uint8).  mode 0: tracking/lucaskanade.py:144-160;
  * mode 1: feature/shitomasi.py:131-151 (buffer_mask = dilate) with valid = buffered mask
- * clear.  stats = output of b200_masked_minmax, masked pixels take *fill_dev. */
+ * clear.  stats = output of b200_masked_minmax, masked pixels take *fill_dev.
+ * mode | B200_QUANTISE_F32: the frames were float32 at the API (img holds them widened): scale in
+ * float32 arithmetic as NumPy does for a float32 array. */
+#define B200_QUANTISE_F32 2
 int b200_quantise_u8(const double *img, const uint8_t *mask, int m, int n, int mode, int dilate,
                      const double *stats, const double *fill_dev, uint8_t *out, uint8_t *valid,
                      void *stream);

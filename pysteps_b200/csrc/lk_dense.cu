@@ -14,6 +14,7 @@
 #include <math_constants.h>
 
 #include "common.cuh"
+#include "quantise_body.cuh"
 
 namespace {
 
@@ -197,6 +198,10 @@ __device__ __forceinline__ uint8_t cast_u8(double v) {
 // mode 0 (tracking/lucaskanade.py:144-160): masked pixels take the fill value, min/max over
 // the unmasked pixels.  mode 1 (feature/shitomasi.py:131-151): additionally row 0 / row 1 are
 // masked as described above, min/max over what is left, and `valid` = buffered mask clear.
+// F32: the frames were float32 at the API, so the reference scales them in float32
+// (img.filled() - im_min) / (im_max - im_min) * 255 with float32 scalars; the values held here are
+// those float32 numbers widened, so narrowing them back is exact.
+template <bool F32>
 __global__ void __launch_bounds__(TX *TY)
 quantise_kernel(const double *__restrict__ img, const uint8_t *__restrict__ mask, int m, int n, int mode,
                 int dil, const double *__restrict__ stats, const double *__restrict__ fill_dev,
@@ -232,7 +237,9 @@ quantise_kernel(const double *__restrict__ img, const uint8_t *__restrict__ mask
     const double im_min = stats[3 * set + 0], im_max = stats[3 * set + 1];
     const double v = msk ? *fill_dev : img[i];
     double q;
-    if (__dsub_rn(im_max, im_min) > 1e-8)
+    if (F32) {
+        q = qz::scale_f32(v, im_min, im_max);
+    } else if (__dsub_rn(im_max, im_min) > 1e-8)
         q = __dmul_rn(__ddiv_rn(__dsub_rn(v, im_min), __dsub_rn(im_max, im_min)), 255.0);
     else
         q = __dsub_rn(v, im_min);
@@ -441,9 +448,13 @@ extern "C" int b200_quantise_u8(const double *img, const uint8_t *mask, int m, i
                                 int dilate, const double *stats, const double *fill_dev,
                                 uint8_t *out, uint8_t *valid, void *stream) {
     B200_REQUIRE(img && mask && stats && fill_dev && out && m >= 1 && n >= 1 && dilate >= 0 &&
-                     dilate <= 31 && (mode == 0 || mode == 1), "bad arguments");
-    quantise_kernel<<<grid2d(m, n), dim3(TX, TY), 0, (cudaStream_t)stream>>>(img, mask, m, n, mode, dilate,
-                                                                            stats, fill_dev, out, valid);
+                     dilate <= 31 && (mode & ~3) == 0, "bad arguments");
+    if (mode & B200_QUANTISE_F32)
+        quantise_kernel<true><<<grid2d(m, n), dim3(TX, TY), 0, (cudaStream_t)stream>>>(img, mask, m, n, mode & 1, dilate,
+                                                                                      stats, fill_dev, out, valid);
+    else
+        quantise_kernel<false><<<grid2d(m, n), dim3(TX, TY), 0, (cudaStream_t)stream>>>(img, mask, m, n, mode & 1, dilate,
+                                                                                       stats, fill_dev, out, valid);
     B200_LAUNCH_CHECK();
     return 0;
 }

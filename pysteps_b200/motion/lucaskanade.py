@@ -45,9 +45,12 @@ class _Frame:
     are allocated up front (on the caller's stream) so that the work itself can be enqueued on
     either stream without involving the caching allocator."""
     __slots__ = ("img", "user_mask", "mask", "stats0", "opened", "stats", "q_track",
-                 "prepared", "have_stats", "have_q")
+                 "prepared", "have_stats", "have_q", "qflag")
 
-    def __init__(self, img_d, user_mask_d, m, n, size_opening):
+    def __init__(self, img_d, user_mask_d, m, n, size_opening, f32=False):
+        # frames that were float32 at the API are scaled to uint8 in float32 arithmetic, as NumPy
+        # does for a float32 array (tracking/lucaskanade.py:144-160, feature/shitomasi.py:141-151)
+        self.qflag = 2 if f32 else 0
         self.img = img_d
         self.user_mask = user_mask_d
         self.mask = torch.empty((m, n), dtype=torch.uint8, device="cuda")
@@ -84,7 +87,7 @@ def _track_image(f, m, n, buffer_mask):
     """the uint8 image track_features builds (tracking/lucaskanade.py:144-160)"""
     if not f.have_q:
         st = _frame_stats(f, m, n, buffer_mask)
-        _call("b200_quantise_u8", f.opened.data_ptr(), f.mask.data_ptr(), m, n, 0, 0, st.data_ptr(),
+        _call("b200_quantise_u8", f.opened.data_ptr(), f.mask.data_ptr(), m, n, 0 | f.qflag, 0, st.data_ptr(),
               st.data_ptr(), f.q_track.data_ptr(), None, _s())
         f.have_q = True
     return f.q_track
@@ -201,6 +204,9 @@ def dense_lucaskanade(input_images, lk_kwargs=None, fd_method="shitomasi", fd_kw
         raise ValueError("b200_rows must satisfy 0 <= r0 < r1 <= m")
     mb = r1 - r0
 
+    f32 = (input_images.dtype == torch.float32) if isinstance(input_images, torch.Tensor) \
+        else (np.asarray(input_images).dtype == np.float32)
+
     # ---- upload (the reference copies its input, :182) ------------------------------------
     user_mask_d = None
     if isinstance(input_images, MaskedArray):
@@ -215,7 +221,7 @@ def dense_lucaskanade(input_images, lk_kwargs=None, fd_method="shitomasi", fd_kw
     # while the side stream prepares the next frame and builds both pyramids.
     main = torch.cuda.current_stream()
     side = _side_stream()
-    frames = [_Frame(frames_d[t], None if user_mask_d is None else user_mask_d[t], m, n, size_opening)
+    frames = [_Frame(frames_d[t], None if user_mask_d is None else user_mask_d[t], m, n, size_opening, f32)
               for t in range(nr_fields)]
 
     def prepare(t):
@@ -258,7 +264,7 @@ def dense_lucaskanade(input_images, lk_kwargs=None, fd_method="shitomasi", fd_kw
         eig = torch.empty((m, n), dtype=torch.float32, device="cuda")
         ev_stats = torch.cuda.Event()
         ev_stats.record(main)
-        _call("b200_quantise_u8", f.opened.data_ptr(), f.mask.data_ptr(), m, n, 1, buffer_mask,
+        _call("b200_quantise_u8", f.opened.data_ptr(), f.mask.data_ptr(), m, n, 1 | f.qflag, buffer_mask,
               st.data_ptr(), st.data_ptr(), q_det.data_ptr(), valid.data_ptr(), _s())
         _call("b200_min_eig", q_det.data_ptr(), m, n, eig.data_ptr(), _s())
         # ---- side stream: next frame + both pyramids (needs this frame's stats only).  Enqueued

@@ -22,6 +22,10 @@ def _s():
     return _device.stream_ptr()
 
 
+def _is_f32(image):
+    return np.asarray(image).dtype == np.float32
+
+
 def _frame(image):
     """(device image float64, device user mask or None) of an ndarray / MaskedArray."""
     if isinstance(image, MaskedArray):
@@ -68,12 +72,12 @@ def detection(input_image, max_corners=1000, max_num_features=None, quality_leve
         raise NotImplementedError("pysteps_b200 detection: max_corners must be positive")
     m, n = input_image.shape
     img, um = _frame(input_image)
-    f = _lk._Frame(img, um, m, n, 0)
+    f = _lk._Frame(img, um, m, n, 0, _is_f32(input_image))
     _lk._prepare_frame(f, m, n, 0)
     st = _lk._frame_stats(f, m, n, int(buffer_mask))
     q = torch.empty((m, n), dtype=torch.uint8, device="cuda")
     valid = torch.empty((m, n), dtype=torch.uint8, device="cuda")
-    _lib.call("b200_quantise_u8", f.opened.data_ptr(), f.mask.data_ptr(), m, n, 1, int(buffer_mask),
+    _lib.call("b200_quantise_u8", f.opened.data_ptr(), f.mask.data_ptr(), m, n, 1 | f.qflag, int(buffer_mask),
               st.data_ptr(), st.data_ptr(), q.data_ptr(), valid.data_ptr(), _s())
     eig = torch.empty((m, n), dtype=torch.float32, device="cuda")
     _lib.call("b200_min_eig", q.data_ptr(), m, n, eig.data_ptr(), _s())
@@ -108,7 +112,7 @@ def track_features(prvs_image, next_image, points, winsize=(50, 50), nr_levels=3
     pyrs = []
     for image, deriv in ((prvs_image, True), (next_image, False)):
         img, um = _frame(image)
-        f = _lk._Frame(img, um, m, n, 0)
+        f = _lk._Frame(img, um, m, n, 0, _is_f32(image))
         _lk._prepare_frame(f, m, n, 0)
         q = _lk._track_image(f, m, n, 0)
         P = torch.empty(total, dtype=torch.uint8, device="cuda")

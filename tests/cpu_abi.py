@@ -238,7 +238,9 @@ def _lk_masked_minmax(img, mask, m, n, dilate, stats0, stats, stream):
 def _lk_quantise(img, mask, m, n, mode, dilate, stats, fill, out, valid, stream):
     from oracle import lucaskanade as ora_lk
     ma = _masked(img, mask, m, n)
-    if mode == 0:
+    if mode & 2:   # B200_QUANTISE_F32: the frames were float32 at the API
+        ma = np.ma.MaskedArray(np.ma.getdata(ma).astype(np.float32), mask=np.ma.getmaskarray(ma))
+    if (mode & 1) == 0:
         q = ora_lk.tracking_image(ma)
     else:
         q, v = ora_lk.detection_image(ma, dilate)

@@ -15,7 +15,7 @@ def lib():
         units = [os.path.join(_HERE, "spline_host.cpp"), os.path.join(_HERE, "proesmans_host.cpp"),
                  os.path.join(_HERE, "knn_host.cpp")]
         srcs = units + [os.path.join(csrc, "spline_body.cuh"), os.path.join(csrc, "proesmans_body.cuh"),
-                        os.path.join(csrc, "knn_body.cuh")]
+                        os.path.join(csrc, "knn_body.cuh"), os.path.join(csrc, "quantise_body.cuh")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
             tmp = f"{so}.tmp.{os.getpid()}"

@@ -4,6 +4,7 @@
 #include <vector>
 
 #include "../../pysteps_b200/csrc/knn_body.cuh"
+#include "../../pysteps_b200/csrc/quantise_body.cuh"
 
 extern "C" {
 
@@ -59,6 +60,11 @@ void host_idw_fill_ckdtree(const double *xy, const double *vals, int npts, int n
             kd::query(t, xgrid[j], ygrid[i], k, inds.data(), nb.data(), q.data(), pool.data(), w.data());
             kd::idw_point(vals, nvar, inds.data(), w.data(), k, power, offset, mean_res, out + (size_t)i * nx + j, N);
         }
+}
+
+// float32 scaling of the quantise kernel, element by element
+void host_scale_f32(const double *v, int64_t count, double im_min, double im_max, double *out) {
+    for (int64_t i = 0; i < count; i++) out[i] = qz::scale_f32(v[i], im_min, im_max);
 }
 
 }  // extern "C"

@@ -4,6 +4,7 @@ b200_rows extension) over randomised frames and argument combinations.  The C-AB
 emulated with the oracle's stage functions (tests/cpu_abi.py), so the shim must reproduce the
 oracle's dense_lucaskanade -- itself pinned to the reference -- bit for bit; errors are compared
 with the live reference when /root/reference exists."""
+import os
 import warnings
 
 import numpy as np
@@ -190,3 +191,34 @@ def test_exact_ties_mode_reproduces_the_reference_dense_field(monkeypatch):
                 n += 1
                 assert got.shape == ref.shape and np.abs(got - ref).max() <= 1e-13, (it, kw)
     assert n >= 20
+
+
+def test_float32_frames_are_scaled_in_float32_like_the_reference():
+    """float32 frames: NumPy scales them to uint8 in float32, which moves some pixels by one grey
+    level against float64 arithmetic and with them corners and vectors; the shim flags the frames
+    (B200_QUANTISE_F32) and reproduces the oracle -- and, with the reference's tie order, the live
+    reference's sparse vectors."""
+    from pysteps_b200.motion.lucaskanade import dense_lucaskanade
+    live = _live()
+    rng = np.random.default_rng(0)
+    with cpu_abi.emulated():
+        for it in range(12):
+            m, n = int(rng.integers(60, 160)), int(rng.integers(60, 160))
+            fr = syn.rain_frames(m, n, int(rng.choice([2, 3])), int(rng.integers(0, 1000)), dx=2, dy=-1)
+            if it % 2:
+                fr = np.where(fr > 0.1, 10 * np.log10(np.maximum(fr, 0.1)), -15.0)
+            fr = (fr + 0.37 * rng.standard_normal(fr.shape)).astype(np.float32)
+            inp = fr if it % 3 else np.ma.masked_invalid(fr)
+            got = dense_lucaskanade(inp.copy(), dense=False)
+            want = ora.dense_lucaskanade(inp.copy(), dense=False)
+            assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), it
+            V = dense_lucaskanade(inp.copy())
+            assert V.dtype == np.float64 and np.array_equal(V, ora.dense_lucaskanade(inp.copy())), it
+            if live is not None:
+                os.environ["PYSTEPS_B200_EXACT_TIES"] = "1"
+                try:
+                    ref = live(inp.copy(), dense=False)
+                    got = dense_lucaskanade(inp.copy(), dense=False)
+                finally:
+                    del os.environ["PYSTEPS_B200_EXACT_TIES"]
+                assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]), it

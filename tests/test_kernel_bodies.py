@@ -267,3 +267,22 @@ def test_gaussian_filter_body_matches_scipy_bitwise(shape, sigma):
     L.host_gaussian_filter.restype = None
     L.host_gaussian_filter(_p(a), shape[0], shape[1], _p(weights), radius, _p(out))
     assert_bits_equal(out, ndi.gaussian_filter(a, sigma), f"{shape} sigma {sigma}")
+
+
+def test_float32_quantise_body_matches_numpy():
+    """`(x - min) / (max - min) * 255` of a float32 array (tracking/lucaskanade.py:144-160) as the
+    F32 variant of the quantise kernel evaluates it."""
+    L = host_kernels.lib()
+    L.host_scale_f32.restype = None
+    rng = np.random.default_rng(6)
+    for lo, hi in ((-15.0, 43.7), (0.0, 1e-9), (3.5, 3.5), (-1e6, 2.5e6)):
+        x = rng.uniform(lo, max(hi, lo + 1e-3), 5000).astype(np.float32)
+        x[:2] = [lo, hi]
+        mn, mx = np.float32(x.min()), np.float32(x.max())
+        want = ((x - mn) / (mx - mn) * 255) if mx - mn > 1e-8 else (x - mn)
+        assert want.dtype == np.float32
+        got = np.empty(x.size)
+        L.host_scale_f32(_p(x.astype(np.float64)), ctypes.c_int64(x.size), ctypes.c_double(float(mn)),
+                         ctypes.c_double(float(mx)), _p(got))
+        assert_bits_equal(got.astype(np.float32), want, f"range {lo}..{hi}")
+        assert np.array_equal(got, want.astype(np.float64))

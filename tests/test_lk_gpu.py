@@ -446,3 +446,23 @@ def test_exact_ties_dense_field_vs_oracle_ckdtree_mode(env):
         with ora.knn_mode("ckdtree"):
             Vo = ora.dense_lucaskanade(fr)
         assert V.shape == Vo.shape and np.abs(V - Vo).max() <= 1e-13, (m, n, T)
+
+
+def test_float32_frames_vs_oracle(env):
+    """float32 frames are scaled to uint8 in float32 arithmetic (B200_QUANTISE_F32), like NumPy
+    does for a float32 array; sparse vectors bit-identical to the oracle, dense field <= 1e-12."""
+    from oracle import lucaskanade as ora
+    from pysteps_b200 import _synthetic as syn
+    from pysteps_b200.motion.lucaskanade import dense_lucaskanade as lk
+    rng = np.random.default_rng(0)
+    for it in range(6):
+        m, n = int(rng.integers(80, 260)), int(rng.integers(80, 260))
+        fr = syn.rain_frames(m, n, int(rng.choice([2, 3])), it, dx=2, dy=-1)
+        if it % 2:
+            fr = np.where(fr > 0.1, 10 * np.log10(np.maximum(fr, 0.1)), -15.0)
+        fr = (fr + 0.37 * rng.standard_normal(fr.shape)).astype(np.float32)
+        xy, uv = lk(fr, dense=False)
+        oxy, ouv = ora.dense_lucaskanade(fr, dense=False)
+        assert np.array_equal(xy, oxy) and np.array_equal(uv, ouv), it
+        V, Vo = lk(fr), ora.dense_lucaskanade(fr)
+        assert V.dtype == np.float64 and np.abs(V - Vo).max() <= 1e-12, it
