@@ -90,10 +90,9 @@ class _Stats:
 def extrapolate(precip, velocity, timesteps, outval=np.nan, xy_coords=None,
                 allow_nonfinite_values=False, vel_timestep=1, **kwargs):
     """Semi-Lagrangian backward extrapolation; same contract as the reference
-    (see its docstring, semilagrangian.py:30-104).  Differences: ``interp_order``
-    must be 1 (0 and 2..5 are built -- csrc/spline.cu -- but stay behind
-    ``PYSTEPS_B200_ENABLE_SPLINE=1`` until they have been verified on hardware) and
-    ``map_coordinates_mode`` one of "constant"/"nearest" (anything else raises
+    (see its docstring, semilagrangian.py:30-104).  ``interp_order`` 0..5 as in scipy (order 1 is
+    the fused trajectory kernel of csrc/sl.cu, the other orders csrc/spline.cu).  Difference:
+    ``map_coordinates_mode`` must be one of "constant"/"nearest" (anything else raises
     NotImplementedError instead of silently using a CPU path).
     """
     if precip is not None and precip.ndim != 2:
@@ -166,10 +165,6 @@ _POLES = {
 _SPLINE_PAD = 12  # scipy.ndimage._prepad_for_spline_filter, mode "nearest"
 
 
-def _spline_enabled():
-    return os.environ.get("PYSTEPS_B200_ENABLE_SPLINE", "") == "1"
-
-
 def _extrapolate_checked(precip, velocity, d_precip, d_vel, stats, on_device, timesteps, outval,
                          xy_coords, vel_timestep, kwargs, deferred_warnings, allow_nonfinite_values=False):
     """semilagrangian.py:125-266 (everything after the finiteness checks)."""
@@ -196,11 +191,6 @@ def _extrapolate_checked(precip, velocity, d_precip, d_vel, stats, on_device, ti
 
     if interp_order not in (0, 1, 2, 3, 4, 5):
         raise RuntimeError("spline order not supported")  # scipy.ndimage._ni_support._check_order
-    if interp_order != 1 and not _spline_enabled():
-        raise NotImplementedError(
-            "pysteps_b200 semilagrangian: only interp_order=1 is implemented on the GPU "
-            f"(got {interp_order}); no CPU fallback is provided -- orders 0 and 2..5 are built but "
-            "not yet verified on hardware; PYSTEPS_B200_ENABLE_SPLINE=1 enables them")
     if map_coordinates_mode not in _MODES:
         raise NotImplementedError(
             "pysteps_b200 semilagrangian: map_coordinates_mode must be 'constant' or "

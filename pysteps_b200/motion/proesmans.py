@@ -2,21 +2,14 @@
 (pysteps/motion/proesmans.py:20-94) with the reference's native extension
 (pysteps/motion/_proesmans.pyx) replaced by ``csrc/proesmans.cu``.
 
-Built and verified on the CPU (the kernels' per-thread bodies and their wavefront schedule are
-executed on the host against the oracle and the reference extension: tests/test_kernel_bodies.py,
-tests/test_host_logic_proesmans.py) but NOT yet run on hardware, so it is opt-in:
-``PYSTEPS_B200_ENABLE_PROESMANS=1``; without it the call raises NotImplementedError.
+Parity: tests/test_proesmans_gpu.py (bit-identical to the IEEE build of the reference source on
+the B200), tests/test_kernel_bodies.py and tests/test_host_logic_proesmans.py (kernel bodies and
+host logic on the CPU).
 """
-import os
-
 import numpy as np
 import torch
 
 from .. import _device, _lib
-
-
-def _enabled():
-    return os.environ.get("PYSTEPS_B200_ENABLE_PROESMANS", "") == "1"
 
 
 def proesmans(input_images, lam=50.0, num_iter=100, num_levels=6, filter_std=0.0, verbose=True,
@@ -36,10 +29,10 @@ def proesmans(input_images, lam=50.0, num_iter=100, num_levels=6, filter_std=0.0
             "Minimum frames: 2\n"
             "Maximum frames: 2\n"
         )
-    if not _enabled():
-        raise NotImplementedError(
-            "pysteps_b200 proesmans is built but not yet verified on hardware; "
-            "PYSTEPS_B200_ENABLE_PROESMANS=1 enables it (there is no CPU fallback)")
+    if input_images.shape[0] < 2:
+        # the reference's own check lets a single frame through and fails on im2 = input_images[-1]
+        # of the missing pair with an IndexError (proesmans.py:73-77); say so before any upload
+        raise IndexError("proesmans needs two input frames")
     del verbose  # Not used
 
     _device.require_cuda()

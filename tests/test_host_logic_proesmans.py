@@ -13,15 +13,15 @@ from proesmans_cases import CASES, build_case
 
 
 @pytest.fixture
-def enabled(monkeypatch):
-    monkeypatch.setenv("PYSTEPS_B200_ENABLE_PROESMANS", "1")
+def enabled():
+    return None
 
 
-def test_is_opt_in_until_verified_on_hardware():
+def test_frame_checks_come_first():
     from pysteps_b200.motion import get_method
     with cpu_abi.emulated():
-        with pytest.raises(NotImplementedError, match="PYSTEPS_B200_ENABLE_PROESMANS"):
-            get_method("proesmans")(np.zeros((2, 16, 16)))
+        with pytest.raises(IndexError):
+            get_method("proesmans")(np.zeros((1, 16, 16)))
         # the frame checks come first, as in the reference (decorators.check_input_frames)
         with pytest.raises(ValueError, match="dimension mismatch"):
             get_method("proesmans")(np.zeros((16, 16)))

@@ -173,7 +173,7 @@ def test_member_loop_with_handles_matches_reference_expression():
 
 @pytest.mark.parametrize("seed", range(3))
 def test_spline_orders_host_logic_and_kernel_bodies(seed, monkeypatch):
-    """interp_order 0 / 3 (behind PYSTEPS_B200_ENABLE_SPLINE=1 until verified on hardware): the
+    """interp_order 0, 2..5: the
     shim's branch -- trajectories per leadtime, prefilter, sampling, mask warps, outval="min" on
     the zero-filled copy, bands -- driven through the emulated C ABI, whose spline entry points
     are the CUDA kernels' own bodies compiled for the host (tests/host_kernels)."""
@@ -182,9 +182,6 @@ def test_spline_orders_host_logic_and_kernel_bodies(seed, monkeypatch):
     ref, live = _reference()
     rng = np.random.default_rng(300 + seed)
     with cpu_abi.emulated():
-        with pytest.raises(NotImplementedError, match="PYSTEPS_B200_ENABLE_SPLINE"):
-            extrap(np.ones((4, 4)), np.ones((2, 4, 4)), 1, interp_order=3)
-        monkeypatch.setenv("PYSTEPS_B200_ENABLE_SPLINE", "1")
         with pytest.raises(RuntimeError, match="spline order not supported"):
             extrap(np.ones((4, 4)), np.ones((2, 4, 4)), 1, interp_order=6)
         n_ok = 0

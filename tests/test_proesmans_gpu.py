@@ -1,9 +1,6 @@
-"""GPU parity tests of the Proesmans method (csrc/proesmans.cu).  Built and verified on the CPU
-(tests/test_kernel_bodies.py, tests/test_host_logic_proesmans.py); not yet run on hardware, hence
-opt-in and skipped unless the variable is set:
-
-    PYSTEPS_B200_ENABLE_PROESMANS=1 python -m pytest tests/test_proesmans_gpu.py -m gpu
-"""
+"""GPU parity tests of the Proesmans method (csrc/proesmans.cu) against the reference-generated
+goldens and the oracle (bodies / host logic also on the CPU: tests/test_kernel_bodies.py,
+tests/test_host_logic_proesmans.py)."""
 import os
 
 import numpy as np
@@ -12,9 +9,7 @@ from conftest import assert_bits_equal
 
 from proesmans_cases import STRICT_CASES, build_case
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("PYSTEPS_B200_ENABLE_PROESMANS") != "1",
-                                 reason="proesmans is not yet verified on hardware (opt-in)")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.fixture(scope="module")

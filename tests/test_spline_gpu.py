@@ -1,19 +1,13 @@
-"""GPU parity tests of interp_order 0 and 2..5 (csrc/spline.cu).  The path is built and its kernel
-bodies and host logic are verified on the CPU (tests/test_kernel_bodies.py,
-tests/test_host_logic_sl.py) but it has not run on hardware yet, so it stays behind
-PYSTEPS_B200_ENABLE_SPLINE=1 and these tests are skipped unless that variable is set:
-
-    PYSTEPS_B200_ENABLE_SPLINE=1 python -m pytest tests/test_spline_gpu.py -m gpu
-"""
+"""GPU parity tests of interp_order 0 and 2..5 (csrc/spline.cu) against the reference-generated
+goldens and the oracle (kernel bodies and host logic are additionally run on the CPU:
+tests/test_kernel_bodies.py, tests/test_host_logic_sl.py)."""
 import os
 
 import numpy as np
 import pytest
 from conftest import assert_bits_equal
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("PYSTEPS_B200_ENABLE_SPLINE") != "1",
-                                 reason="spline orders are not yet verified on hardware (opt-in)")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.fixture(scope="module")
