@@ -4,22 +4,32 @@
 extrapolation.
 
     python bench.py --gpus N --steps K --warmup W          (ours, CUDA)
-    python bench.py --impl reference ...                   (CPU oracle port, host cores)
+    python bench.py --impl reference ...                   (CPU oracle port, all host cores)
 
-One "step" = one pass of the hot path over one batch of synthetic input, on every rank:
-  motion field from this rank's last three frames (dense Lucas-Kanade),
+Headline (every N): one "step" = one pass of the hot path over one batch of synthetic input, on
+every rank:
+  motion field from this rank's last two frames (dense Lucas-Kanade),
   12-leadtime semi-Lagrangian extrapolation of this rank's field with it.
 Metric: Mpix/s advected = (N * T * m * n) / step time, max over ranks (weak scaling: N
 independent nowcasts, one per GPU, no collective on the data path).
-Other workloads (--workload): ensemble24 (24 BPS-perturbed members round-robin over the GPUs,
-one NCCL broadcast of the motion field), composite4096 (one 4096^2 composite, output row bands
-over the GPUs, NCCL all-gather of the motion-field bands), vet_sl12_2048.
+
+The same JSON line carries two more blocks, measured at every N with the same timing rules
+(`--no-extras` skips them, `--workload X` makes X the headline instead):
+  "ensemble24"    BASELINE config[3]'s advection component, STRONG scaling: 24 BPS-perturbed
+                  members x 12 single-step extrapolator calls (nowcasts/utils.py:440-458), members
+                  round-robin over the GPUs, motion field estimated on rank 0, ONE NCCL broadcast
+                  of it.  At N > 1 the N = 1 shape is also timed (rank 0 alone) -> speed-up.
+  "composite4096" BASELINE config[4], STRONG scaling: one 4096^2 composite, LK + 24 leadtimes,
+                  output row bands over the GPUs, NCCL all-gather of the motion-field bands.
 
 value  : inputs resident in HBM, device time by CUDA events, L2 flushed between steps.
 e2e    : the same step through the public NumPy API with pinned HOST buffers, H2D and
          D2H copies inside the timed region.
 roofline: the semi-Lagrangian trajectory kernel (sl_multistep_kernel), algorithmic
-         bytes per launch / CUDA-event time of that launch, vs MEASURED_PEAKS.json.
+         bytes per launch / CUDA-event time of that launch, vs MEASURED_PEAKS.json; a second
+         entry rates the same launch against the FP64 pipe (what actually bounds it).
+parity : before the line is printed, one step's results are compared with the CPU oracle
+         (dense field <= 1e-12 everywhere, extrapolated fields bit-identical); a mismatch raises.
 cpu_baseline: the CPU oracle (port of the reference path) on the same workload.
 """
 import argparse
@@ -35,22 +45,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-M = N_ = 2048
-T_LEAD = 12
-METRIC = "Mpix/s advected (2048^2 frame, 12 leadtimes)"
 UNIT = "Mpix/s"
-MOTION = "lk"
-SCALING = "weak"
-MEMBERS = 0
 
-# BASELINE.json configs.  The default (config[1]) is what `metric` is quoted on; the others are
-# optional extra measurements (python bench.py --workload ...).
+# BASELINE.json configs.  The default (config[1]) is what `metric` is quoted on.
 WORKLOADS = {
-    "lk_sl12_2048": dict(m=2048, n=2048, T=12, motion="lk", scaling="weak",
+    "lk_sl12_2048": dict(m=2048, n=2048, T=12, motion="lk", scaling="weak", members=0,
                          metric="Mpix/s advected (2048^2 frame, 12 leadtimes)"),
-    "vet_sl12_2048": dict(m=2048, n=2048, T=12, motion="vet", scaling="weak",
+    "vet_sl12_2048": dict(m=2048, n=2048, T=12, motion="vet", scaling="weak", members=0,
                           metric="Mpix/s advected (2048^2 frame, 12 leadtimes, VET motion)"),
-    "composite4096": dict(m=4096, n=4096, T=24, motion="lk", scaling="strong",
+    "composite4096": dict(m=4096, n=4096, T=24, motion="lk", scaling="strong", members=0,
                           metric="Mpix/s advected (4096^2 composite, 24 leadtimes, row bands over GPUs)"),
     # config[3]'s advection component: the call shape of nowcasts/utils.py:441-458 -- every
     # member has its own (perturbed) velocity, precipitation field and carried displacement,
@@ -58,14 +61,23 @@ WORKLOADS = {
     "ensemble24": dict(m=2048, n=2048, T=12, motion="lk", scaling="strong", members=24,
                        metric="Mpix/s advected (24-member ensemble, 2048^2, 12 single-step calls per member)"),
 }
+EXTRAS = ("ensemble24", "composite4096")
+
+# module-level view of the selected headline workload (tests/test_bench_host.py reads these)
+M = N_ = 2048
+T_LEAD = 12
+METRIC = WORKLOADS["lk_sl12_2048"]["metric"]
+MOTION = "lk"
+SCALING = "weak"
+MEMBERS = 0
 
 
 def set_workload(name):
-    global M, N_, T_LEAD, METRIC, MOTION, SCALING
+    global M, N_, T_LEAD, METRIC, MOTION, SCALING, MEMBERS
     w = WORKLOADS[name]
-    M, N_, T_LEAD, METRIC, MOTION, SCALING = w["m"], w["n"], w["T"], w["metric"], w["motion"], w["scaling"]
-    global MEMBERS
-    MEMBERS = w.get("members", 0)
+    M, N_, T_LEAD, METRIC, MOTION, SCALING, MEMBERS = (w["m"], w["n"], w["T"], w["metric"], w["motion"],
+                                                       w["scaling"], w["members"])
+    return dict(w, name=name)
 
 
 def have_lk():
@@ -76,28 +88,34 @@ def have_lk():
         return False
 
 
-def workload_name(lk):
-    mot = {"lk": "lk_dense", "vet": "vet"}[MOTION] if lk else "given_field"
-    if MEMBERS:
-        return f"{mot}+semilagrangian_{MEMBERS}members_x{T_LEAD}single_steps_{M}x{N_}"
-    return f"{mot}+semilagrangian_T{T_LEAD}_{M}x{N_}" + ("_rowbands" if SCALING == "strong" else "")
+def workload_name(lk=True, w=None):
+    w = w or dict(m=M, n=N_, T=T_LEAD, motion=MOTION, scaling=SCALING, members=MEMBERS)
+    mot = {"lk": "lk_dense", "vet": "vet"}[w["motion"]] if lk else "given_field"
+    if w["members"]:
+        return f"{mot}+semilagrangian_{w['members']}members_x{w['T']}single_steps_{w['m']}x{w['n']}"
+    return f"{mot}+semilagrangian_T{w['T']}_{w['m']}x{w['n']}" + ("_rowbands" if w["scaling"] == "strong" else "")
 
 
-def make_inputs(seed, lk):
+def config_of(w):
+    """Identical for both arms (`--impl ours` / `--impl reference`)."""
+    return {"workload": workload_name(True, w), "frame": [w["m"], w["n"]], "leadtimes": w["T"]}
+
+
+def make_inputs(w, seed):
     """frames: float64 (2,m,n) for the motion estimator (as pysteps importers deliver them);
     precip: the last frame as float32 (the synthetic data are float32-exact; a float32 array
     keeps the reference's float64 arithmetic and halves the output volume);
     V: synthetic float32 advection field, used only when the LK stage is not built."""
     from pysteps_b200 import _synthetic as syn
-    frames = syn.rain_frames(M, N_, 2, seed)
-    V = syn.velocity_field(M, N_, seed).astype(np.float32)
+    frames = syn.rain_frames(w["m"], w["n"], 2, seed)
+    V = syn.velocity_field(w["m"], w["n"], seed).astype(np.float32)
     return frames, frames[-1].astype(np.float32), V
 
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
     """nvidia-smi in loop mode (-lms 200, the profiling recipe's clocks line) from the warm-up to the
-    end of the end-to-end leg.  The first sample (taken before any load) is dropped."""
+    end of the timed steps.  The first sample (taken before any load) is dropped."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -160,14 +178,16 @@ def stage_rooflines(trace_ms, steps, m, n, peak_gbs, sl_bytes):
     px = m * n
     table = {
         "b200_idw_fill": (16 * px, "alu/latency: exhaustive-in-tile k-NN with register-resident sorted lists"),
-        "b200_sl_extrapolate_rows": (sl_bytes, "L1 wavefronts + FP64 pipe (reference-order float64 trajectories)"),
+        "b200_sl_extrapolate_rows": (sl_bytes, "FP64 pipe + L1 wavefronts + issue (reference-order float64 trajectories)"),
         "b200_min_eig": (5 * px, "latency: one sequential FP64 running sum per column (OpenCV-exact box filter)"),
         "b200_quantise_u8": (10 * px, "hbm/l2 streaming"),
         "b200_mask_invalid": (9 * px, "hbm streaming + reduction"),
         "b200_morph_opening": (17 * px, "hbm/l2 streaming stencil"),
         "b200_masked_minmax": (9 * px, "hbm streaming reduction"),
+        "b200_lk_frontend": (26 * px, "hbm streaming (fused mask + min/max, opening + both quantisations)"),
         "b200_lk_track": (None, "latency: ordered float32 window sums, one CTA per feature"),
         "b200_good_features": (None, "latency: sort + ordered greedy selection"),
+        "b200_detect_outliers": (None, "latency: cKDTree build (one CTA) + one best-first query per vector"),
         "b200_bps_perturb_velocity": (32 * px, "hbm streaming"),
     }
     out = []
@@ -187,93 +207,99 @@ def stage_rooflines(trace_ms, steps, m, n, peak_gbs, sl_bytes):
 
 
 # ----------------------------------------------------------------------------- CPU legs
-def cpu_step(frames, precip, V, lk):
-    """The oracle port of one step on host cores."""
+def host_threads():
+    """All host cores for the CPU legs, whatever the launcher exported (torchrun sets
+    OMP_NUM_THREADS=1)."""
+    import oracle
+    want = int(os.environ.get("BENCH_CPU_THREADS", "0")) or (os.cpu_count() or 1)
+    return oracle.set_num_threads(want)
+
+
+def cpu_step(w, frames, precip, V, lk):
+    """The oracle port of one step on host cores; returns seconds of the WHOLE step (ensemble:
+    motion + members x the one member that is run).  The k-NN stages run the exhaustive
+    lower-index scan (OpenMP C, the faster of the oracle's two modes -- a tougher baseline than
+    the reference's single-threaded cKDTree queries)."""
+    from oracle import lucaskanade as ora_lk
     from oracle import semilagrangian as ora
-    if lk and MOTION == "vet":
+    t0 = time.perf_counter()
+    if lk and w["motion"] == "vet":
         from oracle import vet as ora_vet
         V = ora_vet.vet(frames, verbose=False)
     elif lk:
-        from oracle import lucaskanade as ora_lk
-        V = ora_lk.dense_lucaskanade(frames)
-    if MEMBERS:
+        with ora_lk.knn_mode("lower_index"):
+            V = ora_lk.dense_lucaskanade(frames)
+    if w["members"]:
         # bounded sample: ONE member of the ensemble (the members are independent and identical
-        # in cost); the caller extrapolates to MEMBERS members
+        # in cost), extrapolated to all of them
         from oracle import noise_motion as ora_bps
         t1 = time.perf_counter()
         pert = ora_bps.initialize_bps(V, 1.0, 5.0, randstate=np.random.RandomState(1000))
-        disp, res = None, None
-        for t in range(T_LEAD):
+        disp = None
+        for t in range(w["T"]):
             Vm = ora_bps.perturbed_velocity(V, pert, (t + 1) * 5.0)
-            res, disp = ora.extrapolate(precip, Vm, [1.0], displacement_prev=disp, return_displacement=True)
-        return res, time.perf_counter() - t1
-    return ora.extrapolate(precip, V, T_LEAD)
+            _, disp = ora.extrapolate(precip, Vm, [1.0], displacement_prev=disp, return_displacement=True)
+        member = time.perf_counter() - t1
+        return (t1 - t0) + w["members"] * member
+    ora.extrapolate(precip, V, w["T"])
+    return time.perf_counter() - t0
 
 
-def _timed_cpu_step(frames, precip, V, lk):
-    """seconds of one whole step on the host (ensemble: motion + MEMBERS x the sampled member)"""
-    t0 = time.perf_counter()
-    r = cpu_step(frames, precip, V, lk)
-    dt = time.perf_counter() - t0
-    if MEMBERS:
-        member = r[1]
-        return (dt - member) + MEMBERS * member
-    return dt
-
-
-def cpu_baseline(frames, precip, V, lk, reps=1):
-    import oracle
-    best = None
-    for _ in range(reps):
-        dt = _timed_cpu_step(frames, precip, V, lk)
-        best = dt if best is None else min(best, dt)
-    return {"value": (MEMBERS or 1) * T_LEAD * M * N_ / best / 1e6, "unit": UNIT, "cores": oracle.num_threads(),
+def cpu_baseline(w, frames, precip, V, lk, reps=2):
+    threads = host_threads()
+    times = [cpu_step(w, frames, precip, V, lk) for _ in range(reps)]
+    best = min(times)
+    return {"value": (w["members"] or 1) * w["T"] * w["m"] * w["n"] / best / 1e6, "unit": UNIT, "cores": threads,
             "kind": "port",
-            "sample": f"{reps} full step(s) of {workload_name(lk)} (oracle C/NumPy port, "
-                      f"OpenMP {oracle.num_threads()} threads), best of {reps}; {best:.2f} s"
-                      + (f" (1 of {MEMBERS} members run, scaled)" if MEMBERS else "")}
+            "sample": f"{reps} full step(s) of {workload_name(lk, w)} (oracle C/NumPy port, "
+                      f"OpenMP {threads} threads, exhaustive k-NN mode), best of {reps}: "
+                      + " / ".join(f"{t:.2f}" for t in times) + " s"
+                      + (f" (1 of {w['members']} members run, scaled)" if w["members"] else "")}
 
 
-def run_reference(args):
+def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     lk = have_lk_oracle()
-    frames, precip, V = make_inputs(0, lk)
-    import oracle
+    frames, precip, V = make_inputs(w, 0)
+    threads = host_threads()
+    small = (slice(None), slice(0, 256), slice(0, 256))
     for _ in range(args.warmup):
-        cpu_step(np.ascontiguousarray(frames[:, :256, :256]), np.ascontiguousarray(precip[:256, :256]),
-                 np.ascontiguousarray(V[:, :256, :256]), lk)
+        cpu_step(w, np.ascontiguousarray(frames[small]), np.ascontiguousarray(precip[small[1:]]),
+                 np.ascontiguousarray(V[small]), lk)
     # Every step is a bounded sample of the workload: the full frame when the host is fast enough
-    # for the whole run to end within a few minutes (64 cores: 2.5 s per step), else a centred
-    # crop sized from the first step's time; the metric is per advected pixel either way.
+    # for the whole run to end within a few minutes (64 cores: ~2.5 s per step), else a centred
+    # crop sized from the first step's time (stated in `sample`); the metric is per advected pixel.
     budget_s = float(os.environ.get("BENCH_REFERENCE_BUDGET_S", "240"))
-    dt = _timed_cpu_step(frames, precip, V, lk)
-    pixels = M * N_
-    sample = f"full {M}x{N_} frame"
-    side_m, side_n = M, N_
+    dt = cpu_step(w, frames, precip, V, lk)
+    m, n = w["m"], w["n"]
+    pixels = m * n
+    sample = f"every step on the full {m}x{n} frame"
+    side_m, side_n = m, n
     if dt * args.steps > budget_s and args.steps > 1:
         frac = max((budget_s - dt) / (dt * (args.steps - 1)), 1.0 / 64.0)
-        side_m = max(256, int(M * frac ** 0.5) // 32 * 32)
-        side_n = max(256, int(N_ * frac ** 0.5) // 32 * 32)
-        r0, c0 = (M - side_m) // 2, (N_ - side_n) // 2
+        side_m = max(256, int(m * frac ** 0.5) // 32 * 32)
+        side_n = max(256, int(n * frac ** 0.5) // 32 * 32)
+        r0, c0 = (m - side_m) // 2, (n - side_n) // 2
         frames = np.ascontiguousarray(frames[:, r0:r0 + side_m, c0:c0 + side_n])
         precip = np.ascontiguousarray(precip[r0:r0 + side_m, c0:c0 + side_n])
         V = np.ascontiguousarray(V[:, r0:r0 + side_m, c0:c0 + side_n])
-        sample = f"first step on the full frame, the others on a centred {side_m}x{side_n} crop"
+        sample = (f"first step on the full frame ({dt:.1f} s), the other {args.steps - 1} on a centred "
+                  f"{side_m}x{side_n} crop to stay within {budget_s:.0f} s")
     for _ in range(args.steps - 1):
-        dt += _timed_cpu_step(frames, precip, V, lk)
+        dt += cpu_step(w, frames, precip, V, lk)
         pixels += side_m * side_n
-    val = (MEMBERS or 1) * T_LEAD * pixels / dt / 1e6
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+    val = (w["members"] or 1) * w["T"] * pixels / dt / 1e6
+    line = {"impl": "reference", "metric": w["metric"], "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-            "higher_is_better": True, "scaling": SCALING, "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(lk), "frame": [M, N_], "leadtimes": T_LEAD},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": oracle.num_threads(),
-                             "kind": "port",
+            "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": config_of(w),
+            "note": "host throughput: N independent nowcasts take N times as long on the same cores, so the "
+                    "Mpix/s of this arm is the same at every --gpus N",
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"{args.steps} step(s), {sample}; oracle port of the reference "
-                                       f"path, OpenMP {oracle.num_threads()} threads"},
+                                       f"path, OpenMP {threads} threads (set explicitly), exhaustive k-NN mode"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
@@ -288,266 +314,411 @@ def have_lk_oracle():
 
 
 # ----------------------------------------------------------------------------- GPU arm
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+class Bench:
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        import pysteps_b200
+        from pysteps_b200 import _lib, _shard
+        self.pkg, self.lib, self.shard = pysteps_b200, _lib, _shard
+        self.extrap = pysteps_b200.extrapolation.get_method("semilagrangian")
+        self.lk = have_lk()
+        self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    def motion(self, name):
+        if not self.lk:
+            return None
+        f = self.pkg.motion.get_method(name)
+        if name == "vet":
+            torch = self.torch
+            return lambda fr, **kw: f(fr.cpu().numpy() if torch.is_tensor(fr) else fr, verbose=False)
+        return f
 
-    import pysteps_b200
-    from pysteps_b200 import _lib, _shard
-    extrap = pysteps_b200.extrapolation.get_method("semilagrangian")
-    lk = have_lk()
-    motion = None
-    if lk:
-        from pysteps_b200 import motion as b200_motion
-        motion = b200_motion.get_method(MOTION)
-        if MOTION == "vet":
-            _vet = motion
-            motion = lambda fr: _vet(fr.cpu().numpy() if torch.is_tensor(fr) else fr, verbose=False)  # noqa: E731
+    def pin(self, a):
+        return self.torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
 
-    frames_h, precip_h, V_h = make_inputs(rank, lk)
-    # pinned host buffers for the e2e leg
-    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()  # noqa: E731
-    frames_h = pin(frames_h)
-    precip_h = pin(precip_h)
-    V_h = pin(V_h)
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def all_agree(self, flag):
+        """rank 0 decides, so every rank runs the same number of steps"""
+        if self.world == 1:
+            return bool(flag)
+        t = self.torch.tensor([int(flag)], device="cuda")
+        self.dist.broadcast(t, src=0)
+        return bool(t.item())
+
+    def time_device(self, step, steps, warmup, min_warm_s=0.0, marks=None):
+        """W >= 3 untimed steps (stretched to min_warm_s of the same load for the clock sampler),
+        then `steps` steps, each bracketed by barrier + synchronize and CUDA events, L2 flushed in
+        between (outside the events).  Returns (ms summed over steps [max over ranks], trace,
+        launches, per-phase ms when the step records `marks`)."""
+        torch = self.torch
+        t_w, n_w = time.perf_counter(), 0
+        while True:
+            step()
+            torch.cuda.synchronize()
+            n_w += 1
+            if self.all_agree(n_w >= warmup and (n_w >= 400 or time.perf_counter() - t_w >= min_warm_s)):
+                break
+        self.barrier()
+        launches0 = self.lib.load().b200_launch_count()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        phase = []
+        with self.lib.Trace() as trace:
+            for s, e in ev:
+                self.flush.fill_(1)
+                self.barrier()
+                s.record()
+                step()
+                e.record()
+                if marks is not None:
+                    phase.append(list(marks))
+            self.barrier()
+        launches = self.lib.load().b200_launch_count() - launches0
+        dev_ms = self.shard.max_over_ranks(sum(s.elapsed_time(e) for s, e in ev), device="cuda")
+        phases = None
+        if marks is not None and phase and len(phase[0]) >= 1:
+            # phase boundaries recorded by the step (events on the current stream)
+            acc = [0.0] * (len(phase[0]) + 1)
+            for (s, e), mk in zip(ev, phase):
+                pts = [s] + mk + [e]
+                for i in range(len(pts) - 1):
+                    acc[i] += pts[i].elapsed_time(pts[i + 1])
+            phases = [self.shard.max_over_ranks(a, device="cuda") / steps for a in acc]
+        return dev_ms, trace.summary(), launches, phases
+
+    def time_host(self, step, steps, warmup):
+        # the pinned host pool (torch's caching host allocator: one cudaHostAlloc per new block, tens
+        # of ms for a 200 MB result) reaches its steady state after a few calls
+        out = None
+        for _ in range(max(4, warmup)):
+            out = step()
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            out = step()
+        self.barrier()
+        return self.shard.max_over_ranks(time.perf_counter() - t0, device="cuda"), out
+
+
+def build_standard(b, w, active=None):
+    """config[1] / [2] / [4]: motion field + T-leadtime extrapolation.  Returns step functions and
+    byte counts; `active` = ranks taking part (None: all)."""
+    torch, dist, world, rank = b.torch, b.dist, b.world, b.rank
+    m, n, T = w["m"], w["n"], w["T"]
+    frames_h, precip_h, V_h = (b.pin(a) for a in make_inputs(w, rank))
     frames_d = torch.from_numpy(frames_h).cuda()
     precip_d = torch.from_numpy(precip_h).cuda()
     V_d = torch.from_numpy(V_h).cuda()
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-
-    # strong scaling (one composite): every rank owns a band of output rows, inputs replicated
-    band = _shard.row_band(M, world, rank) if SCALING == "strong" else None
+    motion = b.motion(w["motion"])
+    lk = motion is not None
+    strong = w["scaling"] == "strong"
+    band = b.shard.row_band(m, world, rank) if strong else None
     ekw = {} if band is None else {"b200_rows": band}
+    extrap = b.extrap
 
     def step_device():
-        """inputs resident in HBM; results stay in HBM."""
-        if lk and band is not None and world > 1 and MOTION == "lk":
+        if lk and strong and world > 1 and w["motion"] == "lk":
             # one composite over GPUs: the sparse LK stages are deterministic and replicated, every
             # rank fills its band of the motion field, the bands are all-gathered (the exchange
             # step of this path), and every rank advects its band of output rows
             Vband = motion(frames_d, interp_kwargs={"b200_rows": band})
-            Vd = _shard.gather_row_bands(Vband, M, world, rank)
-            return extrap(precip_d, Vd, T_LEAD, **ekw)
-        if lk and SCALING == "weak":
-            # independent nowcasts: every rank estimates the motion of ITS frames and advects ITS
-            # field -- no collective on the data path
+            Vd = b.shard.gather_row_bands(Vband, m, world, rank)
+            return extrap(precip_d, Vd, T, **ekw)
+        if lk:
             Vd = motion(frames_d)
             if not torch.is_tensor(Vd):
                 Vd = torch.from_numpy(np.ascontiguousarray(Vd)).cuda()
-            return extrap(precip_d, Vd, T_LEAD)
-        if lk:
-            if rank == 0:
-                Vd = motion(frames_d)
-                if not torch.is_tensor(Vd):
-                    Vd = torch.from_numpy(np.ascontiguousarray(Vd)).cuda()
-            else:
-                Vd = torch.empty((2, M, N_), dtype=torch.float64, device="cuda")
-        else:
-            Vd = V_d
-        Vd = _shard.broadcast_field(Vd, src=0)  # the only collective (NCCL over NVLink)
-        return extrap(precip_d, Vd, T_LEAD, **ekw)
-
-    if MEMBERS:
-        from pysteps_b200 import noise as b200_noise
-        bps_init, bps_gen = b200_noise.get_method("bps")
-        mine = _shard.member_indices(MEMBERS, world, rank)
-        # per-member precipitation fields (synthetic); the velocity perturbations are the BPS
-        # perturbator's (noise/motion.py), one seeded RandomState per member as in
-        # nowcasts/steps.py:915-926, evaluated inside the advection call (fused kernel)
-        member_precip = [precip_d * (1.0 + 0.01 * i) for i in mine]
-        member_precip_h = [pin(precip_h * np.float32(1.0 + 0.01 * i)) for i in mine]
-        KMPP, DT_MIN = 1.0, 5.0
-
-        def member_loop(V, fields, resident):
-            """nowcasts/utils.py:440-458: T lead times x this rank's members, each a single-step
-            call with a freshly perturbed motion field, carrying its own displacement."""
-            perts = [bps_init(V, 1.0 / KMPP, DT_MIN, randstate=np.random.RandomState(1000 + i)) for i in mine]
-            disp = [None] * len(mine)
-            last = None
-            for t in range(T_LEAD):
-                for j in range(len(mine)):
-                    Vm = V + bps_gen(perts[j], (t + 1) * DT_MIN)
-                    last, disp[j] = extrap(fields[j], Vm, [1.0], displacement_prev=disp[j],
-                                           return_displacement=True, b200_resident=resident)
-            return last
-
-        def step_device():  # noqa: F811
-            """rank 0: motion field; broadcast; member loop on device-resident fields."""
-            if rank == 0:
-                Vd = motion(frames_d)
-            else:
-                Vd = torch.empty((2, M, N_), dtype=torch.float64, device="cuda")
-            Vd = _shard.broadcast_field(Vd, src=0)
-            return member_loop(Vd, member_precip, False)
+            return extrap(precip_d, Vd, T, **ekw)
+        return extrap(precip_d, V_d, T, **ekw)
 
     def step_host():
         """public NumPy API: H2D of inputs and D2H of the result inside."""
-        if MEMBERS:
-            # NumPy API as nowcast_main_loop uses it: the motion field is uploaded once per
-            # forecast, every member-step uploads its precipitation field and downloads the
-            # advected one; perturbed fields and displacements never leave the device
-            Vh = motion(frames_h) if rank == 0 else None
-            if world > 1:
-                Vd = torch.from_numpy(Vh).cuda() if rank == 0 else \
-                    torch.empty((2, M, N_), dtype=torch.float64, device="cuda")
-                dist.broadcast(Vd, src=0)
-                Vh = Vd.cpu().numpy()
-            return member_loop(Vh, member_precip_h, True)
-        if lk and band is not None and world > 1 and MOTION == "lk":
+        if lk and strong and world > 1 and w["motion"] == "lk":
             Vband = motion(frames_h, interp_kwargs={"b200_rows": band})  # NumPy band
-            Vh = _shard.gather_row_bands(torch.from_numpy(Vband).cuda(), M, world, rank).cpu().numpy()
-        elif lk and SCALING == "weak":
-            Vh = motion(frames_h)  # NumPy (2,m,n) float64, as pysteps returns; independent per rank
+            Vh = b.shard.gather_row_bands(torch.from_numpy(Vband).cuda(), m, world, rank).cpu().numpy()
         elif lk:
-            Vh = motion(frames_h) if rank == 0 else None
-            if world > 1:
-                Vd = torch.from_numpy(Vh).cuda() if rank == 0 else \
-                    torch.empty((2, M, N_), dtype=torch.float64, device="cuda")
-                dist.broadcast(Vd, src=0)
-                Vh = Vd.cpu().numpy()
+            Vh = motion(frames_h)  # NumPy (2,m,n) float64, as pysteps returns it
         else:
             Vh = V_h
-        return extrap(precip_h, Vh, T_LEAD, **ekw)
+        return extrap(precip_h, Vh, T, **ekw)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    rows_here = m if band is None else band[1] - band[0]
+    # LK: frames up, field down, field up again for the extrapolator (the plugin API is NumPy;
+    # the second upload is served from the device copy the motion call left behind, see
+    # pysteps_b200/_device.py: recent_results)
+    h2d = precip_h.nbytes + (frames_h.nbytes if lk else V_h.nbytes)
+    d2h = rows_here * n * 4 * T + (2 * (rows_here if (strong and world > 1) else m) * n * 8 if lk else 0)
+    info = dict(h2d=h2d, d2h=d2h, rows_here=rows_here, lk=lk, inputs=(frames_h, precip_h, V_h),
+                dev_inputs=(frames_d, precip_d, V_d), nfields=(world if w["scaling"] == "weak" else 1))
+    return step_device, step_host, info
 
-    # ---- device-resident timing ------------------------------------------------------
-    # The clock sampler (nvidia-smi -lms 200, one per job) spans the warm-up and the timed steps and
-    # is stopped before the end-to-end leg: every poll holds a driver lock that launches and copies
-    # also take (a 20 ms period was measured to slow a 6 ms step by 3 ms, a 200 ms period the
-    # 10.7 ms end-to-end step by 3.7 ms).  The warm-up is stretched to >= 0.5 s of the same load
-    # so that the median is over several samples under load although the timed region is short.
-    clocks = ClockSampler(local, enabled=(rank == 0))
-    clocks.__enter__()
-    t_w, n_w = time.perf_counter(), 0
-    while True:
-        step_device()
-        torch.cuda.synchronize()
-        n_w += 1
-        done = n_w >= args.warmup and (n_w >= 400 or time.perf_counter() - t_w >= 0.5)
-        if world > 1:  # rank 0 decides, so every rank runs the same number of steps
-            flag = torch.tensor([int(done)], device="cuda")
-            dist.broadcast(flag, src=0)
-            done = bool(flag.item())
-        if done:
-            break
-    barrier()
-    launches0 = _lib.load().b200_launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(args.steps)]
-    with _lib.Trace() as trace:
-        for s, e in ev:
-            flush.fill_(1)  # L2 flush between timed iterations (outside the events)
-            barrier()
-            s.record()
-            step_device()
-            e.record()
-        barrier()
-    clocks.__exit__(None, None, None)
-    launches = _lib.load().b200_launch_count() - launches0
-    dev_ms = sum(s.elapsed_time(e) for s, e in ev)
-    tr = trace.summary()
-    dev_ms = _shard.max_over_ranks(dev_ms, device="cuda")
-    nfields = world if SCALING == "weak" else 1
-    if MEMBERS:
-        nfields = MEMBERS
-    value = nfields * args.steps * T_LEAD * M * N_ / (dev_ms * 1e-3) / 1e6
 
-    # ---- end-to-end timing (host buffers) --------------------------------------------
-    # the pinned host pool (torch's caching host allocator: one cudaHostAlloc per new block, tens of
-    # ms for a 200 MB result) reaches its steady state after a few calls
-    for _ in range(max(6, args.warmup)):
-        step_host()
-    barrier()
+def build_ensemble(b, w, solo=False):
+    """config[3]'s advection component.  solo=True: the N = 1 shape inside an N > 1 job (rank 0
+    runs all members, the other ranks idle) -- the denominator of the speed-up."""
+    torch, dist, world, rank = b.torch, b.dist, b.world, b.rank
+    m, n, T, members = w["m"], w["n"], w["T"], w["members"]
+    frames_h, precip_h, _ = (b.pin(a) for a in make_inputs(w, 0))
+    frames_d = torch.from_numpy(frames_h).cuda()
+    precip_d = torch.from_numpy(precip_h).cuda()
+    motion = b.motion("lk")
+    bps_init, bps_gen = b.pkg.noise.get_method("bps")
+    eff_world = 1 if solo else world
+    mine = b.shard.member_indices(members, eff_world, rank) if (not solo or rank == 0) else []
+    # per-member precipitation fields (synthetic); the velocity perturbations are the BPS
+    # perturbator's (noise/motion.py), one seeded RandomState per member as in
+    # nowcasts/steps.py:915-926, evaluated inside the advection call (fused kernel)
+    member_precip = [precip_d * (1.0 + 0.01 * i) for i in mine]
+    member_precip_h = [b.pin(precip_h * np.float32(1.0 + 0.01 * i)) for i in mine]
+    KMPP, DT_MIN = 1.0, 5.0
+    extrap = b.extrap
+    marks = []
+
+    def member_loop(V, fields, resident):
+        """nowcasts/utils.py:440-458: T lead times x this rank's members, each a single-step
+        call with a freshly perturbed motion field, carrying its own displacement."""
+        perts = [bps_init(V, 1.0 / KMPP, DT_MIN, randstate=np.random.RandomState(1000 + i)) for i in mine]
+        disp = [None] * len(mine)
+        last = None
+        for t in range(T):
+            for j in range(len(mine)):
+                Vm = V + bps_gen(perts[j], (t + 1) * DT_MIN)
+                last, disp[j] = extrap(fields[j], Vm, [1.0], displacement_prev=disp[j],
+                                       return_displacement=True, b200_resident=resident)
+        return last
+
+    def step_device():
+        """rank 0: motion field; broadcast; member loop on device-resident fields."""
+        del marks[:]
+        if solo and rank != 0:  # idle rank of the N = 1 shape: same phase marks, no work
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append(ev)
+            return None
+        if rank == 0:
+            Vd = motion(frames_d)
+        else:
+            Vd = torch.empty((2, m, n), dtype=torch.float64, device="cuda")
+        if not solo:
+            Vd = b.shard.broadcast_field(Vd, src=0)  # the only collective (NCCL over NVLink)
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        marks.append(ev)
+        return member_loop(Vd, member_precip, False)
+
+    def step_host():
+        # NumPy API as nowcast_main_loop uses it: the motion field is uploaded once per
+        # forecast, every member-step uploads its precipitation field and downloads the
+        # advected one; perturbed fields and displacements never leave the device
+        if solo and rank != 0:
+            return None
+        Vh = motion(frames_h) if rank == 0 else None
+        if world > 1 and not solo:
+            Vd = torch.from_numpy(Vh).cuda() if rank == 0 else \
+                torch.empty((2, m, n), dtype=torch.float64, device="cuda")
+            dist.broadcast(Vd, src=0)
+            Vh = Vd.cpu().numpy()
+        return member_loop(Vh, member_precip_h, True)
+
+    # per rank: frames + field once, one precipitation field up / one down per member-step
+    h2d = frames_h.nbytes + 2 * m * n * 8 + len(mine) * T * precip_h.nbytes
+    d2h = 2 * m * n * 8 + len(mine) * T * precip_h.nbytes
+    info = dict(h2d=h2d, d2h=d2h, rows_here=m, lk=True, nfields=members, marks=marks, members_here=len(mine))
+    return step_device, step_host, info
+
+
+def parity_check(b, w):
+    """One step of the headline workload, CUDA vs the CPU oracle on the same inputs (rank 0's):
+    dense motion field <= 1e-12 at every pixel against the oracle in the reference's k-NN order,
+    sparse vectors and the T extrapolated fields bit-identical.  Raises on a mismatch."""
+    torch = b.torch
+    from oracle import lucaskanade as ora_lk
+    from oracle import semilagrangian as ora_sl
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        out = step_host()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    if os.environ.get("BENCH_E2E_BREAKDOWN") and lk and not MEMBERS:  # diagnostic only
-        tm = te = 0.0
-        for _ in range(args.steps):
-            a = time.perf_counter(); Vx = motion(frames_h); b = time.perf_counter()
-            out = extrap(precip_h, Vx, T_LEAD); c = time.perf_counter()
-            tm += b - a; te += c - b
-        print(f"e2e breakdown: loop {1e3 * e2e_s / args.steps:.2f} ms/step; motion {1e3 * tm / args.steps:.2f} "
-              f"extrap {1e3 * te / args.steps:.2f}", file=sys.stderr)
-    e2e_s = _shard.max_over_ranks(e2e_s, device="cuda")
-    e2e_val = nfields * args.steps * T_LEAD * M * N_ / e2e_s / 1e6
-    # LK: frames up, field down, field up again for the extrapolator (plugin API is NumPy)
-    h2d = precip_h.nbytes + (frames_h.nbytes + 2 * M * N_ * 8 if lk else V_h.nbytes)
-    d2h = out.nbytes + (2 * M * N_ * 8 if lk else 0)
-    if MEMBERS:  # per rank: frames + field once, one precipitation field up / one down per member-step
-        h2d = frames_h.nbytes + 2 * M * N_ * 8 + len(mine) * T_LEAD * precip_h.nbytes
-        d2h = 2 * M * N_ * 8 + len(mine) * T_LEAD * precip_h.nbytes
+    frames, precip, Vsyn = make_inputs(w, 0)
+    res = {"checked": workload_name(True, w)}
+    V = Vsyn
+    if b.lk and w["motion"] == "lk":
+        lk = b.motion("lk")
+        xy, uv = lk(frames, dense=False)
+        oxy, ouv = ora_lk.dense_lucaskanade(frames, dense=False)
+        if not (np.array_equal(xy, oxy) and np.array_equal(uv, ouv)):
+            raise AssertionError("bench parity: sparse Lucas-Kanade vectors differ from the oracle")
+        V = lk(frames)
+        Vo = ora_lk.dense_lucaskanade(frames)
+        d = float(np.abs(V - Vo).max())
+        res.update(sparse_vectors=int(len(xy)), sparse_bit_identical=True, dense_field_max_abs_diff=d,
+                   dense_field_tolerance=1e-12)
+        if not d <= 1e-12:
+            raise AssertionError(f"bench parity: dense motion field differs from the oracle by {d:.3e}")
+    got = b.extrap(precip, V, w["T"])
+    want = ora_sl.extrapolate(precip, V, w["T"])
+    same = np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(got[~np.isnan(got)], want[~np.isnan(want)])
+    res.update(extrapolation_bit_identical=bool(same), seconds=round(time.perf_counter() - t0, 1))
+    if not same:
+        raise AssertionError("bench parity: extrapolated fields are not bit-identical to the oracle")
+    return res
 
-    if rank == 0:
-        # ---- roofline of the trajectory kernel (this run's launches) -----------------
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650"
-        k_ms = tr.get("b200_sl_extrapolate_rows", []) or tr.get("b200_sl_extrapolate", [])
-        k_avg = sum(k_ms) / len(k_ms) if k_ms else float("nan")
-        vbytes = 8 if lk else 4  # LK returns float64 fields, synthetic V is float32
-        rows_here = M if band is None else band[1] - band[0]
-        alg_bytes = M * N_ * (2 * vbytes + 4) + rows_here * N_ * 4 * T_LEAD
-        if MEMBERS:  # single-step member calls: V 16 + precip 4 + displacement in/out 32 + out 4 B per pixel
-            alg_bytes = M * N_ * 56
-        achieved = alg_bytes / (k_avg * 1e-3) / 1e9
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "sl_traffic.json")))["bytes_per_launch"]
-        except Exception:
-            pass
-        roofline = {"kernel": "sl_multistep_kernel", "bound": "hbm", "achieved": achieved,
-                    "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                    "peak_source": peak_src, "kernel_ms": k_avg,
-                    "algorithmic_bytes_per_launch": alg_bytes}
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+# FP64 pipe of sm_100a: 64 results per SM per clock (B200: 40 TFLOP/s FP64 FMA = 20e12 instr/s over
+# 148 SMs at 1.965 GHz -> 68.8, i.e. 64/clk); instruction count per pixel-leadtime of
+# sl_multistep_kernel from its SASS (tools/sass_count.py, profiles/r02_sl_kernel.md)
+FP64_PER_CLK_SM = 64
+SL_FP64_INSTR_PER_PIXEL_LEADTIME = 89
+
+
+def measure(b, w, steps, warmup, clocks=None, solo=False):
+    """device-resident + end-to-end timing of one workload -> dict (rank 0) / None."""
+    if w["members"]:
+        step_device, step_host, info = build_ensemble(b, w, solo=solo)
+    else:
+        step_device, step_host, info = build_standard(b, w)
+    m, n, T = w["m"], w["n"], w["T"]
+    marks = info.get("marks")
+    if clocks is not None:
+        clocks.__enter__()
+    dev_ms, tr, launches, phases = b.time_device(step_device, steps, warmup, 0.5 if clocks is not None else 0.0, marks)
+    if clocks is not None:
+        clocks.__exit__(None, None, None)
+    nfields = info["nfields"]
+    value = nfields * steps * T * m * n / (dev_ms * 1e-3) / 1e6
+    e2e_s, out = b.time_host(step_host, steps, warmup)
+    e2e_val = nfields * steps * T * m * n / e2e_s / 1e6
+    if b.rank != 0:
+        return None
+    world = 1 if solo else b.world
+    blk = {"metric": w["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+           "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": w["scaling"],
+           "config": config_of(w),
+           "parallelism": (
+               f"{world} independent nowcast(s), one per GPU, no collective" if w["scaling"] == "weak" else
+               f"{w['members']} members round-robin over {world} GPU(s), NCCL broadcast of the motion field"
+               if w["members"] else
+               f"output row bands over {world} GPU(s), inputs replicated"
+               + (", NCCL all-gather of the motion-field bands" if world > 1 and w["motion"] == "lk" else "")),
+           "fields_per_gpu": 1 if w["scaling"] == "weak" else round(1.0 / world, 4),
+           "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(info["h2d"]),
+                   "d2h_bytes_per_step": int(info["d2h"]), "ms_per_step": 1e3 * e2e_s / steps},
+           "gpu_launches": int(launches), "_trace": tr, "_info": info}
+    if phases is not None and len(phases) == 2:
+        blk["motion_and_broadcast_ms"] = phases[0]
+        blk["member_loop_ms"] = phases[1]
+    return blk
+
+
+def roofline_of(b, w, blk, peaks):
+    tr, info = blk["_trace"], blk["_info"]
+    m, n, T = w["m"], w["n"], w["T"]
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650"
+    k_ms = tr.get("b200_sl_extrapolate_rows", []) or tr.get("b200_sl_extrapolate", [])
+    k_avg = sum(k_ms) / len(k_ms) if k_ms else float("nan")
+    vbytes = 8 if info["lk"] else 4  # LK returns float64 fields, synthetic V is float32
+    alg_bytes = m * n * (2 * vbytes + 4) + info["rows_here"] * n * 4 * T
+    pix_leadtimes = info["rows_here"] * n * T
+    if w["members"]:  # single-step member calls: V 16 + precip 4 + displacement in/out 32 + out 4 B per pixel
+        alg_bytes = m * n * 56
+        pix_leadtimes = m * n
+    achieved = alg_bytes / (k_avg * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "sl_traffic.json")))["bytes_per_launch"]
+    except Exception:
+        pass
+    sm_mhz = float(peaks.get("sm_max_mhz", 1965.0))
+    nsm = b.torch.cuda.get_device_properties(0).multi_processor_count
+    fp64_peak = FP64_PER_CLK_SM * nsm * sm_mhz * 1e6 / 1e9  # G instr/s
+    fp64_ach = SL_FP64_INSTR_PER_PIXEL_LEADTIME * pix_leadtimes * (2 if w["members"] else 1) / (k_avg * 1e-3) / 1e9
+    roofline = {"kernel": "sl_multistep_kernel", "bound": "hbm", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src, "kernel_ms": k_avg, "algorithmic_bytes_per_launch": alg_bytes}
+    roofline_fp64 = {"kernel": "sl_multistep_kernel", "bound": "fp64 pipe (what limits this kernel: the reference's "
+                     "float64 operation order is kept, ~%d FP64 instructions and 36 gathered taps per pixel-leadtime "
+                     "against 5 B of compulsory traffic)" % SL_FP64_INSTR_PER_PIXEL_LEADTIME,
+                     "achieved": fp64_ach, "peak": fp64_peak, "unit": "G FP64 instr/s", "frac": fp64_ach / fp64_peak,
+                     "peak_source": f"{FP64_PER_CLK_SM} FP64 results/clk/SM x {nsm} SMs x {sm_mhz:.0f} MHz",
+                     "kernel_ms": k_avg}
+    return roofline, roofline_fp64, peak, alg_bytes
+
+
+def public(blk):
+    return {k: v for k, v in blk.items() if not k.startswith("_")}
+
+
+def run_ours(args, w):
+    b = Bench()
+    peaks = load_peaks()
+    clocks = ClockSampler(b.local, enabled=(b.rank == 0))
+    head = measure(b, w, args.steps, args.warmup, clocks=clocks)
+    extras = {}
+    if not args.no_extras and args.workload == "lk_sl12_2048":
+        for name in EXTRAS:
+            we = dict(WORKLOADS[name], name=name)
+            es = max(3, min(args.steps, args.extra_steps))
+            blk = measure(b, we, es, 3)
+            solo = None
+            if b.world > 1 and we["members"]:
+                solo = measure(b, we, 2, 3, solo=True)
+            if b.rank == 0:
+                if solo is not None:
+                    blk["one_gpu_ms_per_step"] = solo["ms_per_step"]
+                    blk["speedup_vs_1gpu"] = solo["ms_per_step"] / blk["ms_per_step"]
+                    if "member_loop_ms" in solo and "member_loop_ms" in blk:
+                        blk["one_gpu_member_loop_ms"] = solo["member_loop_ms"]
+                        blk["advection_speedup_vs_1gpu"] = solo["member_loop_ms"] / blk["member_loop_ms"]
+                    blk["one_gpu_e2e_ms_per_step"] = solo["e2e"]["ms_per_step"]
+                    blk["e2e_speedup_vs_1gpu"] = solo["e2e"]["ms_per_step"] / blk["e2e"]["ms_per_step"]
+                r, r64, _, _ = roofline_of(b, we, blk, peaks)
+                blk["roofline"] = r
+                extras[name] = public(blk)
+    if b.rank == 0:
+        roofline, roofline_fp64, peak, alg_bytes = roofline_of(b, w, head, peaks)
+        tr = head["_trace"]
         stage_ms = {k: sum(v) / args.steps for k, v in tr.items()}
         try:
-            stages = stage_rooflines(tr, args.steps, M, N_, peak, alg_bytes)
+            stages = stage_rooflines(tr, args.steps, w["m"], w["n"], peak, alg_bytes)
         except Exception as exc:  # supplementary table only
             stages = [{"error": repr(exc)}]
+        parity = None if args.no_parity else parity_check(b, w)
         # the CPU leg is a property of the host, measured once: rank 0 of the single-GPU run only
-        cpu = cpu_baseline(frames_h, precip_h, V_h, have_lk_oracle()) if (not args.no_cpu and world == 1) else None
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
-                "higher_is_better": True, "scaling": SCALING, "vs_baseline": None,
-                "dtype": "f64 (trajectories, motion field, IDW); f32 precip in/out; u8/i16/f32 "
-                         "OpenCV-exact LK stages", "data": "synthetic",
-                "config": {"workload": workload_name(lk), "frame": [M, N_], "leadtimes": T_LEAD,
-                           "fields_per_gpu": 1 if SCALING == "weak" else round(1.0 / world, 4), "l2": "flushed between timed steps (256 MB fill)",
-                           "parallelism": (
-                               f"{world} independent nowcast(s), one per GPU, no collective" if SCALING == "weak" else
-                               f"{MEMBERS} members round-robin over {world} GPU(s), NCCL broadcast of the motion field"
-                               if MEMBERS else
-                               f"output row bands over {world} GPU(s), inputs replicated"
-                               + (", NCCL all-gather of the motion-field bands" if world > 1 and MOTION == "lk"
-                                  else ""))},
-                "clocks": clocks.summary(),
-                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                        "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / args.steps},
-                "gpu_launches": int(launches),
-                "roofline": roofline, "cpu_baseline": cpu, "stage_ms_per_step": stage_ms,
-                "stage_rooflines": stages}
+        fr, pr, Vh = head["_info"]["inputs"] if "inputs" in head["_info"] else make_inputs(w, 0)
+        cpu = cpu_baseline(w, np.asarray(fr), np.asarray(pr), np.asarray(Vh), have_lk_oracle()) \
+            if (not args.no_cpu and b.world == 1) else None
+        line = public(head)
+        line.update({"vs_baseline": None,
+                     "dtype": "f64 (trajectories, motion field, IDW); f32 precip in/out; u8/i16/f32 "
+                              "OpenCV-exact LK stages", "data": "synthetic",
+                     "l2": "flushed between timed steps (256 MB fill)",
+                     "clocks": clocks.summary(), "roofline": roofline, "roofline_fp64": roofline_fp64,
+                     "parity": parity, "cpu_baseline": cpu, "stage_ms_per_step": stage_ms,
+                     "stage_rooflines": stages})
+        line.update(extras)
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    else:
+        if not args.no_parity:
+            pass  # rank 0 checks; the others wait at the final barrier
+    b.barrier()
+    if b.world > 1:
+        b.dist.destroy_process_group()
     return 0
 
 
@@ -558,13 +729,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of one step")
+    ap.add_argument("--no-extras", action="store_true", help="headline workload only")
+    ap.add_argument("--extra-steps", type=int, default=5, help="timed steps of the ensemble24 / composite4096 blocks")
     ap.add_argument("--workload", default="lk_sl12_2048", choices=sorted(WORKLOADS))
     args = ap.parse_args()
-    set_workload(args.workload)
+    w = set_workload(args.workload)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
-        return run_reference(args)
-    return run_ours(args)
+        return run_reference(args, w)
+    return run_ours(args, w)
 
 
 if __name__ == "__main__":

@@ -247,15 +247,17 @@ int b200_lk_compact_tracks(const float *p0, const float *p1, const uint8_t *stat
                            int *pool_count, int pool_cap, void *stream);
 
 /* pysteps/utils/cleansing.py:124-249 detect_outliers(uv, thr, xy, k), multivariate local
- * branch: out[i] = 1 where the Mahalanobis distance to the k nearest vectors exceeds thr. */
+ * branch: out[i] = 1 where the Mahalanobis distance to the k nearest vectors exceeds thr.  The
+ * k+1 nearest vectors are taken in scipy.spatial.cKDTree's own order (cleansing.py:219-221), ties
+ * and coincident vectors included: the tree is built and queried on the device exactly as scipy
+ * does (csrc/knn.cu, knn_body.cuh) -- with integer corner coordinates that order decides tests. */
 int b200_detect_outliers(const double *uv, const double *xy, const int *n_dev, int n_cap,
                          double thr, int k, uint8_t *out, void *stream);
-/* The same test with the k+1 nearest vectors taken in scipy.spatial.cKDTree's own order, ties and
- * coincident vectors included (the tree is built and queried on the device exactly as scipy does,
- * csrc/knn_body.cuh): with integer corner coordinates that order decides outlier tests.  Reads one
- * int back (the node count) and synchronises the stream. */
-int b200_detect_outliers_ckdtree(const double *uv, const double *xy, const int *n_dev, int n_cap,
-                                 double thr, int k, uint8_t *out, void *stream);
+/* scipy.spatial.cKDTree(xy) (leafsize 16, median splits by std::nth_element) built on the device:
+ * tree_indices[n_cap] = tree.indices (the tree order of the points), *node_count = number of
+ * nodes; both device pointers.  Stage entry used by the parity tests of the build. */
+int b200_kdtree_build(const double *xy, const int *n_dev, int n_cap, int *tree_indices,
+                      int *node_count, void *stream);
 /* rows with drop == 0, order preserved */
 int b200_compact_rows(const double *xy, const double *uv, const uint8_t *drop, const int *n_dev,
                       int n_cap, double *out_xy, double *out_uv, int *out_count, void *stream);
@@ -265,7 +267,10 @@ int b200_decluster(const double *xy, const double *uv, const int *n_dev, int n_c
                    int min_samples, double *out_xy, double *out_uv, int *out_count, void *stream);
 
 /* pysteps/utils/interpolate.py:26-114 idwinterp2d: k-nearest inverse-distance weighting of
- * (npts, nvar) values onto the (ny, nx) grid -> out (nvar, ny, nx). k <= 32.
+ * (npts, nvar) values onto the (ny, nx) grid -> out (nvar, ny, nx). k <= 32.  Exhaustive
+ * tile-culled search; grid points whose k-th and (k+1)-th neighbours are exactly equidistant are
+ * recomputed from scipy.spatial.cKDTree's query order (tree built on a library-internal side
+ * stream), so the neighbour SET is the reference's everywhere (interpolate.py:78-81).
  * coords_on_16th_grid != 0 is the caller's promise that every vector and grid coordinate is
  * a multiple of 1/16 with magnitude < 2^14 (true for dense_lucaskanade: pixel grids and
  * medians of integer corners); it enables a faster, result-identical key packing. */
@@ -278,7 +283,7 @@ int b200_idw_fill(const double *xy, const double *vals, const int *npts_dev, int
  * as the reference does it (scipy.spatial.cKDTree's query order, numpy's pairwise sum of the
  * weights, values accumulated in neighbour order): equal to the reference at EVERY grid point to
  * the last bits (np.power vs pow), ties included; much slower than b200_idw_fill (a tree search
- * per grid point).  k <= 128.  Reads one int back and synchronises the stream. */
+ * per grid point; b200_idw_fill runs it only where the neighbour set depends on it).  k <= 128. */
 int b200_idw_fill_ckdtree(const double *xy, const double *vals, const int *npts_dev, int npts_cap,
                           int nvar, int k, double power, double dist_offset, double mean_res,
                           const double *xgrid, int nx, const double *ygrid, int ny, double *out,

@@ -42,3 +42,9 @@ def lib():
 
 def num_threads():
     return int(lib().ora_num_threads())
+
+
+def set_num_threads(n):
+    """OpenMP threads of the C oracle (all host cores: os.cpu_count())."""
+    lib().ora_set_num_threads(int(n))
+    return num_threads()

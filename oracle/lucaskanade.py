@@ -288,12 +288,15 @@ def track_features(prvs_image, next_image, points, winsize=(50, 50), nr_levels=3
 
 # How equidistant / coincident neighbours are chosen and ordered by the two k-NN users
 # (detect_outliers, idwinterp2d):
-#   "lower_index" (default) -- ascending distance, ties by lower index: the rule of the CUDA path;
-#   "ckdtree"               -- exactly as scipy.spatial.cKDTree returns them (oracle/ckdtree.py):
-#                              with it the whole of dense_lucaskanade is bit-identical to the
-#                              reference (tests/test_oracle_lk.py), which isolates the tie rule as
-#                              the only difference between the CUDA path and the reference.
-_KNN_MODE = ["lower_index"]
+#   "ckdtree" (default) -- exactly as scipy.spatial.cKDTree returns them (oracle/ckdtree.py): with
+#                          it the whole of dense_lucaskanade is bit-identical to the reference
+#                          (tests/test_oracle_lk.py); the CUDA path follows the same order
+#                          (csrc/knn.cu);
+#   "lower_index"       -- ascending distance, ties by lower index (an exhaustive scan without a
+#                          tree; OpenMP C for the grid fill, ~3x faster): a valid k-NN set that
+#                          differs from the reference's only at exact distance ties.  Used as the
+#                          CPU timing baseline of bench.py and by the tests that isolate the tie rule.
+_KNN_MODE = ["ckdtree"]
 
 
 class knn_mode:

@@ -50,6 +50,17 @@ int ora_num_threads(void)
 #endif
 }
 
+/* launchers such as torchrun export OMP_NUM_THREADS=1; the CPU timing legs of bench.py set the
+ * thread count they report explicitly */
+void ora_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n >= 1) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* x86-64 cvttsd2si semantics of (npy_intp)floor(c) */
 static inline int64_t cast_floor(double f)
 {

@@ -76,8 +76,7 @@ _SIGNATURES = {
                                        c_void_p, c_int, c_void_p]),
     "b200_detect_outliers": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_double, c_int, c_void_p,
                                      c_void_p]),
-    "b200_detect_outliers_ckdtree": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_double, c_int, c_void_p,
-                                     c_void_p]),
+    "b200_kdtree_build": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "b200_compact_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                   c_void_p, c_void_p]),
     "b200_decluster": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_double, c_int, c_void_p, c_void_p,

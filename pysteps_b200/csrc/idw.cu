@@ -8,10 +8,20 @@
 // memory once per CTA and every thread scans them for its own pixel, keeping the k best
 // (squared distance, index) pairs sorted in registers.  It is FP64-ALU bound, not HBM
 // bound (~5 FP64 ops per pixel-vector pair vs 16 B written per pixel); distances and
-// weights are float64 in the reference's operation order (ties: lower index first).
+// weights are float64.
+//
+// Neighbour ORDER: an exhaustive scan has no tree, so equal distances are listed by lower index,
+// scipy.spatial.cKDTree lists them in its tree's order.  Inside the list that only permutes equal
+// weights (identical result up to the order of one addition); it matters where the k-th and the
+// (k+1)-th neighbour are exactly equidistant, because then the two pick different vectors.  Every
+// thread therefore tracks the smallest candidate it did NOT keep; a grid point whose k-th distance
+// equals it is appended to a list and recomputed from scipy's own query (knn.cu: idw_fix_kernel,
+// tree built on a side stream while this kernel runs).  The fill is then the reference's at every
+// grid point (<= 1e-12; the weights use rsqrt where NumPy uses sqrt/power/divide).
 #include <math_constants.h>
 
 #include "common.cuh"
+#include "knn_device.cuh"
 
 namespace {
 
@@ -29,6 +39,8 @@ struct IDWParams {
     int nx, ny;
     double power, offset, mean_res;
     double *out;  // (nvar, ny, nx)
+    int *tie_list;   // grid points whose k-th and (k+1)-th neighbours are equidistant (or null)
+    int *tie_count;
 };
 
 // numpy's pairwise summation for n < 128 (8 accumulators, then the remainder)
@@ -96,7 +108,7 @@ __device__ __forceinline__ bool key_less(unsigned long long da, int ia, unsigned
 template <int K, bool EXACT, bool PACKED>
 __device__ __forceinline__ void topk_scan(const double2 *__restrict__ spt, const int *__restrict__ sidx,
                                           int ncand, double qx, double qy, int k, bool first,
-                                          unsigned long long (&bd)[K], int (&bi)[K]) {
+                                          unsigned long long (&bd)[K], int (&bi)[K], unsigned long long &rej) {
     auto dist2 = [&](int t) -> unsigned long long {
         const double2 s = spt[t];
         const double dx = __dsub_rn(s.x, qx), dy = __dsub_rn(s.y, qy);
@@ -137,7 +149,12 @@ __device__ __forceinline__ void topk_scan(const double2 *__restrict__ spt, const
                 if (q == last) { wd = bd[q]; wi = bi[q]; }
         }
         const int id = PACKED ? 0 : sidx[t];
-        if (PACKED ? (d2 < wd) : key_less(d2, id, wd, wi)) {
+        const bool better = PACKED ? (d2 < wd) : key_less(d2, id, wd, wi);
+        // smallest (squared distance) key that is not in the list: the evicted worst or the
+        // rejected candidate
+        const unsigned long long gone = better ? wd : d2;
+        rej = gone < rej ? gone : rej;
+        if (better) {
             bool lt[K];
 #pragma unroll
             for (int q = 0; q < K; q++) lt[q] = PACKED ? (d2 < bd[q]) : key_less(d2, id, bd[q], bi[q]);
@@ -157,8 +174,10 @@ __device__ __forceinline__ void topk_scan(const double2 *__restrict__ spt, const
     }
 }
 
-template <int K, bool EXACT, bool PACKED>
-__global__ void __launch_bounds__(IDW_THREADS) idw_kernel(const IDWParams p) {
+// FASTW: the weighting of dense_lucaskanade's call (two variables, power 1/2, unit resolution,
+// positive offset) from rsqrt; otherwise the general NumPy-order epilogue.
+template <int K, bool EXACT, bool PACKED, bool FASTW>
+__global__ void __launch_bounds__(IDW_THREADS, FASTW ? 3 : 1) idw_kernel(const IDWParams p) {
     __shared__ double2 spt[IDW_CHUNK];
     __shared__ int sidx[IDW_CHUNK];
     __shared__ int hist[IDW_BINS];   // counts, then exclusive offsets
@@ -241,6 +260,7 @@ __global__ void __launch_bounds__(IDW_THREADS) idw_kernel(const IDWParams p) {
     int bi[K];
 #pragma unroll
     for (int q = 0; q < K; q++) { bd[q] = 0x7ff0000000000000ull; bi[q] = 0x7fffffff; }  // +inf
+    unsigned long long rej = ~0ull;  // smallest key among the candidates that are not in the list
 
     // sorted: all candidates fit in shared memory (one round, counting sort by centre-distance
     // bin); otherwise plain exhaustive rounds over chunks of all vectors
@@ -268,9 +288,51 @@ __global__ void __launch_bounds__(IDW_THREADS) idw_kernel(const IDWParams p) {
             }
         }
         __syncthreads();
-        if (active) topk_scan<K, EXACT, PACKED>(spt, sidx, cnt, qx, qy, k, r == 0, bd, bi);
+        if (active) topk_scan<K, EXACT, PACKED>(spt, sidx, cnt, qx, qy, k, r == 0, bd, bi, rej);
+    }
+    // ---- equidistant k-th / (k+1)-th neighbour: listed for the exact-order recomputation -----
+    if (p.tie_list != nullptr) {
+        unsigned long long kth = bd[K - 1];
+        if (!EXACT) {
+#pragma unroll
+            for (int q = 0; q < K; q++)
+                if (q == k - 1) kth = bd[q];
+        }
+        const unsigned long long dmask = PACKED ? ~2047ull : ~0ull;
+        const bool tie = active && k >= 1 && ((kth & dmask) == (rej & dmask));
+        const unsigned bal = __ballot_sync(0xffffffffu, tie);
+        if (bal) {
+            int base = 0;
+            if (lane == __ffs(bal) - 1) base = atomicAdd(p.tie_count, __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+            if (tie) p.tie_list[base + __popc(bal & ((1u << lane) - 1u))] = i * p.nx + j;
+        }
     }
     if (!active || k < 1) return;
+    if (FASTW) {
+        // dense_lucaskanade's call: w = (sqrt(d2) + offset)^-1/2 from two rsqrt (FMA pipe) instead
+        // of sqrt, pow and a divide per neighbour, normalised once -- relative error a few 1e-16
+        double ws = 0.0, ax = 0.0, ay = 0.0;
+        const double2 *__restrict__ v2 = reinterpret_cast<const double2 *>(p.vals);
+#pragma unroll
+        for (int q = 0; q < K; q++) {
+            if (q < k) {
+                const unsigned long long b = PACKED ? (bd[q] & ~2047ull) : bd[q];
+                const int id = PACKED ? (int)(bd[q] & 2047ull) : bi[q];
+                const double d2 = __longlong_as_double((long long)b);
+                const double dist = d2 > 0.0 ? d2 * rsqrt(d2) : 0.0;
+                const double w = rsqrt(dist + p.offset);
+                const double2 v = v2[id];
+                ws += w;
+                ax = fma(w, v.x, ax);
+                ay = fma(w, v.y, ay);
+            }
+        }
+        const double inv = 1.0 / ws;
+        p.out[((size_t)0 * p.ny + i) * p.nx + j] = ax * inv;
+        p.out[((size_t)1 * p.ny + i) * p.nx + j] = ay * inv;
+        return;
+    }
     double w[K];
 #pragma unroll
     for (int q = 0; q < K; q++) {
@@ -294,6 +356,31 @@ __global__ void __launch_bounds__(IDW_THREADS) idw_kernel(const IDWParams p) {
     }
 }
 
+// library-internal side stream of the calling thread's device + fork/join events: the tree build
+// (one CTA, latency bound) overlaps the exhaustive fill, the recomputation of the listed grid
+// points waits for both
+struct SideStream {
+    cudaStream_t s = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    int dev = -1;
+};
+
+int side_stream(SideStream **out) {
+    static thread_local SideStream per_dev[16];
+    int dev = 0;
+    B200_CUDA(cudaGetDevice(&dev));
+    B200_REQUIRE(dev >= 0 && dev < 16, "device index out of range");
+    SideStream &ss = per_dev[dev];
+    if (ss.s == nullptr) {
+        B200_CUDA(cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking));
+        B200_CUDA(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
+        B200_CUDA(cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming));
+        ss.dev = dev;
+    }
+    *out = &ss;
+    return 0;
+}
+
 }  // namespace
 
 extern "C" int b200_idw_fill(const double *xy, const double *vals, const int *npts_dev, int npts_cap,
@@ -306,22 +393,44 @@ extern "C" int b200_idw_fill(const double *xy, const double *vals, const int *np
         b200::set_error("idw: k must be <= 32 (k=None / larger k is not implemented)");
         return B200_ENOTSUP;
     }
+    cudaStream_t s = (cudaStream_t)stream;
+    // ---- cKDTree of the vectors on the side stream (see the header comment) -----------------
+    kdp::TreeScratch ts;
+    b200::Scratch tie;
+    SideStream *ss = nullptr;
+    if (int rc = side_stream(&ss)) return rc;
+    if (int rc = kdp::tree_alloc(ts, npts_cap, s)) return rc;
+    const size_t N = (size_t)ny * nx;
+    B200_REQUIRE(N < ((size_t)1 << 31), "grid too large");
+    B200_CUDA(tie.alloc(sizeof(int) * (N + 1), s));
+    int *tie_count = (int *)tie.p, *tie_list = tie_count + 1;
+    B200_CUDA(cudaMemsetAsync(tie_count, 0, sizeof(int), s));
+    B200_CUDA(cudaEventRecord(ss->fork, s));
+    B200_CUDA(cudaStreamWaitEvent(ss->s, ss->fork, 0));
+    if (int rc = kdp::tree_build(xy, npts_dev, npts_cap, ts.tb, ss->s)) return rc;
+    B200_CUDA(cudaEventRecord(ss->join, ss->s));
+
     IDWParams p;
     p.xy = xy; p.vals = vals; p.npts_dev = npts_dev; p.npts_cap = npts_cap; p.nvar = nvar; p.k = k;
     p.gx = xgrid; p.gy = ygrid; p.nx = nx; p.ny = ny;
     p.power = power; p.offset = dist_offset; p.mean_res = mean_res; p.out = out;
+    p.tie_list = tie_list; p.tie_count = tie_count;
     dim3 grid(b200::ceil_div(nx, IDW_TX), b200::ceil_div(ny, IDW_TY));
     dim3 block(IDW_THREADS);
-    cudaStream_t s = (cudaStream_t)stream;
     // the host knows npts only as a capacity when npts_dev is given; EXACT needs k == K <= npts
     const bool exact_ok = (npts_dev == nullptr) && npts_cap >= k;
     // the caller vouches that every coordinate (vectors and grid) is a multiple of 1/16 with
     // magnitude < 2^14; with <= 2048 vectors the index fits the zero low bits of the distance
     const bool packed = coords_on_16th_grid != 0 && exact_ok && npts_cap <= IDW_CHUNK;
-    if (k == 20 && packed) idw_kernel<20, true, true><<<grid, block, 0, s>>>(p);
-    else if (k == 20 && exact_ok) idw_kernel<20, true, false><<<grid, block, 0, s>>>(p);
-    else if (k == 8 && exact_ok) idw_kernel<8, true, false><<<grid, block, 0, s>>>(p);
-    else idw_kernel<32, false, false><<<grid, block, 0, s>>>(p);
+    const bool fastw = nvar == 2 && power == 0.5 && mean_res == 1.0 && dist_offset > 0.0;
+    if (k == 20 && packed && fastw) idw_kernel<20, true, true, true><<<grid, block, 0, s>>>(p);
+    else if (k == 20 && packed) idw_kernel<20, true, true, false><<<grid, block, 0, s>>>(p);
+    else if (k == 20 && exact_ok && fastw) idw_kernel<20, true, false, true><<<grid, block, 0, s>>>(p);
+    else if (k == 20 && exact_ok) idw_kernel<20, true, false, false><<<grid, block, 0, s>>>(p);
+    else if (k == 8 && exact_ok) idw_kernel<8, true, false, false><<<grid, block, 0, s>>>(p);
+    else idw_kernel<32, false, false, false><<<grid, block, 0, s>>>(p);
     B200_LAUNCH_CHECK();
-    return 0;
+    B200_CUDA(cudaStreamWaitEvent(s, ss->join, 0));
+    return kdp::idw_fix(xy, vals, nvar, k, power, dist_offset, mean_res, xgrid, nx, ygrid, ny, ts.tb, tie_list,
+                        tie_count, out, s);
 }

@@ -11,7 +11,7 @@
 
 #if defined(__CUDACC__)
 #define KD_FN __host__ __device__ __forceinline__
-#define KD_FN_NOINLINE __host__ __device__
+#define KD_FN_NOINLINE inline __host__ __device__ __noinline__
 #else
 #define KD_FN inline
 #define KD_FN_NOINLINE inline
@@ -217,27 +217,242 @@ KD_FN_NOINLINE void build(Tree &t, int *stack) {
     }
 }
 
+// ---- the same build on position-aligned (x, y, index) triples -------------------------------------
+// The parallel device build (knn.cu) keeps the coordinates of the point at tree position p in
+// kx[p], ky[p] beside idx[p] and moves the three together, so a comparison is one load.  Its
+// partition steps are the libstdc++ loops restated as PAIR SWAPS: with A the positions (ascending)
+// where the left scan stops and B the positions (descending) where the right scan stops, the
+// sequential loop swaps (A_i, B_i) for every i below the first i with A_i >= B_i, nothing else.
+// The functions below are that formulation executed serially (host tests pin it against the
+// sequential restatement above and, through it, against libstdc++ and scipy); knn.cu executes the
+// identical formulation with one warp per tree node.
+struct Tri { double *kx, *ky; int *idx; };
+struct Elem { double x, y; int i; };
+
+KD_FN Elem tri_load(const Tri &a, int p) { Elem e; e.x = a.kx[p]; e.y = a.ky[p]; e.i = a.idx[p]; return e; }
+KD_FN void tri_store(const Tri &a, int p, const Elem &e) { a.kx[p] = e.x; a.ky[p] = e.y; a.idx[p] = e.i; }
+KD_FN void tri_swap(const Tri &a, int p, int q) {
+    const Elem e = tri_load(a, p);
+    tri_store(a, p, tri_load(a, q));
+    tri_store(a, q, e);
+}
+KD_FN double ekey(const Elem &e, int d) { return d ? e.y : e.x; }
+KD_FN const double *tri_keys(const Tri &a, int d) { return d ? a.ky : a.kx; }
+
+KD_FN void tri_push_heap(const Tri &a, int base, int hole, int top, const Elem &value, int d) {
+    int parent = (hole - 1) / 2;
+    while (hole > top && ekey(tri_load(a, base + parent), d) < ekey(value, d)) {
+        tri_store(a, base + hole, tri_load(a, base + parent));
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    tri_store(a, base + hole, value);
+}
+
+KD_FN void tri_adjust_heap(const Tri &a, int base, int hole, int len, const Elem &value, int d) {
+    const int top = hole;
+    int child = hole;
+    const double *K = tri_keys(a, d);
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (K[base + child] < K[base + child - 1]) child--;
+        tri_store(a, base + hole, tri_load(a, base + child));
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        tri_store(a, base + hole, tri_load(a, base + child - 1));
+        hole = child - 1;
+    }
+    tri_push_heap(a, base, hole, top, value, d);
+}
+
+// std::__heap_select(first, middle, last) followed by iter_swap(first, nth) is the caller's job
+KD_FN_NOINLINE void tri_heap_select(const Tri &a, int first, int middle, int last, int d) {
+    const int len = middle - first;
+    const double *K = tri_keys(a, d);
+    if (len >= 2) {
+        int parent = (len - 2) / 2;
+        for (;;) {
+            tri_adjust_heap(a, first, parent, len, tri_load(a, first + parent), d);
+            if (parent == 0) break;
+            parent--;
+        }
+    }
+    for (int i = middle; i < last; i++)
+        if (K[i] < K[first]) {
+            const Elem value = tri_load(a, i);
+            tri_store(a, i, tri_load(a, first));
+            tri_adjust_heap(a, first, 0, len, value, d);
+        }
+}
+
+// std::__insertion_sort(first, last)
+KD_FN void tri_insertion_sort(const Tri &a, int first, int last, int d) {
+    for (int i = first + 1; i < last; i++) {
+        const Elem v = tri_load(a, i);
+        if (ekey(v, d) < tri_keys(a, d)[first]) {
+            for (int j = i; j > first; j--) tri_store(a, j, tri_load(a, j - 1));
+            tri_store(a, first, v);
+        } else {
+            int j = i;
+            while (ekey(v, d) < tri_keys(a, d)[j - 1]) {
+                tri_store(a, j, tri_load(a, j - 1));
+                j--;
+            }
+            tri_store(a, j, v);
+        }
+    }
+}
+
+// std::__move_median_to_first(first, first + 1, mid, last - 1): position of the median
+KD_FN int tri_median_pick(const double *K, int first, int mid, int last) {
+    const int ra = first + 1, rb = mid, rc = last - 1;
+    if (K[ra] < K[rb]) {
+        if (K[rb] < K[rc]) return rb;
+        if (K[ra] < K[rc]) return rc;
+        return ra;
+    }
+    if (K[ra] < K[rc]) return ra;
+    if (K[rb] < K[rc]) return rc;
+    return rb;
+}
+
+// MODE 0: std::__unguarded_partition(lo, hi, pivot) -- left scan stops where !(v < piv), right scan
+//         where !(piv < v); returns the cut.
+// MODE 1: partition_below(lo, hi, split) -- left stops where !(v < split), right where !(v >= split);
+//         returns the first position of the ">= split" block.
+// posA / posB: scratch of hi - lo entries each.
+template <int MODE, class P>
+KD_FN int pair_partition_serial(const Tri &a, int d, int lo, int hi, double piv, P *posA, P *posB) {
+    const double *K = tri_keys(a, d);
+    int cntA = 0, cntB = 0;
+    for (int p = lo; p < hi; p++)
+        if (!(K[p] < piv)) posA[cntA++] = (P)p;
+    for (int p = hi - 1; p >= lo; p--)
+        if (MODE == 0 ? !(piv < K[p]) : !(K[p] >= piv)) posB[cntB++] = (P)p;
+    const int npair = cntA < cntB ? cntA : cntB;
+    int j = 0;
+    while (j < npair && posA[j] < posB[j]) {
+        tri_swap(a, posA[j], posB[j]);
+        j++;
+    }
+    if (MODE == 1) return hi - cntA;
+    const int fa = j < cntA ? (int)posA[j] : hi, fb = j > 0 ? (int)posB[j - 1] : hi;
+    return fa < fb ? fa : fb;
+}
+
+// the tree build on triples, serial execution of the pair formulation; depth_limit < 0: libstdc++'s
+// 2 * floor(log2(len)).  Node numbering is breadth-first here (sequential build: depth-first); a
+// query never looks at node numbers, only at the structure.
+template <class P>
+KD_FN_NOINLINE void build_pairs(Tree &t, const Tri &a, P *posA, P *posB, int *queue, int depth_limit) {
+    const int n = t.n;
+    for (int i = 0; i < n; i++) { a.kx[i] = t.data[2 * (size_t)i]; a.ky[i] = t.data[2 * (size_t)i + 1]; a.idx[i] = i; }
+    for (int c = 0; c < 2; c++) {
+        t.maxes[c] = t.mins[c] = n ? t.data[c] : 0.0;
+        for (int i = 1; i < n; i++) {
+            const double v = t.data[2 * (size_t)i + c];
+            if (v > t.maxes[c]) t.maxes[c] = v;
+            if (v < t.mins[c]) t.mins[c] = v;
+        }
+    }
+    t.nnodes = 1;
+    t.nodes[0].start = 0; t.nodes[0].end = n;
+    t.nodes[0].split_dim = -1; t.nodes[0].less = t.nodes[0].greater = -1; t.nodes[0].split = 0.0;
+    int qh = 0, qt = 0;
+    if (n > LEAFSIZE) queue[qt++] = 0;
+    while (qh < qt) {
+        const int me = queue[qh++];
+        const int start = t.nodes[me].start, end = t.nodes[me].end;
+        double mx[2], mn[2];
+        mx[0] = mn[0] = a.kx[start]; mx[1] = mn[1] = a.ky[start];
+        for (int j = start + 1; j < end; j++) {
+            mx[0] = mx[0] > a.kx[j] ? mx[0] : a.kx[j]; mn[0] = mn[0] < a.kx[j] ? mn[0] : a.kx[j];
+            mx[1] = mx[1] > a.ky[j] ? mx[1] : a.ky[j]; mn[1] = mn[1] < a.ky[j] ? mn[1] : a.ky[j];
+        }
+        int d = 0;
+        double size = 0.0;
+        for (int c = 0; c < 2; c++)
+            if (mx[c] - mn[c] > size) { d = c; size = mx[c] - mn[c]; }
+        if (mx[d] == mn[d]) continue;
+        const double *K = tri_keys(a, d);
+        const int nth = start + (end - start) / 2;
+        {   // std::nth_element(start, nth, end)
+            int first = start, last = end, depth = depth_limit;
+            if (depth < 0) { depth = 0; for (int m = last - first; m > 1; m >>= 1) depth++; depth *= 2; }
+            bool done = false;
+            while (last - first > 3) {
+                if (depth == 0) {
+                    tri_heap_select(a, first, nth + 1, last, d);
+                    tri_swap(a, first, nth);
+                    done = true;
+                    break;
+                }
+                depth--;
+                const int mid = first + (last - first) / 2;
+                tri_swap(a, first, tri_median_pick(K, first, mid, last));
+                const int cut = pair_partition_serial<0>(a, d, first + 1, last, K[first], posA, posB);
+                if (cut <= nth) first = cut; else last = cut;
+            }
+            if (!done) tri_insertion_sort(a, first, last, d);
+        }
+        double split = K[nth];
+        int p = pair_partition_serial<1>(a, d, start, end, split, posA, posB);
+        if (p == start) {
+            split = nextafter(split, (double)INFINITY);
+            p = pair_partition_serial<1>(a, d, start, end, split, posA, posB);
+        }
+        const int lo = t.nnodes++, hi = t.nnodes++;
+        for (int c = 0; c < 2; c++) {
+            Node &ch = t.nodes[c ? hi : lo];
+            ch.start = c ? p : start; ch.end = c ? end : p;
+            ch.split_dim = -1; ch.less = ch.greater = -1; ch.split = 0.0;
+            if (ch.end - ch.start > LEAFSIZE) queue[qt++] = c ? hi : lo;
+        }
+        t.nodes[me].less = lo; t.nodes[me].greater = hi; t.nodes[me].split_dim = d; t.nodes[me].split = split;
+    }
+    for (int i = 0; i < n; i++) t.idx[i] = a.idx[i];
+}
+
 // ---- scipy's binary heap ------------------------------------------------------------------------
 struct Item { double priority; int payload; };
+struct NodeInfo { int node; double side[2]; double min_distance; };
 
-KD_FN void heap_push(Item *h, int &n, Item it) {
+// scipy keeps {priority, pointer to a nodeinfo} in its node queue with priority == min_distance; here
+// the nodeinfo itself is the heap element (same comparisons, same sift order, no side pool)
+KD_FN double prio(const Item &a) { return a.priority; }
+KD_FN double prio(const NodeInfo &a) { return a.min_distance; }
+
+// heap storage handle: anything indexable (a plain pointer on the host; on the device per-thread
+// arrays interleaved across the threads of a CTA in shared memory)
+template <class T>
+struct Strided {
+    T *p;
+    int stride;
+    KD_FN T &operator[](int i) const { return p[(size_t)i * stride]; }
+};
+
+template <class H, class T>
+KD_FN void heap_push(H h, int &n, const T &it) {
     int i = n++;
     h[i] = it;
-    while (i > 0 && h[i].priority < h[(i - 1) / 2].priority) {
-        const Item tmp = h[(i - 1) / 2];
+    while (i > 0 && prio(h[i]) < prio(h[(i - 1) / 2])) {
+        const T tmp = h[(i - 1) / 2];
         h[(i - 1) / 2] = h[i];
         h[i] = tmp;
         i = (i - 1) / 2;
     }
 }
 
-KD_FN void heap_remove(Item *h, int &n) {
+template <class T, class H>
+KD_FN void heap_remove(H h, int &n) {
     h[0] = h[n - 1];
     n--;
     int i = 0, j = 1, k = 2;
-    while ((j < n && h[i].priority > h[j].priority) || (k < n && h[i].priority > h[k].priority)) {
-        const int l = (k < n && h[j].priority > h[k].priority) ? k : j;
-        const Item tmp = h[l];
+    while ((j < n && prio(h[i]) > prio(h[j])) || (k < n && prio(h[i]) > prio(h[k]))) {
+        const int l = (k < n && prio(h[j]) > prio(h[k])) ? k : j;
+        const T tmp = h[l];
         h[l] = h[i];
         h[i] = tmp;
         i = l;
@@ -246,14 +461,23 @@ KD_FN void heap_remove(Item *h, int &n) {
     }
 }
 
-struct NodeInfo { int node; double side[2]; double min_distance; };
+// no spill space: a full pending-node heap is an error
+struct NoGrow {
+    template <class Q>
+    KD_FN bool operator()(Q &, int &, int) const { return false; }
+};
 
 // tree.query(x, k): the kmax nearest points in scipy's order (missing: index n).  Scratch per
-// query: nb (kmax items), q and pool (nnodes entries each).
-KD_FN_NOINLINE void query(const Tree &t, double x0, double x1, int kmax, int *out_idx, Item *nb, Item *q,
-                          NodeInfo *pool, double *out_dist = nullptr) {
+// query: nb (kmax items) and q (qcap pending nodes).  A query queues at most one far child per
+// internal node it visits, so qcap = number of nodes can never overflow; with a smaller heap,
+// grow(q, qcap, qn) is asked for a larger one when it is full (it moves the qn entries), and the
+// return value is false (result invalid) if it could not provide one.
+template <class NB, class Q, class Grow>
+KD_FN_NOINLINE bool query(const Tree &t, double x0, double x1, int kmax, int *out_idx, NB nb, Q q,
+                          int qcap, const Grow &grow, double *out_dist = nullptr) {
     const double x[2] = {x0, x1};
-    int nbn = 0, qn = 0, pooln = 0;
+    int nbn = 0, qn = 0;
+    bool ok = true;
     NodeInfo cur;
     cur.node = 0;
     cur.min_distance = 0.0;
@@ -276,7 +500,7 @@ KD_FN_NOINLINE void query(const Tree &t, double x0, double x1, int kmax, int *ou
                 d += dx * dx;
                 d += dy * dy;
                 if (d < dub) {
-                    if (nbn == kmax) heap_remove(nb, nbn);
+                    if (nbn == kmax) heap_remove<Item>(nb, nbn);
                     Item it;
                     it.priority = -d;
                     it.payload = pi;
@@ -285,8 +509,8 @@ KD_FN_NOINLINE void query(const Tree &t, double x0, double x1, int kmax, int *ou
                 }
             }
             if (qn == 0) break;
-            cur = pool[q[0].payload];
-            heap_remove(q, qn);
+            cur = q[0];
+            heap_remove<NodeInfo>(q, qn);
         } else {
             if (cur.min_distance > dub) break;
             const int sd = node.split_dim;
@@ -310,25 +534,23 @@ KD_FN_NOINLINE void query(const Tree &t, double x0, double x1, int kmax, int *ou
                 far = tmp;
             }
             if (far.min_distance <= dub) {
-                pool[pooln] = far;
-                Item it;
-                it.priority = far.min_distance;
-                it.payload = pooln;
-                pooln++;
-                heap_push(q, qn, it);
+                if (qn == qcap && !grow(q, qcap, qn)) ok = false;
+                else heap_push(q, qn, far);
             }
         }
     }
     const int found = nbn;
     for (int i = found - 1; i >= 0; i--) {
-        out_idx[i] = nb[0].payload;
-        if (out_dist) out_dist[i] = sqrt(-nb[0].priority);
-        heap_remove(nb, nbn);
+        const Item top = nb[0];
+        out_idx[i] = top.payload;
+        if (out_dist) out_dist[i] = sqrt(-top.priority);
+        heap_remove<Item>(nb, nbn);
     }
     for (int i = found; i < kmax; i++) {
         out_idx[i] = t.n;
         if (out_dist) out_dist[i] = (double)INFINITY;
     }
+    return ok;
 }
 
 // numpy's pairwise summation of n <= 128 contiguous doubles (DOUBLE_pairwise_sum): 8 running

@@ -1,141 +1,15 @@
 // sparse.cu -- the sparse-vector cleansing stages of dense_lucaskanade on the device
-// (sm_100a): local Mahalanobis outlier detection and grid-cell declustering.
+// (sm_100a): compaction of the kept vectors and grid-cell declustering (the outlier test itself
+// needs scipy.spatial.cKDTree's neighbour order and lives in knn.cu).
 //
-// Reference: pysteps/utils/cleansing.py:124-249 (detect_outliers, coord + k given) and
-// pysteps/utils/cleansing.py:21-121 (decluster).  Both are Python loops over <= a few
-// thousand vectors around cKDTree / np.cov / np.linalg.inv / np.median; here each is one
-// small kernel (float64, deterministic order) so the vectors never leave the device.
+// Reference: pysteps/utils/cleansing.py:21-121 (decluster), a Python loop over <= a few thousand
+// vectors around np.unique / np.median; here one small kernel (float64, deterministic order) so
+// the vectors never leave the device.
 #include <math_constants.h>
 
 #include "common.cuh"
 
 namespace {
-
-constexpr int OUT_WARPS = 4;
-constexpr int OUT_KMAX = 64;  // neighbours incl. self
-
-// one warp per vector: k+1 nearest by (distance, index) via repeated warp arg-min, then the
-// 2x2 sample covariance of the k neighbours and the Mahalanobis distance of the vector.
-// CACHED: n <= 32 * OUT_CACHE, every lane keeps its squared distances in registers, so the
-// k+1 selection rounds only compare (the distances are computed once, not k+1 times).
-constexpr int OUT_CACHE = 64;
-
-template <bool CACHED>
-__global__ void __launch_bounds__(32 * OUT_WARPS)
-outliers_kernel(const double *__restrict__ uv, const double *__restrict__ xy, const int *__restrict__ n_dev,
-                int n_cap, double thr, int k, uint8_t *__restrict__ out) {
-    __shared__ int nbr[OUT_WARPS][OUT_KMAX];
-    const int n = n_dev ? min(*n_dev, n_cap) : n_cap;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int i = blockIdx.x * OUT_WARPS + wid;
-    if (i >= n) return;
-    if (n < 2) {  // cleansing.py:177-178
-        if (lane == 0) out[i] = 0;
-        return;
-    }
-    const int kk = min(n, k + 1);  // :198
-    const double xi = xy[2 * i], yi = xy[2 * i + 1];
-    double last_d = -1.0;
-    int last_j = -1;
-    double dc[CACHED ? OUT_CACHE : 1];
-    if (CACHED) {
-#pragma unroll
-        for (int q = 0; q < OUT_CACHE; q++) {
-            const int j = q * 32 + lane;
-            dc[q] = CUDART_INF;
-            if (j < n) {
-                const double dx = __dsub_rn(xy[2 * j], xi), dy = __dsub_rn(xy[2 * j + 1], yi);
-                dc[q] = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-            }
-        }
-    }
-    for (int r = 0; r < kk; r++) {
-        double bd = CUDART_INF;
-        int bj = 0x7fffffff;
-        if (CACHED) {
-#pragma unroll
-            for (int q = 0; q < OUT_CACHE; q++) {
-                const int j = q * 32 + lane;
-                const double d = dc[q];
-                // ascending j within a lane: the first strict improvement is the lowest index
-                const bool after = (d > last_d) || (d == last_d && j > last_j);
-                if (j < n && after && d < bd) { bd = d; bj = j; }
-            }
-        } else {
-            for (int j = lane; j < n; j += 32) {
-                const double dx = __dsub_rn(xy[2 * j], xi), dy = __dsub_rn(xy[2 * j + 1], yi);
-                const double d = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-                const bool after = (d > last_d) || (d == last_d && j > last_j);
-                if (after && (d < bd || (d == bd && j < bj))) { bd = d; bj = j; }
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double od = __shfl_xor_sync(0xffffffffu, bd, o);
-            const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
-            if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; }
-        }
-        last_d = bd; last_j = bj;
-        if (lane == 0) nbr[wid][r] = bj;
-    }
-    __syncwarp();
-    if (lane != 0) return;
-    const int m = kk - 1;  // neighbours without the nearest (normally the vector itself), :228,234
-    // mean of the neighbours (row by row) and centring, :236-237
-    double mu = 0.0, mv = 0.0;
-    for (int q = 1; q <= m; q++) {
-        const int j = nbr[wid][q];
-        mu = (q == 1) ? uv[2 * j] : __dadd_rn(mu, uv[2 * j]);
-        mv = (q == 1) ? uv[2 * j + 1] : __dadd_rn(mv, uv[2 * j + 1]);
-    }
-    mu = __ddiv_rn(mu, (double)m);
-    mv = __ddiv_rn(mv, (double)m);
-    const double zu = __dsub_rn(uv[2 * i], mu), zv = __dsub_rn(uv[2 * i + 1], mv);
-    // np.cov of the centred neighbours: subtract their (tiny) mean again, ddof = 1
-    double au = 0.0, av = 0.0;
-    for (int q = 1; q <= m; q++) {
-        const int j = nbr[wid][q];
-        au = __dadd_rn(au, __dsub_rn(uv[2 * j], mu));
-        av = __dadd_rn(av, __dsub_rn(uv[2 * j + 1], mv));
-    }
-    au = __ddiv_rn(au, (double)m);
-    av = __ddiv_rn(av, (double)m);
-    double suu = 0.0, suv = 0.0, svv = 0.0;
-    for (int q = 1; q <= m; q++) {
-        const int j = nbr[wid][q];
-        const double a = __dsub_rn(__dsub_rn(uv[2 * j], mu), au);
-        const double b = __dsub_rn(__dsub_rn(uv[2 * j + 1], mv), av);
-        suu = __dadd_rn(suu, __dmul_rn(a, a));
-        suv = __dadd_rn(suv, __dmul_rn(a, b));
-        svv = __dadd_rn(svv, __dmul_rn(b, b));
-    }
-    const double fact = __ddiv_rn(1.0, (double)(m - 1));  // m == 1 -> inf/nan like np.cov
-    const double a = __dmul_rn(suu, fact), b = __dmul_rn(suv, fact), d = __dmul_rn(svv, fact);
-    // np.linalg.inv: LU with partial pivoting; exactly singular -> LinAlgError -> MD = 0
-    double MD = 0.0;
-    const bool swap = fabs(b) > fabs(a);
-    const double p0 = swap ? b : a, p1 = swap ? d : b;   // pivot row
-    const double q0 = swap ? a : b, q1 = swap ? b : d;   // other row
-    if (p0 != 0.0 && !(isnan(p0))) {
-        const double l = __dmul_rn(q0, __ddiv_rn(1.0, p0));
-        const double u22 = __dsub_rn(q1, __dmul_rn(l, p1));
-        if (u22 != 0.0) {
-            // solve V X = I column by column (rows permuted when swap)
-            // column e0, e1 of the identity after the row permutation
-            const double r00 = swap ? 0.0 : 1.0, r10 = swap ? 1.0 : 0.0;  // P*e0
-            const double r01 = swap ? 1.0 : 0.0, r11 = swap ? 0.0 : 1.0;  // P*e1
-            const double y10 = __dsub_rn(r10, __dmul_rn(l, r00)), y11 = __dsub_rn(r11, __dmul_rn(l, r01));
-            const double x10 = __ddiv_rn(y10, u22), x11 = __ddiv_rn(y11, u22);
-            const double x00 = __ddiv_rn(__dsub_rn(r00, __dmul_rn(p1, x10)), p0);
-            const double x01 = __ddiv_rn(__dsub_rn(r01, __dmul_rn(p1, x11)), p0);
-            // MD = sqrt(z VI z^T), :241
-            const double t0 = __dadd_rn(__dmul_rn(zu, x00), __dmul_rn(zv, x10));
-            const double t1 = __dadd_rn(__dmul_rn(zu, x01), __dmul_rn(zv, x11));
-            MD = sqrt(__dadd_rn(__dmul_rn(t0, zu), __dmul_rn(t1, zv)));
-        }
-    }
-    out[i] = (MD > thr) ? 1 : 0;  // NaN compares false, as in NumPy
-}
 
 // keep rows whose flag is 0, preserving order (xy[~outliers], uv[~outliers])
 __global__ void __launch_bounds__(1024)
@@ -172,7 +46,7 @@ compact_rows_kernel(const double *__restrict__ xy, const double *__restrict__ uv
 }
 
 // ---- decluster ---------------------------------------------------------------------------
-constexpr int DC_MAX = 4096;
+constexpr int DC_MAX = 16384;  // vectors (12 B of shared memory each)
 
 __device__ __forceinline__ double median_of(const double *__restrict__ a, int stride,
                                             const unsigned long long *__restrict__ keys, int s) {
@@ -194,16 +68,17 @@ __device__ __forceinline__ double median_of(const double *__restrict__ a, int st
 
 __global__ void __launch_bounds__(1024)
 decluster_kernel(const double *__restrict__ xy, const double *__restrict__ uv, const int *__restrict__ n_dev,
-                 int n_cap, double scale, int min_samples, double *__restrict__ oxy, double *__restrict__ ouv,
-                 int *__restrict__ out_count) {
-    __shared__ unsigned long long key[DC_MAX];
-    __shared__ unsigned short seg_start[DC_MAX + 1];
+                 int n_cap, int cap_pad, double scale, int min_samples, double *__restrict__ oxy,
+                 double *__restrict__ ouv, int *__restrict__ out_count) {
+    extern __shared__ __align__(16) unsigned char dc_smem[];
     __shared__ int s_nseg;
     const int n = n_dev ? min(*n_dev, n_cap) : n_cap;
     const int tid = threadIdx.x;
     int npad = 1;
     while (npad < n) npad <<= 1;
     if (npad < 2) npad = 2;
+    unsigned long long *key = reinterpret_cast<unsigned long long *>(dc_smem);  // cap_pad entries
+    int *seg_start = reinterpret_cast<int *>(key + cap_pad);                    // cap_pad + 1
     // key = (cell_x, cell_y, index): np.unique(axis=0) orders cells lexicographically by x then y
     for (int i = tid; i < npad; i += blockDim.x) {
         unsigned long long kv = ~0ull;
@@ -250,11 +125,11 @@ decluster_kernel(const double *__restrict__ xy, const double *__restrict__ uv, c
         int pos = base + incl - local;  // number of heads before this thread's elements
         for (int q = 0; q < per; q++) {
             const int i = i0 + q;
-            if (i < n && (i == 0 || (key[i] >> 22) != (key[i - 1] >> 22))) seg_start[pos++] = (unsigned short)i;
+            if (i < n && (i == 0 || (key[i] >> 22) != (key[i - 1] >> 22))) seg_start[pos++] = i;
         }
         if (tid == (int)blockDim.x - 1) {
             s_nseg = base + incl;
-            seg_start[base + incl] = (unsigned short)n;
+            seg_start[base + incl] = n;
         }
     }
     __syncthreads();
@@ -284,24 +159,6 @@ decluster_kernel(const double *__restrict__ xy, const double *__restrict__ uv, c
 
 }  // namespace
 
-extern "C" int b200_detect_outliers(const double *uv, const double *xy, const int *n_dev, int n_cap,
-                                    double thr, int k, uint8_t *out, void *stream) {
-    B200_REQUIRE(uv && xy && out && n_cap >= 0 && k >= 1, "bad arguments");
-    if (k + 1 > OUT_KMAX) {
-        b200::set_error("detect_outliers: k must be < %d", OUT_KMAX);
-        return B200_ENOTSUP;
-    }
-    if (n_cap == 0) return 0;
-    if (n_cap <= 32 * OUT_CACHE)
-        outliers_kernel<true><<<b200::ceil_div(n_cap, OUT_WARPS), 32 * OUT_WARPS, 0, (cudaStream_t)stream>>>(
-            uv, xy, n_dev, n_cap, thr, k, out);
-    else
-        outliers_kernel<false><<<b200::ceil_div(n_cap, OUT_WARPS), 32 * OUT_WARPS, 0, (cudaStream_t)stream>>>(
-            uv, xy, n_dev, n_cap, thr, k, out);
-    B200_LAUNCH_CHECK();
-    return 0;
-}
-
 extern "C" int b200_compact_rows(const double *xy, const double *uv, const uint8_t *drop, const int *n_dev,
                                  int n_cap, double *out_xy, double *out_uv, int *out_count, void *stream) {
     B200_REQUIRE(xy && uv && drop && out_xy && out_uv && out_count && n_cap >= 0, "bad arguments");
@@ -317,8 +174,12 @@ extern "C" int b200_decluster(const double *xy, const double *uv, const int *n_d
         b200::set_error("decluster: at most %d vectors are supported", DC_MAX);
         return B200_ENOTSUP;
     }
-    decluster_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(xy, uv, n_dev, n_cap, scale, min_samples, out_xy, out_uv,
-                                                          out_count);
+    int cap_pad = 2;
+    while (cap_pad < n_cap) cap_pad <<= 1;
+    const size_t smem = (size_t)cap_pad * 8 + ((size_t)cap_pad + 1) * 4;
+    B200_CUDA(cudaFuncSetAttribute(decluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    decluster_kernel<<<1, 1024, smem, (cudaStream_t)stream>>>(xy, uv, n_dev, n_cap, cap_pad, scale, min_samples,
+                                                             out_xy, out_uv, out_count);
     B200_LAUNCH_CHECK();
     return 0;
 }

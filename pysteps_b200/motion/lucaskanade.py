@@ -97,10 +97,6 @@ _side_streams = {}
 _grids = {}
 
 
-def exact_ties():
-    return os.environ.get("PYSTEPS_B200_EXACT_TIES", "") == "1"
-
-
 def _pixel_grid(a, b):
     """np.arange(a, b) as a float64 device vector (lucaskanade.py:271-272), built once."""
     key = (torch.cuda.current_device(), a, b)
@@ -308,10 +304,9 @@ def dense_lucaskanade(input_images, lk_kwargs=None, fd_method="shitomasi", fd_kw
     kept_uv = torch.empty((pool_cap, 2), dtype=torch.float64, device="cuda")
     if k_outlier is None:
         raise NotImplementedError("pysteps_b200 LK: k_outlier=None (global outlier test) is not implemented")
-    # PYSTEPS_B200_EXACT_TIES=1: equidistant / coincident neighbours in scipy.spatial.cKDTree's own
-    # order (csrc/knn.cu) instead of by lower index -- built and verified on the CPU, opt-in until it
-    # has run on hardware
-    _call("b200_detect_outliers_ckdtree" if exact_ties() else "b200_detect_outliers",
+    # equidistant / coincident neighbours in scipy.spatial.cKDTree's own order (csrc/knn.cu): with
+    # integer corner coordinates that order decides outlier tests
+    _call("b200_detect_outliers",
           pool_uv.data_ptr(), pool_xy.data_ptr(), counts[0:1].data_ptr(),
           pool_cap, float(nr_std_outlier), int(k_outlier), flags.data_ptr(), _s())
     _call("b200_compact_rows", pool_xy.data_ptr(), pool_uv.data_ptr(), flags.data_ptr(),
@@ -368,15 +363,11 @@ def dense_lucaskanade(input_images, lk_kwargs=None, fd_method="shitomasi", fd_kw
         # of 1/2): squared distances are exact small multiples of 1/256 -> packed-key fast path
         on_grid = bool(np.all(xy_h * 16.0 == np.rint(xy_h * 16.0)) and np.abs(xy_h).max() < 16384.0
                        and max(m, n) < 16384)
-        if exact_ties():
-            # every grid point searched, ordered and weighted as the reference does (csrc/knn.cu)
-            _call("b200_idw_fill_ckdtree", dec_xy.data_ptr(), dec_uv.data_ptr(), None, n_dec, 2,
-                  int(min(int(k), n_dec)), power, dist_offset, 1.0, xgrid.data_ptr(), n, ygrid.data_ptr(), mb,
-                  out.data_ptr(), _s())
-        else:
-            _call("b200_idw_fill", dec_xy.data_ptr(), dec_uv.data_ptr(), None, n_dec, 2, int(min(int(k), n_dec)),
-                  power, dist_offset, 1.0, xgrid.data_ptr(), n, ygrid.data_ptr(), mb, int(on_grid),
-                  out.data_ptr(), _s())
+        # exhaustive tile search; grid points whose neighbour set depends on cKDTree's tie order are
+        # recomputed from its query (csrc/idw.cu, knn.cu)
+        _call("b200_idw_fill", dec_xy.data_ptr(), dec_uv.data_ptr(), None, n_dec, 2, int(min(int(k), n_dec)),
+              power, dist_offset, 1.0, xgrid.data_ptr(), n, ygrid.data_ptr(), mb, int(on_grid),
+              out.data_ptr(), _s())
 
     if verbose:
         torch.cuda.current_stream().synchronize()

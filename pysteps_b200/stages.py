@@ -158,7 +158,7 @@ def detect_outliers(input_array, thr, coord=None, k=None, verbose=False):
     duv = _device.to_device(np.ascontiguousarray(input_array, dtype=np.float64))
     dxy = _device.to_device(np.ascontiguousarray(coord, dtype=np.float64))
     flags = torch.empty(nsamples, dtype=torch.uint8, device="cuda")
-    _lib.call("b200_detect_outliers_ckdtree" if _lk.exact_ties() else "b200_detect_outliers",
+    _lib.call("b200_detect_outliers",
               duv.data_ptr(), dxy.data_ptr(), None, nsamples, float(thr), int(k), flags.data_ptr(), _s())
     out = flags.cpu().numpy().astype(bool)
     if verbose:
@@ -254,14 +254,9 @@ def idwinterp2d(xy_coord, values, xgrid, ygrid, power=0.5, k=20, dist_offset=0.5
 
         def fill(gx, gy, mean_res, dst):
             dgx, dgy = _device.to_device(gx), _device.to_device(gy)
-            if _lk.exact_ties():  # cKDTree's neighbour order and numpy's reductions (csrc/knn.cu), opt-in
-                _lib.call("b200_idw_fill_ckdtree", dxy.data_ptr(), dv.data_ptr(), None, npts, nvar, kk, float(power),
-                          float(dist_offset), mean_res, dgx.data_ptr(), gx.size, dgy.data_ptr(), gy.size,
-                          dst.data_ptr(), _s())
-            else:
-                _lib.call("b200_idw_fill", dxy.data_ptr(), dv.data_ptr(), None, npts, nvar, kk, float(power),
-                          float(dist_offset), mean_res, dgx.data_ptr(), gx.size, dgy.data_ptr(), gy.size,
-                          int(on_grid), dst.data_ptr(), _s())
+            _lib.call("b200_idw_fill", dxy.data_ptr(), dv.data_ptr(), None, npts, nvar, kk, float(power),
+                      float(dist_offset), mean_res, dgx.data_ptr(), gx.size, dgy.data_ptr(), gy.size,
+                      int(on_grid), dst.data_ptr(), _s())
 
         if len({r for row in res for r in row}) == 1:
             fill(xg, yg, res[0][0], out)

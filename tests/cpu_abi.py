@@ -298,14 +298,6 @@ def _count(n_dev, cap):
 
 
 def _lk_detect_outliers(uv, xy, n_dev, cap, thr, k, out, stream):
-    from oracle import lucaskanade as ora_lk
-    cnt = _count(n_dev, cap)
-    if cnt:
-        _view(out, (cap,), np.uint8)[:cnt] = ora_lk.detect_outliers(_view(uv, (cap, 2))[:cnt].copy(), thr,
-                                                                    _view(xy, (cap, 2))[:cnt].copy(), k)
-
-
-def _lk_detect_outliers_ckdtree(uv, xy, n_dev, cap, thr, k, out, stream):
     """the kernel's own body (csrc/knn_body.cuh) compiled for the host"""
     import host_kernels
     cnt = _count(n_dev, cap)
@@ -371,7 +363,6 @@ _TABLE_LK = {"b200_mask_invalid": _lk_mask_invalid, "b200_morph_opening": _lk_mo
              "b200_min_eig": _lk_min_eig, "b200_good_features": _lk_good_features,
              "b200_lk_build_pyramid": _lk_build_pyramid, "b200_lk_track": _lk_track,
              "b200_lk_compact_tracks": _lk_compact_tracks, "b200_detect_outliers": _lk_detect_outliers,
-             "b200_detect_outliers_ckdtree": _lk_detect_outliers_ckdtree,
              "b200_compact_rows": _lk_compact_rows, "b200_decluster": _lk_decluster,
              "b200_idw_fill": _lk_idw_fill, "b200_idw_fill_ckdtree": _lk_idw_fill_ckdtree, "b200_fill_f64": _fill_f64}
 

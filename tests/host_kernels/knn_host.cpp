@@ -19,11 +19,38 @@ void host_kd_knn(const double *data, int n, const double *queries, int nq, int k
     t.nodes = nodes.data();
     kd::build(t, stack.data());
     for (int i = 0; i < n; i++) perm[i] = idx[i];
-    std::vector<kd::Item> nb(k), q(t.nnodes + 1);
-    std::vector<kd::NodeInfo> pool(t.nnodes + 1);
+    std::vector<kd::Item> nb(k);
+    std::vector<kd::NodeInfo> q(t.nnodes + 1);
     for (int i = 0; i < nq; i++)
         kd::query(t, queries[2 * (size_t)i], queries[2 * (size_t)i + 1], k, out_idx + (size_t)i * k, nb.data(), q.data(),
-                  pool.data());
+                  t.nnodes + 1, kd::NoGrow());
+}
+
+// the same through the pair-swap formulation of the build that knn.cu runs with one warp per node
+// (knn_body.cuh: build_pairs); depth_limit < 0: libstdc++'s own, 0..: forces the heap-select branch.
+// Returns the number of queries whose pending-node heap would have overflowed `qcap`.
+int host_kd_knn_pairs(const double *data, int n, const double *queries, int nq, int k, int depth_limit, int qcap,
+                      int *perm, int *out_idx) {
+    std::vector<int> idx(n > 0 ? n : 1), tidx(n > 0 ? n : 1), queue(n + 1), posA(n + 1), posB(n + 1);
+    std::vector<double> kx(n > 0 ? n : 1), ky(n > 0 ? n : 1);
+    std::vector<kd::Node> nodes(kd::max_nodes(n));
+    kd::Tree t;
+    t.data = data;
+    t.n = n;
+    t.idx = idx.data();
+    t.nodes = nodes.data();
+    kd::Tri a;
+    a.kx = kx.data(); a.ky = ky.data(); a.idx = tidx.data();
+    kd::build_pairs(t, a, posA.data(), posB.data(), queue.data(), depth_limit);
+    for (int i = 0; i < n; i++) perm[i] = idx[i];
+    if (qcap <= 0) qcap = t.nnodes + 1;
+    std::vector<kd::Item> nb(k);
+    std::vector<kd::NodeInfo> q(qcap);
+    int overflow = 0;
+    for (int i = 0; i < nq; i++)
+        overflow += !kd::query(t, queries[2 * (size_t)i], queries[2 * (size_t)i + 1], k, out_idx + (size_t)i * k,
+                               nb.data(), q.data(), qcap, kd::NoGrow());
+    return overflow;
 }
 
 // == b200_detect_outliers_ckdtree
@@ -50,14 +77,14 @@ void host_idw_fill_ckdtree(const double *xy, const double *vals, int npts, int n
     t.idx = idx.data();
     t.nodes = nodes.data();
     kd::build(t, stack.data());
-    std::vector<kd::Item> nb(k), q(t.nnodes + 1);
-    std::vector<kd::NodeInfo> pool(t.nnodes + 1);
+    std::vector<kd::Item> nb(k);
+    std::vector<kd::NodeInfo> q(t.nnodes + 1);
     std::vector<int> inds(k);
     std::vector<double> w(k);
     const size_t N = (size_t)ny * nx;
     for (int i = ny - 1; i >= 0; i--)
         for (int j = 0; j < nx; j++) {
-            kd::query(t, xgrid[j], ygrid[i], k, inds.data(), nb.data(), q.data(), pool.data(), w.data());
+            kd::query(t, xgrid[j], ygrid[i], k, inds.data(), nb.data(), q.data(), t.nnodes + 1, kd::NoGrow(), w.data());
             kd::idw_point(vals, nvar, inds.data(), w.data(), k, power, offset, mean_res, out + (size_t)i * nx + j, N);
         }
 }

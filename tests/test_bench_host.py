@@ -27,5 +27,25 @@ def test_workloads_and_metric_names():
         bench.set_workload(name)
         assert bench.M == w["m"] and bench.T_LEAD == w["T"] and bench.SCALING in ("weak", "strong")
         assert "Mpix/s" in bench.METRIC
-    bench.set_workload("lk_sl12_2048")
+    w = bench.set_workload("lk_sl12_2048")
     assert bench.MEMBERS == 0 and bench.workload_name(True) == "lk_dense+semilagrangian_T12_2048x2048"
+    # both arms print the same config dict (the driver compares them)
+    assert bench.config_of(w) == {"workload": "lk_dense+semilagrangian_T12_2048x2048", "frame": [2048, 2048],
+                                  "leadtimes": 12}
+    assert bench.workload_name(True, dict(bench.WORKLOADS["ensemble24"])) == \
+        "lk_dense+semilagrangian_24members_x12single_steps_2048x2048"
+
+
+def test_reference_arm_runs_with_all_host_threads_under_a_launcher(monkeypatch, capsys):
+    """torchrun exports OMP_NUM_THREADS=1; the reference arm sets the thread count explicitly and
+    reports it, on the same config as the CUDA arm."""
+    import types
+    monkeypatch.setenv("OMP_NUM_THREADS", "1")
+    monkeypatch.setenv("BENCH_REFERENCE_BUDGET_S", "1")
+    w = dict(bench.WORKLOADS["lk_sl12_2048"], name="tiny", m=256, n=256, T=2)
+    args = types.SimpleNamespace(steps=2, warmup=0, gpus=4)
+    assert bench.run_reference(args, w) == 0
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["config"] == bench.config_of(w)
+    assert line["cpu_baseline"]["cores"] == (os.cpu_count() or 1) and line["n_gpus"] == 4
+    assert line["value"] > 0 and line["e2e"]["value"] == line["value"]

@@ -140,14 +140,13 @@ def test_row_band_fill_and_stage_mirrors():
         assert np.array_equal(stages.idwinterp2d(dxy, duv, np.arange(96), np.arange(30, 70)), g[:, 30:70])
 
 
-def test_exact_ties_mode_reproduces_the_reference_sparse_vectors(monkeypatch):
-    """PYSTEPS_B200_EXACT_TIES=1 (csrc/knn.cu, opt-in until verified on hardware): with the outlier
-    stage taking neighbours in cKDTree's own order the sparse vectors equal the LIVE reference bit
-    for bit -- also on three-frame inputs whose pooled vectors coincide, where the default
-    lower-index rule can keep or drop a different vector."""
+def test_sparse_vectors_equal_the_live_reference():
+    """The outlier stage takes neighbours in cKDTree's own order (csrc/knn.cu; emulated here by the
+    kernel body compiled for the host): the sparse vectors equal the LIVE reference bit for bit --
+    also on three-frame inputs whose pooled vectors coincide, where a lower-index rule would keep
+    or drop a different vector."""
     from pysteps_b200.motion.lucaskanade import dense_lucaskanade
     live = _live()
-    monkeypatch.setenv("PYSTEPS_B200_EXACT_TIES", "1")
     rng = np.random.default_rng(2000)
     n = 0
     with cpu_abi.emulated():
@@ -169,15 +168,13 @@ def test_exact_ties_mode_reproduces_the_reference_sparse_vectors(monkeypatch):
     assert n >= 40
 
 
-def test_exact_ties_mode_reproduces_the_reference_dense_field(monkeypatch):
-    """... and the dense field equals the live reference at EVERY pixel to the last bits (np.power
-    vs pow), where the default mode differs by a bounded amount on the ~0.3 % of pixels with a
-    k-NN tie."""
+def test_dense_field_equals_the_live_reference_everywhere():
+    """... and the dense field equals the live reference at EVERY pixel to the last bits, pixels
+    with a k-NN tie included."""
     from pysteps_b200.motion.lucaskanade import dense_lucaskanade
     live = _live()
     if live is None:
         pytest.skip("/root/reference or cv2 not present")
-    monkeypatch.setenv("PYSTEPS_B200_EXACT_TIES", "1")
     rng = np.random.default_rng(2001)
     n = 0
     with cpu_abi.emulated():
@@ -215,10 +212,5 @@ def test_float32_frames_are_scaled_in_float32_like_the_reference():
             V = dense_lucaskanade(inp.copy())
             assert V.dtype == np.float64 and np.array_equal(V, ora.dense_lucaskanade(inp.copy())), it
             if live is not None:
-                os.environ["PYSTEPS_B200_EXACT_TIES"] = "1"
-                try:
-                    ref = live(inp.copy(), dense=False)
-                    got = dense_lucaskanade(inp.copy(), dense=False)
-                finally:
-                    del os.environ["PYSTEPS_B200_EXACT_TIES"]
+                ref = live(inp.copy(), dense=False)
                 assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]), it

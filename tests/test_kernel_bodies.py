@@ -183,6 +183,53 @@ def test_knn_body_matches_scipy_ckdtree(kind, n):
         assert np.array_equal(out, ref.query(queries, k=k)[1].reshape(len(queries), -1)), (kind, n, k)
 
 
+@pytest.mark.parametrize("kind", ["int", "half", "dup", "few_values", "real", "sorted", "const_x"])
+@pytest.mark.parametrize("n", [1, 17, 18, 33, 60, 400, 2000, 4096])
+def test_knn_pair_formulation_build_matches_scipy_ckdtree(kind, n):
+    """The build as knn.cu runs it -- libstdc++'s partition loops restated as pair swaps on
+    position-aligned (x, y, index) triples (knn_body.cuh: build_pairs) -- gives scipy's own tree
+    order and neighbour lists; with the introselect depth limit forced to 0..3 (heap-select branch)
+    it still equals the sequential restatement given the same limit... which libstdc++ pins for the
+    default limit only, so forced limits are compared on the k-NN SETS' distances."""
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(n * 7 + len(kind))
+    W = int(rng.choice([16, 64, 300, 2048]))
+    pts = np.floor(rng.uniform(0, W, (n, 2)))
+    if kind == "half":
+        pts = np.floor(rng.uniform(0, W, (n, 2)) * 2) / 2
+    elif kind == "dup" and n >= 8:
+        pts[: n // 4] = pts[n // 4: 2 * (n // 4)]
+    elif kind == "few_values":
+        pts = np.floor(rng.uniform(0, 4, (n, 2)))
+    elif kind == "real":
+        pts = rng.uniform(0, W, (n, 2))
+    elif kind == "sorted":
+        pts = pts[np.lexsort((pts[:, 1], pts[:, 0]))]
+    elif kind == "const_x":
+        pts[:, 0] = 7.0
+    pts = np.ascontiguousarray(pts)
+    L = host_kernels.lib()
+    L.host_kd_knn_pairs.restype = ctypes.c_int
+    ref = cKDTree(pts)
+    queries = np.ascontiguousarray(np.concatenate([pts[:200], np.floor(rng.uniform(-2, W + 2, (100, 2)))]))
+    for k in (2, 21, 31):
+        k = min(k, n)
+        perm = np.empty(n, np.int32)
+        out = np.empty((len(queries), k), np.int32)
+        ovf = L.host_kd_knn_pairs(_p(pts), n, _p(queries), len(queries), k, -1, 0, _p(perm), _p(out))
+        assert ovf == 0
+        assert np.array_equal(perm, ref.indices), (kind, n)
+        want_d, want_i = ref.query(queries, k=k)
+        assert np.array_equal(out, want_i.reshape(len(queries), -1)), (kind, n, k)
+        # the device query uses a 128-entry pending-node heap: never reached on these sets
+        assert L.host_kd_knn_pairs(_p(pts), n, _p(queries), len(queries), k, -1, 128, _p(perm), _p(out)) == 0
+        for depth in (0, 1, 3):  # heap-select branch: a valid tree (same neighbour distances)
+            L.host_kd_knn_pairs(_p(pts), n, _p(queries), len(queries), k, depth, 0, _p(perm), _p(out))
+            assert sorted(perm.tolist()) == list(range(n))
+            d = np.sqrt(((pts[out] - queries[:, None, :]) ** 2).sum(-1))
+            assert np.array_equal(d, want_d.reshape(len(queries), -1)), (kind, n, k, depth)
+
+
 def test_outlier_body_matches_the_reference_at_ties():
     """detect_outliers of the reference (scipy cKDTree + np.cov + np.linalg.inv) on vector sets with
     many equidistant and coincident positions: the body's flags equal the reference's (live when
