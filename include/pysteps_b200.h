@@ -292,7 +292,7 @@ int b200_idw_fill_ckdtree(const double *xy, const double *vals, const int *npts_
 /* ------------------------------------------------------------------------
  * Variational Echo Tracking -- replaces the native extension of the reference,
  * pysteps/motion/_vet.pyx.  The CG optimiser (scipy.optimize.minimize, vet.py:593-600)
- * stays on the host and calls b200_vet_cost once per cost / gradient evaluation.
+ * stays on the host; every point it visits costs one b200_vet_value_and_gradient call.
  * Note the reference's axis naming: axis 0 of the images is "x", axis 1 is "y"
  * (_vet.pyx:129-130); sector_disp is (2, xs, ys), images are (nx, ny), mask is int8.
  * ---------------------------------------------------------------------- */
@@ -303,6 +303,25 @@ int b200_idw_fill_ckdtree(const double *xy, const double *vals, const int *npts_
 int b200_vet_cost(const double *sector_disp, const double *templ, const double *input,
                   const int8_t *mask, int xs, int ys, int nx, int ny, float smooth_gain,
                   int gradient, double *out, void *stream);
+/* vet_cost_function AND vet_cost_function_gradient (vet.py:165-299) at the same point from one
+ * pass over the images -- what a line search asks for.  x_host: sector displacements (2, xs, ys)
+ * on the HOST; images (nframes, nx, ny) and mask (nx, ny) int8 on the device (2 or 3 frames: the
+ * pairs of vet.py:257-268, summed in its order); work: device scratch of 6 * xs * ys + 4 doubles.
+ * Returns value_host[0] = residuals, [1] = smoothness penalty (the cost is their sum) and
+ * gradient_host (2, xs, ys).  Synchronises the stream (the optimiser needs the numbers). */
+int b200_vet_value_and_gradient(const double *x_host, const double *images, int nframes,
+                                const int8_t *mask, int xs, int ys, int nx, int ny,
+                                float smooth_gain, double *work, double *value_host,
+                                double *gradient_host, void *stream);
+/* The image stack and mask of one minimisation level from the raw frames (vet.py:507-523 cleaning,
+ * :510-517 the global `padding` frame, :548-561 the level's divisibility padding): images
+ * (nframes, M, N) zero where a frame is invalid (user_mask set, or -- user_mask NULL -- not finite),
+ * edge-replicated into the level padding; mask (M, N) int8 = any frame invalid | global padding
+ * ring | level padding.  The level frame starts (pad_i_before, pad_j_before) before the globally
+ * padded input. */
+int b200_vet_level_images(const double *frames, const uint8_t *user_mask, int nframes, int m,
+                          int n, int padding, int pad_i_before, int pad_j_before, int M, int N,
+                          double *images, int8_t *mask, void *stream);
 /* _vet.pyx:66-232 _warp (vet.morph, vet.py:93-153): out, out_mask (int8) and, if grad is
  * not NULL, the gradient (2, nx, ny). */
 int b200_vet_warp(const double *image, const int8_t *mask, const double *displacement, int nx,

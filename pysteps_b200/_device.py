@@ -2,6 +2,7 @@
 pinned-host memory and as the owner of the CUDA stream; all arithmetic runs in
 the kernels of ``libpysteps_b200.so``."""
 import threading
+import weakref
 
 import numpy as np
 import torch
@@ -104,3 +105,64 @@ def to_host(t):
 
 def ptr(t):
     return None if t is None else t.data_ptr()
+
+
+# ---- device copies of results that were handed out as NumPy arrays ---------------------------
+# The plugin API is NumPy: motion.get_method("lk")(frames) returns an ndarray and the caller passes
+# that same ndarray to extrapolation.get_method("semilagrangian") (nowcasts/steps.py:656-664 with
+# the field of examples/plot_steps_nowcast.py:87).  The device tensor the array was downloaded from
+# is remembered under the array's identity, so the second call does not upload 64 MB (2048^2) that
+# are already in HBM.  Guards: the entry dies with the array (weakref), and a hit requires the same
+# object, shape, dtype, buffer address AND an unchanged sample of its contents (every
+# (size/16384)-th element) -- an array rewritten in place is uploaded again like any other array.
+# A rewrite that touches none of the sampled elements is not seen: call forget_results() after
+# editing a returned field in place at isolated pixels, or pass a copy.
+_recent = {}
+_recent_lock = threading.Lock()
+_RECENT_MAX = 8
+
+
+def _sample_fingerprint(a):
+    flat = a.reshape(-1)
+    step = max(1, flat.size // 16384)
+    return (a.shape, a.dtype.str, a.__array_interface__["data"][0], flat[::step].tobytes())
+
+
+def remember_result(host_array, tensor):
+    """Associate the NumPy result `host_array` with the device tensor it was copied from."""
+    key = id(host_array)
+
+    def _drop(_ref, key=key, d=_recent, lock=_recent_lock):  # globals are gone at interpreter exit
+        with lock:
+            d.pop(key, None)
+
+    try:
+        ref = weakref.ref(host_array, _drop)
+    except TypeError:
+        return host_array
+    with _recent_lock:
+        if len(_recent) >= _RECENT_MAX:
+            _recent.pop(next(iter(_recent)))
+        _recent[key] = (ref, _sample_fingerprint(host_array), tensor)
+    return host_array
+
+
+def recall_result(host_array):
+    """The device tensor of a remembered, unmodified NumPy result, else None."""
+    if not isinstance(host_array, np.ndarray):
+        return None
+    with _recent_lock:
+        hit = _recent.get(id(host_array))
+    if hit is None or hit[0]() is not host_array or not host_array.flags.c_contiguous:
+        return None
+    if hit[1] != _sample_fingerprint(host_array):
+        with _recent_lock:
+            _recent.pop(id(host_array), None)
+        return None
+    return hit[2]
+
+
+def forget_results():
+    """Drop every remembered device copy (after editing a returned array in place)."""
+    with _recent_lock:
+        _recent.clear()

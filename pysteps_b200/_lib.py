@@ -87,6 +87,10 @@ _SIGNATURES = {
                                       c_double, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "b200_vet_cost": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                               ctypes.c_float, c_int, c_void_p, c_void_p]),
+    "b200_vet_value_and_gradient": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                                            ctypes.c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200_vet_level_images": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                      c_void_p, c_void_p, c_void_p]),
     "b200_vet_warp": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
                               c_void_p]),
     "b200_zoom_bilinear": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

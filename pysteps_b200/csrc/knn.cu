@@ -18,7 +18,7 @@
 //                      permutation the sequential loops produce (knn_body.cuh: build_pairs is the
 //                      serial statement of it, pinned against scipy on the host), at ~n/32 steps per
 //                      pass instead of n.
-//   outliers_kernel    one thread per vector: scipy's query for its k+1 nearest, then the
+//   outliers_warp_kernel  one warp per vector: scipy's query for its k+1 nearest, then the
 //                      Mahalanobis test on them.
 //   idw_fix_kernel     the grid fill's exhaustive tile search (idw.cu) is order-free except where
 //                      the k-th and (k+1)-th neighbour are exactly equidistant; those grid points
@@ -224,6 +224,164 @@ __global__ void kd_build_serial_kernel(const double *__restrict__ xy, const int 
     }
 }
 
+// ---- one WARP per query -----------------------------------------------------------------------
+// A best-first search is one long dependent chain (heap sifts); threads of a warp running 32
+// different searches diverge at every branch and each pays for all (measured: 380 us for 1000
+// searches).  Here a warp runs ONE search: every lane executes the scalar control flow on the same
+// values (uniform, no divergence), lane 0 alone writes the heaps in shared memory, and the lanes
+// share the one data-parallel part -- the distances of a leaf's points.  The order of every
+// comparison, push and pop is scipy's (knn_body.cuh: query states it serially; the GPU tests pin
+// both against the oracle); the heap sifts carry the moving element in a register instead of
+// swapping, which visits the same positions with the same comparisons.
+constexpr int QW = 4;  // warps (queries in flight) per CTA
+
+struct WarpScratch {
+    kd::NodeInfo q[kdp::QHEAP];
+    kd::Item nb[kdp::NBSMEM];
+    double w[kdp::NBSMEM];
+    int inds[kdp::NBSMEM];
+};
+
+template <class T>
+__device__ __forceinline__ void wheap_push(T *h, int &n, const T &it, int lane) {
+    int i = n++;
+    while (i > 0 && kd::prio(it) < kd::prio(h[(i - 1) / 2])) {
+        if (lane == 0) h[i] = h[(i - 1) / 2];
+        i = (i - 1) / 2;
+    }
+    if (lane == 0) h[i] = it;
+    __syncwarp();
+}
+
+template <class T>
+__device__ __forceinline__ void wheap_remove(T *h, int &n, int lane) {
+    const T it = h[n - 1];
+    n--;
+    int i = 0, j = 1, k = 2;
+    while ((j < n && kd::prio(it) > kd::prio(h[j])) || (k < n && kd::prio(it) > kd::prio(h[k]))) {
+        const int l = (k < n && kd::prio(h[j]) > kd::prio(h[k])) ? k : j;
+        if (lane == 0) h[i] = h[l];
+        i = l;
+        j = 2 * i + 1;
+        k = 2 * i + 2;
+    }
+    if (lane == 0 && n > 0) h[i] = it;
+    __syncwarp();
+}
+
+// kd::query for one warp; out_idx / out_dist in shared memory.  Returns with the results visible
+// to every lane.
+__device__ void warp_query(const kd::Tree &t, const kdp::TreeBuf &tb, double x0, double x1, int kmax,
+                           WarpScratch &ws, bool want_dist, int lane) {
+    kd::NodeInfo *q = ws.q;
+    kd::Item *nb = ws.nb;
+    int qcap = kdp::QHEAP;
+    const double x[2] = {x0, x1};
+    int nbn = 0, qn = 0;
+    kd::NodeInfo cur;
+    cur.node = 0;
+    cur.min_distance = 0.0;
+    for (int c = 0; c < 2; c++) {
+        double s = x[c] - t.maxes[c];
+        const double s2 = t.mins[c] - x[c];
+        if (s2 > s) s = s2;
+        if (s < 0.0) s = 0.0;
+        cur.side[c] = s * s;
+        cur.min_distance += cur.side[c];
+    }
+    double dub = (double)INFINITY;
+    for (;;) {
+        const kd::Node node = t.nodes[cur.node];
+        if (node.split_dim == -1) {
+            for (int base = node.start; base < node.end; base += 32) {
+                const int i = base + lane;
+                const bool valid = i < node.end;
+                int pi = 0;
+                double d = (double)INFINITY;
+                if (valid) {
+                    pi = t.idx[i];
+                    const double dx = t.data[2 * (size_t)pi] - x[0], dy = t.data[2 * (size_t)pi + 1] - x[1];
+                    d = 0.0;
+                    d += dx * dx;
+                    d += dy * dy;
+                }
+                // candidates against the bound as it stands; each is re-tested in index order
+                // against the bound as the sequential loop would have it by then
+                unsigned m = __ballot_sync(FULL, valid && d < dub);
+                while (m) {
+                    const int l = __ffs(m) - 1;
+                    m &= m - 1;
+                    const double dl = __shfl_sync(FULL, d, l);
+                    const int pl = __shfl_sync(FULL, pi, l);
+                    if (dl < dub) {
+                        if (nbn == kmax) wheap_remove(nb, nbn, lane);
+                        kd::Item it;
+                        it.priority = -dl;
+                        it.payload = pl;
+                        wheap_push(nb, nbn, it, lane);
+                        if (nbn == kmax) dub = -nb[0].priority;
+                    }
+                }
+            }
+            if (qn == 0) break;
+            cur = q[0];
+            wheap_remove(q, qn, lane);
+        } else {
+            if (cur.min_distance > dub) break;
+            const int sd = node.split_dim;
+            kd::NodeInfo far = cur;
+            double s;
+            if (x[sd] < node.split) {
+                cur.node = node.less;
+                far.node = node.greater;
+                s = node.split - x[sd];
+            } else {
+                cur.node = node.greater;
+                far.node = node.less;
+                s = x[sd] - node.split;
+            }
+            s = s * s;
+            far.min_distance += s - far.side[sd];
+            far.side[sd] = s;
+            if (cur.min_distance > far.min_distance) {
+                const kd::NodeInfo tmp = cur;
+                cur = far;
+                far = tmp;
+            }
+            if (far.min_distance <= dub) {
+                if (qn == qcap) {  // rare: move the pending nodes to a node-count sized piece of the arena
+                    const int need = tb.meta[0];
+                    int off = 0;
+                    if (lane == 0) off = atomicAdd(&tb.meta[2], need);
+                    off = __shfl_sync(FULL, off, 0);
+                    if (qcap >= need || off + need > kdp::ARENA) __trap();
+                    kd::NodeInfo *big = tb.arena + off;
+                    for (int e = lane; e < qn; e += 32) big[e] = q[e];
+                    __syncwarp();
+                    q = big;
+                    qcap = need;
+                }
+                wheap_push(q, qn, far, lane);
+            }
+        }
+    }
+    const int found = nbn;
+    for (int i = found - 1; i >= 0; i--) {
+        const kd::Item top = nb[0];
+        if (lane == 0) {
+            ws.inds[i] = top.payload;
+            if (want_dist) ws.w[i] = sqrt(-top.priority);
+        }
+        wheap_remove(nb, nbn, lane);
+    }
+    if (lane == 0)
+        for (int i = found; i < kmax; i++) {
+            ws.inds[i] = t.n;
+            if (want_dist) ws.w[i] = (double)INFINITY;
+        }
+    __syncwarp();
+}
+
 struct OutlierParams {
     const double *xy, *uv;
     int k;
@@ -235,25 +393,42 @@ struct OutlierParams {
     uint8_t *out;
 };
 
-// one thread per vector: scipy's query for its k+1 nearest, Mahalanobis test on them
-template <bool SMEM>
-__global__ void __launch_bounds__(kdp::QTHREADS)
-outliers_kernel(const __grid_constant__ OutlierParams p) {
-    extern __shared__ __align__(16) unsigned char q_smem[];
+// one warp per vector: scipy's query for its k+1 nearest, Mahalanobis test on them
+__global__ void __launch_bounds__(32 * QW)
+outliers_warp_kernel(const __grid_constant__ OutlierParams p) {
+    __shared__ WarpScratch scratch[QW];
     const int n = p.tb.meta[1];
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= n) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int v = blockIdx.x * QW + wid;
+    if (v >= n) return;
     if (n < 2) {  // cleansing.py:178-179
-        p.out[tid] = 0;
+        if (lane == 0) p.out[v] = 0;
         return;
     }
     const int kk = min(p.k + 1, n);  // :197
     const kd::Tree t = kdp::tree_of(p.tb, p.xy);
-    int local_inds[SMEM ? kdp::NBSMEM : 1];
-    int *inds = SMEM ? local_inds : p.inds + (size_t)tid * (p.k + 1);
-    const kdp::QueryHeaps h = kdp::query_heaps<SMEM>(q_smem, p.nb, p.q, (size_t)tid, p.k + 1);
+    WarpScratch &ws = scratch[wid];
+    warp_query(t, p.tb, p.xy[2 * (size_t)v], p.xy[2 * (size_t)v + 1], kk, ws, false, lane);
+    if (lane == 0) p.out[v] = kd::mahalanobis_outlier(p.uv, v, ws.inds, kk - 1, p.thr) ? 1 : 0;
+}
+
+// general neighbour count: one thread per vector, heaps in global scratch
+__global__ void __launch_bounds__(kdp::QTHREADS)
+outliers_kernel(const __grid_constant__ OutlierParams p) {
+    const int n = p.tb.meta[1];
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= n) return;
+    if (n < 2) {
+        p.out[tid] = 0;
+        return;
+    }
+    const int kk = min(p.k + 1, n);
+    const kd::Tree t = kdp::tree_of(p.tb, p.xy);
+    int *inds = p.inds + (size_t)tid * (p.k + 1);
+    kd::Strided<kd::Item> nb{p.nb + (size_t)tid * (p.k + 1), 1};
+    kd::Strided<kd::NodeInfo> q{p.q + (size_t)tid * kdp::QHEAP, 1};
     kdp::ArenaGrow grow(p.tb);
-    kd::query(t, p.xy[2 * (size_t)tid], p.xy[2 * (size_t)tid + 1], kk, inds, h.nb, h.q, kdp::QHEAP, grow);
+    kd::query(t, p.xy[2 * (size_t)tid], p.xy[2 * (size_t)tid + 1], kk, inds, nb, q, kdp::QHEAP, grow);
     p.out[tid] = kd::mahalanobis_outlier(p.uv, tid, inds, kk - 1, p.thr) ? 1 : 0;
 }
 
@@ -271,12 +446,31 @@ struct IdwFixParams {
     double *out;           // (nvar, ny, nx)
 };
 
-// scipy's query and numpy's weighting (knn_body.cuh: idw_point) for the listed grid points; a
-// fixed number of threads strides over the list
-template <bool SMEM>
+// scipy's query and numpy's weighting (knn_body.cuh: idw_point) for the listed grid points, one
+// warp per grid point at a time
+__global__ void __launch_bounds__(32 * QW)
+idw_fix_warp_kernel(const __grid_constant__ IdwFixParams p) {
+    __shared__ WarpScratch scratch[QW];
+    const int n = p.tb.meta[1];
+    const int k = min(p.k, n);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const size_t warp = (size_t)blockIdx.x * QW + wid, nwarps = (size_t)gridDim.x * QW;
+    const size_t N = (size_t)p.ny * p.nx;
+    const size_t count = p.list_count ? (size_t)min(*p.list_count, (int)min(N, (size_t)0x7fffffff)) : N;
+    if (k < 1) return;
+    const kd::Tree t = kdp::tree_of(p.tb, p.xy);
+    WarpScratch &ws = scratch[wid];
+    for (size_t e = warp; e < count; e += nwarps) {
+        const size_t g = p.list_count ? (size_t)p.list[e] : e;
+        const int i = (int)(g / p.nx), j = (int)(g % p.nx);
+        warp_query(t, p.tb, p.xgrid[j], p.ygrid[i], k, ws, true, lane);
+        if (lane == 0) kd::idw_point(p.vals, p.nvar, ws.inds, ws.w, k, p.power, p.offset, p.mean_res, p.out + g, N);
+        __syncwarp();
+    }
+}
+
 __global__ void __launch_bounds__(kdp::QTHREADS)
 idw_fix_kernel(const __grid_constant__ IdwFixParams p) {
-    extern __shared__ __align__(16) unsigned char q_smem[];
     const int n = p.tb.meta[1];
     const int k = min(p.k, n);
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -285,16 +479,15 @@ idw_fix_kernel(const __grid_constant__ IdwFixParams p) {
     const size_t count = p.list_count ? (size_t)min(*p.list_count, (int)min(N, (size_t)0x7fffffff)) : N;
     if (k < 1) return;
     const kd::Tree t = kdp::tree_of(p.tb, p.xy);
-    int local_inds[SMEM ? kdp::NBSMEM : 1];
-    double local_w[SMEM ? kdp::NBSMEM : 1];
-    int *inds = SMEM ? local_inds : p.inds + tid * p.k;
-    double *w = SMEM ? local_w : p.w + tid * p.k;
+    int *inds = p.inds + tid * p.k;
+    double *w = p.w + tid * p.k;
     for (size_t e = tid; e < count; e += nthreads) {
         const size_t g = p.list_count ? (size_t)p.list[e] : e;
         const int i = (int)(g / p.nx), j = (int)(g % p.nx);
-        const kdp::QueryHeaps h = kdp::query_heaps<SMEM>(q_smem, p.nb, p.q, tid, p.k);
+        kd::Strided<kd::Item> nb{p.nb + tid * p.k, 1};
+        kd::Strided<kd::NodeInfo> q{p.q + tid * kdp::QHEAP, 1};
         kdp::ArenaGrow grow(p.tb);
-        kd::query(t, p.xgrid[j], p.ygrid[i], k, inds, h.nb, h.q, kdp::QHEAP, grow, w);
+        kd::query(t, p.xgrid[j], p.ygrid[i], k, inds, nb, q, kdp::QHEAP, grow, w);
         kd::idw_point(p.vals, p.nvar, inds, w, k, p.power, p.offset, p.mean_res, p.out + g, N);
     }
 }
@@ -342,15 +535,15 @@ int idw_fix(const double *xy, const double *vals, int nvar, int k, double power,
     p.power = power; p.offset = dist_offset; p.mean_res = mean_res; p.tb = tb;
     p.list = list; p.list_count = list_count; p.out = out;
     const size_t N = (size_t)ny * nx;
-    const int T = QTHREADS;
-    const int blocks = (int)std::max<size_t>(1, std::min<size_t>((N + T - 1) / T, (size_t)b200::num_sms() * 2));
     if (k <= NBSMEM) {
-        B200_CUDA(cudaFuncSetAttribute(idw_fix_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)QUERY_SMEM));
-        idw_fix_kernel<true><<<blocks, T, QUERY_SMEM, s>>>(p);
+        // as many warps as the chip holds (one search each); the list is usually shorter
+        const int blocks = (int)std::max<size_t>(1, std::min<size_t>((N + QW - 1) / QW, (size_t)b200::num_sms() * 12));
+        idw_fix_warp_kernel<<<blocks, 32 * QW, 0, s>>>(p);
         B200_LAUNCH_CHECK();
         return 0;
     }
+    const int T = QTHREADS;
+    const int blocks = (int)std::max<size_t>(1, std::min<size_t>((N + T - 1) / T, (size_t)b200::num_sms() * 2));
     const size_t nthreads = (size_t)blocks * T;
     b200::Scratch inds, w, nb, q;
     B200_CUDA(inds.alloc(sizeof(int) * nthreads * k, s));
@@ -358,7 +551,7 @@ int idw_fix(const double *xy, const double *vals, int nvar, int k, double power,
     B200_CUDA(nb.alloc(sizeof(kd::Item) * nthreads * k, s));
     B200_CUDA(q.alloc(sizeof(kd::NodeInfo) * nthreads * QHEAP, s));
     p.inds = (int *)inds.p; p.w = (double *)w.p; p.nb = (kd::Item *)nb.p; p.q = (kd::NodeInfo *)q.p;
-    idw_fix_kernel<false><<<blocks, T, 0, s>>>(p);
+    idw_fix_kernel<<<blocks, T, 0, s>>>(p);
     B200_LAUNCH_CHECK();
     return 0;
 }
@@ -404,20 +597,18 @@ extern "C" int b200_detect_outliers(const double *uv, const double *xy, const in
     OutlierParams p;
     memset(&p, 0, sizeof(p));
     p.xy = xy; p.uv = uv; p.k = k; p.thr = thr; p.tb = ts.tb; p.out = out;
-    const int T = kdp::QTHREADS;
     if (k + 1 <= kdp::NBSMEM) {
-        B200_CUDA(cudaFuncSetAttribute(outliers_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)kdp::QUERY_SMEM));
-        outliers_kernel<true><<<b200::ceil_div(n_cap, T), T, kdp::QUERY_SMEM, s>>>(p);
+        outliers_warp_kernel<<<b200::ceil_div(n_cap, QW), 32 * QW, 0, s>>>(p);
         B200_LAUNCH_CHECK();
         return 0;
     }
+    const int T = kdp::QTHREADS;
     b200::Scratch inds, nb, q;
     B200_CUDA(inds.alloc(sizeof(int) * (size_t)n_cap * (k + 1), s));
     B200_CUDA(nb.alloc(sizeof(kd::Item) * (size_t)n_cap * (k + 1), s));
     B200_CUDA(q.alloc(sizeof(kd::NodeInfo) * (size_t)n_cap * kdp::QHEAP, s));
     p.inds = (int *)inds.p; p.nb = (kd::Item *)nb.p; p.q = (kd::NodeInfo *)q.p;
-    outliers_kernel<false><<<b200::ceil_div(n_cap, T), T, 0, s>>>(p);
+    outliers_kernel<<<b200::ceil_div(n_cap, T), T, 0, s>>>(p);
     B200_LAUNCH_CHECK();
     return 0;
 }

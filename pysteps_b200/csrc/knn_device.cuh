@@ -64,32 +64,6 @@ struct ArenaGrow {
     }
 };
 
-// per-thread heaps of a query CTA: interleaved across the QTHREADS threads in shared memory (the
-// same entry of neighbouring threads is contiguous: conflict-free when the threads move alike),
-// or -- neighbour lists longer than NBSMEM -- plain per-thread arrays in global scratch
-struct QueryHeaps {
-    kd::Strided<kd::Item> nb;
-    kd::Strided<kd::NodeInfo> q;
-};
-constexpr size_t QUERY_SMEM = (size_t)QTHREADS * (NBSMEM * sizeof(kd::Item) + QHEAP * sizeof(kd::NodeInfo));
-
-template <bool SMEM>
-__device__ __forceinline__ QueryHeaps query_heaps(unsigned char *smem, kd::Item *nb_glob, kd::NodeInfo *q_glob,
-                                                  size_t tid, int kmax) {
-    QueryHeaps h;
-    if (SMEM) {
-        h.nb.p = reinterpret_cast<kd::Item *>(smem) + threadIdx.x;
-        h.nb.stride = QTHREADS;
-        h.q.p = reinterpret_cast<kd::NodeInfo *>(smem + (size_t)QTHREADS * NBSMEM * sizeof(kd::Item)) + threadIdx.x;
-        h.q.stride = QTHREADS;
-    } else {
-        h.nb.p = nb_glob + tid * kmax;
-        h.nb.stride = 1;
-        h.q.p = q_glob + tid * QHEAP;
-        h.q.stride = 1;
-    }
-    return h;
-}
 #endif
 
 int tree_alloc(TreeScratch &ts, int n_cap, cudaStream_t s);

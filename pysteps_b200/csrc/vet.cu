@@ -19,6 +19,8 @@
 // finalising kernel adds, per sector, the <= 4 adjacent cells in the reference's loop order.
 #include <math_constants.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace {
@@ -94,13 +96,15 @@ __device__ __forceinline__ void block_reduce(double (&v)[NV], double *sm /* NV *
         }
 }
 
-// grid = (strips, ncx * ncy).  GRAD = false: partial[cell][strip] = sum of squared residuals.
-// GRAD = true: partial[cell][strip][corner k][axis a] = sum g_a * coef_k.
-template <bool GRAD>
+// grid = (strips, ncx * ncy).  MODE 0: partial[cell][strip] = sum of squared residuals.
+// MODE 1: partial[cell][strip][corner k][axis a] = sum g_a * coef_k.  MODE 2: both from ONE pass
+// over the images (entries 0..7 the gradient sums, entry 8 the residual sum) -- a line search
+// asks for value and slope at the same point.
+template <int MODE>
 __global__ void __launch_bounds__(VET_THREADS)
 vet_eval_kernel(const double *__restrict__ sd, const double *__restrict__ templ, const double *__restrict__ input,
                 const int8_t *__restrict__ mask, const VetGeom g, double *__restrict__ partial) {
-    __shared__ double sm[8 * 8];
+    __shared__ double sm[9 * 8];
     const int cell = blockIdx.y, strip = blockIdx.x;
     const int l0 = cell / g.ncy, m0 = cell - l0 * g.ncy, l1 = l0 + 1, m1 = m0 + 1;
     const int i_beg = cell_start(l0, g.i_shift, g.xss), i_end = cell_end(l0, g.i_shift, g.xss, g.xs, g.nx);
@@ -120,7 +124,9 @@ vet_eval_kernel(const double *__restrict__ sd, const double *__restrict__ templ,
         s10[a] = sd[a * S + (size_t)l1 * g.ys + m0];
         s11[a] = sd[a * S + (size_t)l1 * g.ys + m1];
     }
-    constexpr int NV = GRAD ? 8 : 1;
+    constexpr bool GRAD = MODE >= 1, COST = MODE != 1;
+    constexpr int NV = MODE == 0 ? 1 : (MODE == 1 ? 8 : 9);
+    constexpr int CI = MODE == 0 ? 0 : 8;  // slot of the residual sum
     double acc[NV];
 #pragma unroll
     for (int k = 0; k < NV; k++) acc[k] = 0.0;
@@ -146,12 +152,13 @@ vet_eval_kernel(const double *__restrict__ sd, const double *__restrict__ templ,
         const Warped w = warp_pixel(templ, mask, g.nx, g.ny, i, j, disp[0], disp[1]);
         const size_t idx = (size_t)i * g.ny + j;
         const bool mm = w.masked || mask[idx] > 0;  // :493 / :554
-        if (!GRAD) {
+        if (COST) {
             if (!mm) {
                 const double r = __dsub_rn(w.value, input[idx]);
-                acc[0] = __dadd_rn(acc[0], __dmul_rn(r, r));
+                acc[CI] = __dadd_rn(acc[CI], __dmul_rn(r, r));
             }
-        } else {
+        }
+        if (GRAD) {
             // the reference's row range [i_min, i_max) stops one row short of the band (:466-476)
             if (i < i_end - 1) {
                 const double b = mm ? 0.0 : __dmul_rn(2.0, __dsub_rn(input[idx], w.value));
@@ -190,11 +197,12 @@ __device__ __forceinline__ Deriv second_diff(const double *__restrict__ S, int l
 
 // cost: out[0] = residuals (fixed-order sum of the partials), out[1] = smoothness penalty
 __global__ void __launch_bounds__(VET_THREADS)
-vet_final_cost_kernel(const double *__restrict__ partial, int nparts, const double *__restrict__ sd,
-                      const VetGeom g, double smooth_gain, double *__restrict__ out) {
+vet_final_cost_kernel(const double *__restrict__ partial, int nparts, int nv, int off,
+                      const double *__restrict__ sd, const VetGeom g, double smooth_gain,
+                      double *__restrict__ out) {
     __shared__ double sm[2 * 8];
     double v[2] = {0.0, 0.0};
-    for (int i = threadIdx.x; i < nparts; i += VET_THREADS) v[0] = __dadd_rn(v[0], partial[i]);
+    for (int i = threadIdx.x; i < nparts; i += VET_THREADS) v[0] = __dadd_rn(v[0], partial[(size_t)i * nv + off]);
     if (smooth_gain > 0.0) {
         const int ni = max(g.xs - 2, 0) * max(g.ys - 2, 0);
         for (int t = threadIdx.x; t < 2 * ni; t += VET_THREADS) {
@@ -214,7 +222,7 @@ vet_final_cost_kernel(const double *__restrict__ partial, int nparts, const doub
 
 // gradient: out (2, xs, ys) = grad_residuals + 2 * smooth_gain * grad_smooth
 __global__ void __launch_bounds__(VET_THREADS)
-vet_final_grad_kernel(const double *__restrict__ partial, const double *__restrict__ sd, const VetGeom g,
+vet_final_grad_kernel(const double *__restrict__ partial, int nv, const double *__restrict__ sd, const VetGeom g,
                       double smooth_gain, double *__restrict__ out) {
     const int t = blockIdx.x * VET_THREADS + threadIdx.x;
     const int S = g.xs * g.ys;
@@ -228,7 +236,7 @@ vet_final_grad_kernel(const double *__restrict__ partial, const double *__restri
     for (int k = 0; k < 4; k++) {
         if (cl[k] < 0 || cl[k] >= g.ncx || cm[k] < 0 || cm[k] >= g.ncy) continue;
         const size_t cell = (size_t)cl[k] * g.ncy + cm[k];
-        for (int s = 0; s < g.strips; s++) gr = __dadd_rn(gr, partial[(cell * g.strips + s) * 8 + 2 * k + a]);
+        for (int s = 0; s < g.strips; s++) gr = __dadd_rn(gr, partial[(cell * g.strips + s) * nv + 2 * k + a]);
     }
     double gs = 0.0;
     if (smooth_gain > 0.0) {
@@ -291,9 +299,11 @@ zoom_kernel(const double *__restrict__ a, int c, int h, int w, int oh, int ow, d
 
 }  // namespace
 
-extern "C" int b200_vet_cost(const double *sector_disp, const double *templ, const double *input,
-                             const int8_t *mask, int xs, int ys, int nx, int ny, float smooth_gain,
-                             int gradient, double *out, void *stream) {
+// mode 0: out = {residuals, smoothness}; 1: out = gradient (2, xs, ys); 2: out = {residuals,
+// smoothness, gradient...} from one pass over the images
+static int vet_launch(int mode, const double *sector_disp, const double *templ, const double *input,
+                      const int8_t *mask, int xs, int ys, int nx, int ny, float smooth_gain, double *out,
+                      cudaStream_t s) {
     B200_REQUIRE(sector_disp && templ && input && mask && out, "bad arguments");
     B200_REQUIRE(xs >= 2 && ys >= 2 && nx >= 1 && ny >= 1, "need at least 2 x 2 sectors");
     if (nx % xs != 0 || ny % ys != 0) {
@@ -310,25 +320,113 @@ extern "C" int b200_vet_cost(const double *sector_disp, const double *templ, con
     // enough CTAs to cover the chip a few times whatever the sector count (2x2 .. 32x32)
     const int want = b200::num_sms() * 8;
     g.strips = std::max(1, std::min((want + ncells - 1) / ncells, std::max(g.xss / 2, 1)));
-    cudaStream_t s = (cudaStream_t)stream;
-    const int nv = gradient ? 8 : 1;
+    const int nv = mode == 0 ? 1 : (mode == 1 ? 8 : 9);
     b200::Scratch part;
     B200_CUDA(part.alloc(sizeof(double) * (size_t)ncells * g.strips * nv, s));
     dim3 grid(g.strips, ncells);
     const double gain = (double)smooth_gain;  // C float parameter of the reference (:242)
-    if (gradient) {
-        vet_eval_kernel<true><<<grid, VET_THREADS, 0, s>>>(sector_disp, templ, input, mask, g, (double *)part.p);
-        B200_LAUNCH_CHECK();
-        vet_final_grad_kernel<<<b200::ceil_div(2 * xs * ys, VET_THREADS), VET_THREADS, 0, s>>>(
-            (const double *)part.p, sector_disp, g, gain, out);
-        B200_LAUNCH_CHECK();
-    } else {
-        vet_eval_kernel<false><<<grid, VET_THREADS, 0, s>>>(sector_disp, templ, input, mask, g, (double *)part.p);
-        B200_LAUNCH_CHECK();
-        vet_final_cost_kernel<<<1, VET_THREADS, 0, s>>>((const double *)part.p, ncells * g.strips, sector_disp, g,
+    double *P = (double *)part.p;
+    if (mode == 0) vet_eval_kernel<0><<<grid, VET_THREADS, 0, s>>>(sector_disp, templ, input, mask, g, P);
+    else if (mode == 1) vet_eval_kernel<1><<<grid, VET_THREADS, 0, s>>>(sector_disp, templ, input, mask, g, P);
+    else vet_eval_kernel<2><<<grid, VET_THREADS, 0, s>>>(sector_disp, templ, input, mask, g, P);
+    B200_LAUNCH_CHECK();
+    if (mode != 1) {
+        vet_final_cost_kernel<<<1, VET_THREADS, 0, s>>>(P, ncells * g.strips, nv, mode == 0 ? 0 : 8, sector_disp, g,
                                                       gain, out);
         B200_LAUNCH_CHECK();
     }
+    if (mode != 0) {
+        vet_final_grad_kernel<<<b200::ceil_div(2 * xs * ys, VET_THREADS), VET_THREADS, 0, s>>>(
+            P, nv, sector_disp, g, gain, mode == 1 ? out : out + 2);
+        B200_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+extern "C" int b200_vet_cost(const double *sector_disp, const double *templ, const double *input,
+                             const int8_t *mask, int xs, int ys, int nx, int ny, float smooth_gain,
+                             int gradient, double *out, void *stream) {
+    return vet_launch(gradient ? 1 : 0, sector_disp, templ, input, mask, xs, ys, nx, ny, smooth_gain, out,
+                      (cudaStream_t)stream);
+}
+
+extern "C" int b200_vet_value_and_gradient(const double *x_host, const double *images, int nframes,
+                                           const int8_t *mask, int xs, int ys, int nx, int ny,
+                                           float smooth_gain, double *work, double *value_host,
+                                           double *gradient_host, void *stream) {
+    B200_REQUIRE(x_host && images && mask && work && value_host && gradient_host, "bad arguments");
+    B200_REQUIRE(nframes == 2 || nframes == 3, "two or three frames");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t S = (size_t)2 * xs * ys, N = (size_t)nx * ny;
+    // work: x (S) | pair 0 {residuals, smoothness, gradient (S)} | pair 1 {...}
+    double *dx = work, *r0 = work + S, *r1 = r0 + 2 + S;
+    B200_CUDA(cudaMemcpyAsync(dx, x_host, S * sizeof(double), cudaMemcpyHostToDevice, s));
+    // vet.py:257-268: (centre, next), then -- three frames -- (previous, centre)
+    const double *a = images + (nframes == 3 ? N : 0), *b = a + N;
+    if (int rc = vet_launch(2, dx, a, b, mask, xs, ys, nx, ny, smooth_gain, r0, s)) return rc;
+    if (nframes == 3)
+        if (int rc = vet_launch(2, dx, images, images + N, mask, xs, ys, nx, ny, smooth_gain, r1, s)) return rc;
+    // one read-back of everything; the sums over the pairs in the reference's order on the host
+    static thread_local std::vector<double> stage;
+    stage.resize((size_t)(nframes == 3 ? 2 : 1) * (2 + S));
+    B200_CUDA(cudaMemcpyAsync(stage.data(), r0, stage.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    B200_CUDA(cudaStreamSynchronize(s));
+    double residuals = stage[0], smoothness = stage[1];
+    const double *g0 = stage.data() + 2;
+    if (nframes == 3) {
+        const double *p1 = stage.data() + 2 + S;
+        residuals += p1[0];    // :263-268
+        smoothness += p1[1];
+        for (size_t i = 0; i < S; i++) gradient_host[i] = g0[i] + p1[2 + i];  // :288-293
+    } else {
+        for (size_t i = 0; i < S; i++) gradient_host[i] = g0[i];
+    }
+    value_host[0] = residuals;
+    value_host[1] = smoothness;
+    return 0;
+}
+
+// One kernel per minimisation level: cleaning (vet.py:507-523), the global `padding` frame and the
+// level's divisibility padding (:548-561) from the raw frames.
+//   valid(t, pixel)  = user mask clear when a mask is given, else the value is finite
+//   image[t]         = the frame where valid, 0 elsewhere; outside the globally padded frame the
+//                      nearest edge value of it (numpy.pad "edge")
+//   mask             = 1 where any frame is invalid, in the global padding ring, and in the level's
+//                      own padding (constant 1)
+__global__ void __launch_bounds__(256)
+vet_level_kernel(const double *__restrict__ frames, const uint8_t *__restrict__ umask, int T, int m, int n,
+                 int gpad, int pi0, int pj0, int M, int N, double *__restrict__ out, int8_t *__restrict__ omask) {
+    const int J = blockIdx.x * 32 + threadIdx.x, I = blockIdx.y * 8 + threadIdx.y;
+    if (I >= M || J >= N) return;
+    const int mg = m + 2 * gpad, ng = n + 2 * gpad;
+    const bool inside = I >= pi0 && I < pi0 + mg && J >= pj0 && J < pj0 + ng;
+    const int ii = min(max(I - pi0, 0), mg - 1), jj = min(max(J - pj0, 0), ng - 1);
+    const int si = ii - gpad, sj = jj - gpad;
+    const bool in_src = si >= 0 && si < m && sj >= 0 && sj < n;
+    bool any_bad = false;
+    for (int t = 0; t < T; t++) {
+        double v = 0.0;
+        bool bad = true;
+        if (in_src) {
+            const size_t idx = ((size_t)t * m + si) * n + sj;
+            v = frames[idx];
+            bad = umask ? umask[idx] != 0 : !isfinite(v);
+        }
+        any_bad |= bad;
+        out[((size_t)t * M + I) * N + J] = bad ? 0.0 : v;
+    }
+    omask[(size_t)I * N + J] = (!inside || any_bad) ? 1 : 0;
+}
+
+extern "C" int b200_vet_level_images(const double *frames, const uint8_t *user_mask, int nframes, int m,
+                                     int n, int padding, int pad_i_before, int pad_j_before, int M, int N,
+                                     double *images, int8_t *mask, void *stream) {
+    B200_REQUIRE(frames && images && mask && nframes >= 1 && m >= 1 && n >= 1 && padding >= 0, "bad arguments");
+    B200_REQUIRE(pad_i_before >= 0 && pad_j_before >= 0 && M >= m + 2 * padding + pad_i_before &&
+                     N >= n + 2 * padding + pad_j_before, "level frame smaller than the padded input");
+    vet_level_kernel<<<dim3(b200::ceil_div(N, 32), b200::ceil_div(M, 8)), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+        frames, user_mask, nframes, m, n, padding, pad_i_before, pad_j_before, M, N, images, mask);
+    B200_LAUNCH_CHECK();
     return 0;
 }
 

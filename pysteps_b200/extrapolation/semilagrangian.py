@@ -60,6 +60,9 @@ def _field_tensor(a):
     if isinstance(a, torch.Tensor):
         dt = a.dtype
     else:
+        kept = _device.recall_result(a)  # a field this package returned: still in HBM
+        if kept is not None:
+            return kept
         a = np.asarray(a)
         dt = a.dtype
     if dt in (np.float32, torch.float32):

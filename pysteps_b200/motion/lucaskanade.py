@@ -372,4 +372,4 @@ def dense_lucaskanade(input_images, lk_kwargs=None, fd_method="shitomasi", fd_kw
     if verbose:
         torch.cuda.current_stream().synchronize()
         print("--- total time: %.2f seconds ---" % (time.time() - t0))
-    return out if on_device else _device.to_host(out)
+    return out if on_device else _device.remember_result(_device.to_host(out), out)

@@ -1,97 +1,155 @@
 """B200 Variational Echo Tracking -- drop-in for ``pysteps.motion.vet``
-(pysteps/motion/vet.py:93-648).
+(pysteps/motion/vet.py:93-648; native extension pysteps/motion/_vet.pyx -> csrc/vet.cu).
 
-The reference splits VET into a Python driver (masking, padding, sector pyramid,
-``scipy.optimize.minimize`` CG loop, ``scipy.ndimage.zoom`` upsampling) and a native
-extension (``_vet.pyx``: ``_warp`` and ``_cost_function``).  Here the driver is mirrored in
-Python, the optimiser stays SciPy's, and the native extension is ``csrc/vet.cu``: each
-cost / gradient evaluation of the ~1000 the optimiser requests is one fused kernel over the
-device-resident image pair plus a tiny finalising kernel (``b200_vet_cost``); per evaluation
-the host sends <= 2*32*32 sector displacements and reads back a scalar or that many
-gradient values.  The final full-resolution zoom runs on the device (``b200_zoom_bilinear``).
+Design (not the reference's control flow):
+
+* The raw frames are uploaded ONCE.  Every minimisation level derives its image stack and mask
+  from them on the device in one kernel (``b200_vet_level_images``: NaN / user-mask cleaning,
+  the global ``padding`` ring and the level's divisibility padding) -- nothing of image size is
+  built on the host, and a level whose padding equals an earlier one reuses that stack.
+* The objective is evaluated as a PAIR: value and gradient at the same point from one pass over
+  the images (``b200_vet_value_and_gradient``: one kernel per frame pair + two tiny finalisers,
+  one 16 KB upload, one read-back).  A line search asks for both at every trial step, so the
+  ~800 separate cost / gradient evaluations of a 2048^2 field become ~400 fused ones.
+  ``_Objective`` memoises the last point; SciPy's CG (the optimiser the reference uses,
+  vet.py:593-600 -- same iterates, same stopping rule) sees an ordinary ``fun`` / ``jac``.
+* Sector fields move between levels through the device zoom (``b200_zoom_bilinear``,
+  bit-identical to ``scipy.ndimage.zoom(order=1, mode="nearest")``), the final field is zoomed,
+  cropped and flipped on the device and crosses PCIe once.
 """
 import numpy
 import torch
 from numpy.ma.core import MaskedArray
-from scipy.ndimage import zoom
 from scipy.optimize import minimize
 
 from .. import _device, _lib
 
+_INDEXING = ("yx", "xy", "ij")
+
 
 def round_int(scalar):
-    """Round number to nearest integer (vet.py:41-45)."""
     return int(numpy.round(scalar))
 
 
 def ceil_int(scalar):
-    """Round number up to the nearest integer (vet.py:48-52)."""
     return int(numpy.ceil(scalar))
 
 
 def get_padding(dimension_size, sectors):
-    """Padding before/after so that `sectors` divides the dimension (vet.py:55-90)."""
-    reminder = dimension_size % sectors
-    if reminder != 0:
-        pad = sectors - reminder
-        pad_before = pad // 2
-        if pad % 2 == 0:
-            pad_after = pad_before
-        else:
-            pad_after = pad_before + 1
-        return pad_before, pad_after
-    return 0, 0
+    """(before, after) so that `sectors` divides the padded size; the odd cell goes after
+    (vet.py:55-90)."""
+    missing = (-int(dimension_size)) % int(sectors)
+    return missing // 2, missing - missing // 2
+
+
+def _stream():
+    return _device.stream_ptr()
 
 
 def morph(image, displacement, gradient=False):
     """Morph an image by a displacement field (vet.py:93-153 -> _vet._warp).
     Returns (image, mask) or (image, mask, gradient) as NumPy arrays."""
     _device.require_cuda()
-    if not isinstance(image, MaskedArray):
-        _mask = numpy.zeros_like(image, dtype="int8")
-    else:
-        _mask = numpy.asarray(numpy.ma.getmaskarray(image), dtype="int8", order="C")
-    _image = numpy.asarray(image, dtype="float64", order="C")
-    _displacement = numpy.asarray(displacement, dtype="float64", order="C")
-    nx, ny = _image.shape
-    d_img = _device.to_device(_image)
-    d_mask = _device.to_device(_mask)
-    d_disp = _device.to_device(_displacement)
+    masked = isinstance(image, MaskedArray)
+    d_mask = _device.to_device(numpy.ascontiguousarray(numpy.ma.getmaskarray(image), dtype=numpy.int8)) if masked \
+        else torch.zeros(tuple(numpy.shape(image)), dtype=torch.int8, device="cuda")
+    d_img = _device.to_device(numpy.ascontiguousarray(numpy.ma.getdata(image), dtype=numpy.float64))
+    d_disp = _device.to_device(numpy.ascontiguousarray(displacement, dtype=numpy.float64))
+    nx, ny = (int(v) for v in d_img.shape)
     out = torch.empty((nx, ny), dtype=torch.float64, device="cuda")
     omask = torch.empty((nx, ny), dtype=torch.int8, device="cuda")
     grad = torch.empty((2, nx, ny), dtype=torch.float64, device="cuda") if gradient else None
     _lib.call("b200_vet_warp", d_img.data_ptr(), d_mask.data_ptr(), d_disp.data_ptr(), nx, ny,
-              out.data_ptr(), omask.data_ptr(), _device.ptr(grad), _device.stream_ptr())
-    if gradient:
-        return out.cpu().numpy(), omask.cpu().numpy(), grad.cpu().numpy()
-    return out.cpu().numpy(), omask.cpu().numpy()
+              out.data_ptr(), omask.data_ptr(), _device.ptr(grad), _stream())
+    res = (out.cpu().numpy(), omask.cpu().numpy())
+    return res + (grad.cpu().numpy(),) if gradient else res
 
 
-class _DeviceImages:
-    """Image stack and mask of one minimisation level, resident on the device."""
+# ---------------------------------------------------------------------------------------------
+class _LevelImages:
+    """Image stack (T, M, N) float64 and mask (M, N) int8 of one level, resident in HBM."""
 
-    def __init__(self, input_images, mask):
-        self.shape = input_images.shape
-        self.images = _device.to_device(numpy.ascontiguousarray(input_images, dtype=numpy.float64))
-        self.mask = _device.to_device(numpy.ascontiguousarray(mask, dtype=numpy.int8))
-        self._sd = {}
-        self._out = {}
+    def __init__(self, images, mask):
+        self.images, self.mask = images, mask
+        self.shape = tuple(int(v) for v in images.shape)
 
-    def evaluate(self, sector_displacement_2d, pair, smooth_gain, gradient):
-        """_cost_function(sector_displacement, images[pair[0]], images[pair[1]], mask, ...)."""
-        shp = tuple(sector_displacement_2d.shape)
-        if shp not in self._sd:
-            self._sd[shp] = torch.empty(shp, dtype=torch.float64, device="cuda")
-            self._out[shp] = (torch.empty(2, dtype=torch.float64, device="cuda"),
-                              torch.empty(shp, dtype=torch.float64, device="cuda"))
-        sd = self._sd[shp]
-        sd.copy_(torch.from_numpy(numpy.ascontiguousarray(sector_displacement_2d, dtype=numpy.float64)))
-        out = self._out[shp][1 if gradient else 0]
-        nx, ny = int(self.shape[1]), int(self.shape[2])
-        _lib.call("b200_vet_cost", sd.data_ptr(), self.images[pair[0]].data_ptr(),
-                  self.images[pair[1]].data_ptr(), self.mask.data_ptr(), int(shp[1]), int(shp[2]), nx, ny,
-                  float(smooth_gain), 1 if gradient else 0, out.data_ptr(), _device.stream_ptr())
-        return out.cpu().numpy()
+    @classmethod
+    def from_host(cls, images, mask):
+        return cls(_device.to_device(numpy.ascontiguousarray(images, dtype=numpy.float64)),
+                   _device.to_device(numpy.ascontiguousarray(mask, dtype=numpy.int8)))
+
+
+class _Frames:
+    """The raw input on the device; hands out the level stacks."""
+
+    def __init__(self, input_images, padding):
+        user_mask = None
+        if isinstance(input_images, MaskedArray):
+            # a MaskedArray is taken at its word: only its own mask (vet.py:500-505)
+            user_mask = _device.to_device(numpy.ascontiguousarray(numpy.ma.getmaskarray(input_images),
+                                                                  dtype=numpy.uint8))
+        self.frames = _device.to_device(numpy.ascontiguousarray(numpy.ma.getdata(input_images), dtype=numpy.float64))
+        self.user_mask = user_mask
+        self.T, self.m, self.n = (int(v) for v in self.frames.shape)
+        self.padding = int(padding)
+        self.mg, self.ng = self.m + 2 * self.padding, self.n + 2 * self.padding  # globally padded frame
+        self._levels = {}
+
+    def level(self, pad_i, pad_j):
+        key = (pad_i, pad_j)
+        if key not in self._levels:
+            M, N = self.mg + pad_i[0] + pad_i[1], self.ng + pad_j[0] + pad_j[1]
+            images = torch.empty((self.T, M, N), dtype=torch.float64, device="cuda")
+            mask = torch.empty((M, N), dtype=torch.int8, device="cuda")
+            _lib.call("b200_vet_level_images", self.frames.data_ptr(), _device.ptr(self.user_mask), self.T,
+                      self.m, self.n, self.padding, pad_i[0], pad_j[0], M, N, images.data_ptr(),
+                      mask.data_ptr(), _stream())
+            self._levels[key] = _LevelImages(images, mask)
+        return self._levels[key]
+
+
+class _Objective:
+    """VET cost and gradient on one level for a (2, bi, bj) sector field, evaluated as a pair and
+    memoised on the last point."""
+
+    def __init__(self, level, blocks_shape, smooth_gain):
+        bi, bj = int(blocks_shape[0]), int(blocks_shape[1])
+        if bi < 2 or bj < 2:
+            raise NotImplementedError("pysteps_b200 VET: at least 2 x 2 sectors are required")
+        if level.shape[1] % bi != 0 or level.shape[2] % bj != 0:
+            raise ValueError("Error computing cost function.\n",
+                             "The number of sectors don't divide the image size")
+        self.level, self.bi, self.bj = level, bi, bj
+        self.gain = float(smooth_gain)
+        self.size = 2 * bi * bj
+        self.work = torch.empty(3 * self.size + 4, dtype=torch.float64, device="cuda")
+        self._x = None
+        self._parts = numpy.zeros(2)
+        self._grad = numpy.zeros(self.size)
+
+    def _at(self, x):
+        x = numpy.ascontiguousarray(x, dtype=numpy.float64).reshape(-1)
+        if x.size != self.size:
+            raise ValueError(f"cannot reshape array of size {x.size} into shape {(2, self.bi, self.bj)}")
+        if self._x is None or not numpy.array_equal(x, self._x):
+            T, nx, ny = self.level.shape
+            _lib.call("b200_vet_value_and_gradient", x.ctypes.data, self.level.images.data_ptr(), T,
+                      self.level.mask.data_ptr(), self.bi, self.bj, nx, ny, self.gain, self.work.data_ptr(),
+                      self._parts.ctypes.data, self._grad.ctypes.data, _stream())
+            self._x = x.copy()
+        return self
+
+    def parts(self, x):
+        """(residuals, smoothness penalty)"""
+        self._at(x)
+        return float(self._parts[0]), float(self._parts[1])
+
+    def value(self, x):
+        r, s = self.parts(x)
+        return r + s
+
+    def gradient(self, x):
+        return self._at(x)._grad.copy()
 
 
 def vet_cost_function_gradient(*args, **kwargs):
@@ -102,40 +160,47 @@ def vet_cost_function_gradient(*args, **kwargs):
 
 def vet_cost_function(sector_displacement_1d, input_images, blocks_shape, mask, smooth_gain,
                       debug=False, gradient=False):
-    """VET cost function / gradient (vet.py:165-299).  `input_images` may be the NumPy stack
-    of the reference or a device-resident `_DeviceImages` (what `vet` passes, so that the
-    images are uploaded once per minimisation level and not once per evaluation)."""
+    """VET cost function / gradient for a flattened (2, bi, bj) sector field (vet.py:165-299).
+    `input_images`: the (2 or 3, nx, ny) NumPy stack of the reference with its int8 `mask`."""
     _device.require_cuda()
-    if not isinstance(input_images, _DeviceImages):
-        input_images = _DeviceImages(numpy.asarray(input_images), numpy.asarray(mask))
-    sector_displacement_2d = numpy.asarray(sector_displacement_1d).reshape(*((2,) + tuple(blocks_shape)))
-    if sector_displacement_2d.shape[1] < 2 or sector_displacement_2d.shape[2] < 2:
-        raise NotImplementedError("pysteps_b200 VET: at least 2 x 2 sectors are required")
-    if (input_images.shape[1] % sector_displacement_2d.shape[1] != 0
-            or input_images.shape[2] % sector_displacement_2d.shape[2] != 0):
-        raise ValueError("Error computing cost function.\n",
-                         "The number of sectors don't divide the image size")
-    if input_images.shape[0] == 3:
-        three_times = True
-        pairs = ((1, 2), (0, 1))  # (center, next), then (previous, center)
-    else:
-        three_times = False
-        pairs = ((0, 1),)
+    level = input_images if isinstance(input_images, _LevelImages) else \
+        _LevelImages.from_host(numpy.asarray(input_images), numpy.asarray(mask))
+    if level.shape[0] not in (2, 3):
+        raise ValueError("vet_cost_function needs two or three frames")
+    obj = _Objective(level, blocks_shape, smooth_gain)
     if gradient:
-        gradient_values = input_images.evaluate(sector_displacement_2d, pairs[0], smooth_gain, True)
-        if three_times:
-            gradient_values = gradient_values + input_images.evaluate(
-                sector_displacement_2d, pairs[1], smooth_gain, True)
-        return gradient_values.ravel()
-    residuals, smoothness_penalty = input_images.evaluate(sector_displacement_2d, pairs[0], smooth_gain, False)
-    if three_times:
-        _residuals, _smoothness = input_images.evaluate(sector_displacement_2d, pairs[1], smooth_gain, False)
-        residuals += _residuals
-        smoothness_penalty += _smoothness
+        return obj.gradient(sector_displacement_1d)
+    residuals, smoothness_penalty = obj.parts(sector_displacement_1d)
     if debug:
         print("\nresiduals", residuals)
         print("smoothness_penalty", smoothness_penalty)
     return residuals + smoothness_penalty
+
+
+# ---------------------------------------------------------------------------------------------
+def _sector_table(sectors):
+    """(levels, 2) array of sector counts per axis, coarse to fine (vet.py:525-543)."""
+    s = numpy.asarray(sectors, dtype="int", order="C")
+    if s.ndim == 1:
+        s = numpy.stack([s, s])
+    elif s.ndim != 2:
+        raise ValueError(
+            "Incorrect sectors dimensions.\n"
+            + "Only 1D or 2D arrays are supported to define"
+            + "the number of sectors used in"
+            + "the scaling procedure"
+        )
+    return numpy.sort(s, axis=1).T.copy()
+
+
+def _zoom_on_device(field, oh, ow):
+    """scipy.ndimage.zoom(field, (1, oh/h, ow/w), order=1, mode="nearest") -> device tensor"""
+    d_in = field if isinstance(field, torch.Tensor) else \
+        _device.to_device(numpy.ascontiguousarray(field, dtype=numpy.float64))
+    c, h, w = (int(v) for v in d_in.shape)
+    out = torch.empty((c, oh, ow), dtype=torch.float64, device="cuda")
+    _lib.call("b200_zoom_bilinear", d_in.data_ptr(), c, h, w, oh, ow, out.data_ptr(), _stream())
+    return out
 
 
 def vet(input_images, sectors=((32, 16, 4, 2), (32, 16, 4, 2)), smooth_gain=1e6, first_guess=None,
@@ -155,165 +220,67 @@ def vet(input_images, sectors=((32, 16, 4, 2), (32, 16, 4, 2)), smooth_gain=1e6,
             "Maximum frames: 3\n"
         )
     _device.require_cuda()
+    say = print if verbose else (lambda *a, **k: None)
 
-    if verbose:
-        def debug_print(*args, **kwargs):
-            print(*args, **kwargs)
-    else:
-        def debug_print(*args, **kwargs):
-            del args
-            del kwargs
-
-    if options is None:
-        options = dict()
-    else:
-        options = dict(options)
-
-    options.setdefault("eps", 0.1)
-    options.setdefault("gtol", 0.1)
-    options.setdefault("maxiter", 100)
-    options.setdefault("disp", False)
-    optimization_method = options.pop("method", "CG")
-
-    pad_i = None
-    pad_j = None
-    sectors_in_i = None
-    sectors_in_j = None
-
-    debug_print("Running VET algorithm")
-
-    valid_indexing = ["yx", "xy", "ij"]
-    if indexing not in valid_indexing:
+    opts = {"eps": 0.1, "gtol": 0.1, "maxiter": 100, "disp": False}
+    opts.update(options or {})
+    method = opts.pop("method", "CG")
+    say("Running VET algorithm")
+    if indexing not in _INDEXING:
         raise ValueError(
             "Invalid indexing values: {0}\n".format(indexing)
-            + "Supported values: {0}".format(str(valid_indexing))
+            + "Supported values: {0}".format(str(list(_INDEXING)))
         )
 
-    if not isinstance(input_images, MaskedArray):
-        input_images = numpy.ma.masked_invalid(input_images)
-    else:
-        input_images = input_images.copy()  # the reference writes into .data below
-
-    mask = numpy.ma.getmaskarray(input_images)
-
-    if padding > 0:
-        padding_tuple = ((0, 0), (padding, padding), (padding, padding))
-        input_images_data = numpy.pad(numpy.ma.getdata(input_images), padding_tuple, "constant",
-                                      constant_values=numpy.nan)
-        mask = numpy.pad(mask, padding_tuple, "constant", constant_values=True)
-        input_images = numpy.ma.MaskedArray(data=input_images_data, mask=mask)
-
-    input_images.data[mask] = 0  # Remove any Nan from the raw data
-
-    mask = numpy.asarray(numpy.any(mask, axis=0), dtype="int8", order="C")
-    input_images = numpy.asarray(input_images.data, dtype="float64", order="C")
-
-    sectors = numpy.asarray(sectors, dtype="int", order="C")
-    if sectors.ndim == 1:
-        new_sectors = numpy.zeros((2,) + sectors.shape, dtype="int", order="C") + sectors.reshape(
-            (1, sectors.shape[0]))
-        sectors = new_sectors
-    elif sectors.ndim > 2 or sectors.ndim < 1:
-        raise ValueError(
-            "Incorrect sectors dimensions.\n"
-            + "Only 1D or 2D arrays are supported to define"
-            + "the number of sectors used in"
-            + "the scaling procedure"
-        )
-
-    sectors[0, :].sort()
-    sectors[1, :].sort()
-
-    first_guess_shape = (2, int(sectors[0, 0]), int(sectors[1, 0]))
+    frames = _Frames(input_images, padding)
+    table = _sector_table(sectors)
+    guess_shape = (2, int(table[0, 0]), int(table[0, 1]))
     if first_guess is None:
-        first_guess = numpy.zeros(first_guess_shape, order="C")
-    else:
-        if first_guess.shape != first_guess_shape:
-            raise ValueError(
-                "The shape of the initial guess do not match the number of "
-                + "sectors of the first scaling guess\n"
-                + "first_guess.shape={}\n".format(str(first_guess.shape))
-                + "Expected shape={}".format(str(first_guess_shape))
-            )
-        else:
-            first_guess = numpy.asarray(first_guess, order="C", dtype="float64")
-
-    scaling_guesses = list()
-    previous_sectors_in_i = sectors[0, 0]
-    previous_sectors_in_j = sectors[1, 0]
-    _shape = input_images.shape
-    device_cache = {}
-
-    for n, (sectors_in_i, sectors_in_j) in enumerate(zip(sectors[0, :], sectors[1, :])):
-        pad_i = get_padding(input_images.shape[1], sectors_in_i)
-        pad_j = get_padding(input_images.shape[2], sectors_in_j)
-
-        if (pad_i != (0, 0)) or (pad_j != (0, 0)):
-            _input_images = numpy.pad(input_images, ((0, 0), pad_i, pad_j), "edge")
-            _mask = numpy.pad(mask, (pad_i, pad_j), "constant", constant_values=1)
-            _mask = numpy.ascontiguousarray(_mask)
-        else:
-            _input_images = input_images
-            _mask = mask
-        _shape = _input_images.shape
-
-        # one upload per distinct padding (the images of a level do not change during CG)
-        key = (pad_i, pad_j)
-        if key not in device_cache:
-            device_cache[key] = _DeviceImages(_input_images, _mask)
-        dev_images = device_cache[key]
-
-        sector_shape = (_shape[1] // sectors_in_i, _shape[2] // sectors_in_j)
-        debug_print("original image shape: " + str(input_images.shape))
-        debug_print("padded image shape: " + str(_shape))
-        debug_print("padded template_image image shape: " + str(_shape))
-        debug_print("\nNumber of sectors: {0:d},{1:d}".format(sectors_in_i, sectors_in_j))
-        debug_print("Sector Shape:", sector_shape)
-
-        if n > 0:
-            first_guess = zoom(
-                first_guess,
-                (1, sectors_in_i / previous_sectors_in_i, sectors_in_j / previous_sectors_in_j),
-                order=1, mode="nearest",
-            )
-
-        debug_print("Minimizing")
-        result = minimize(
-            vet_cost_function,
-            first_guess.flatten(),
-            jac=vet_cost_function_gradient,
-            args=(dev_images, (sectors_in_i, sectors_in_j), _mask, smooth_gain),
-            method=optimization_method,
-            options=options,
+        x = numpy.zeros(guess_shape)
+    elif first_guess.shape != guess_shape:
+        raise ValueError(
+            "The shape of the initial guess do not match the number of "
+            + "sectors of the first scaling guess\n"
+            + "first_guess.shape={}\n".format(str(first_guess.shape))
+            + "Expected shape={}".format(str(guess_shape))
         )
-        first_guess = result.x.reshape(*first_guess.shape)
+    else:
+        x = numpy.asarray(first_guess, order="C", dtype="float64")
 
+    history = []
+    level = pads = None
+    for n_level, (bi, bj) in enumerate((int(a), int(b)) for a, b in table):
+        pads = (get_padding(frames.mg, bi), get_padding(frames.ng, bj))
+        level = frames.level(*pads)
+        say(f"level {n_level}: {bi} x {bj} sectors of {level.shape[1] // bi} x {level.shape[2] // bj} px, "
+            f"frame {frames.mg} x {frames.ng} padded to {level.shape[1]} x {level.shape[2]}")
+        if n_level > 0:
+            # the finer grid starts from the bilinear zoom of the coarser solution (vet.py:580-589)
+            factor_i, factor_j = bi / x.shape[1], bj / x.shape[2]
+            x = _zoom_on_device(x, int(round(x.shape[1] * factor_i)), int(round(x.shape[2] * factor_j))).cpu().numpy()
+        obj = _Objective(level, (bi, bj), smooth_gain)
+        result = minimize(obj.value, x.reshape(-1), jac=obj.gradient, method=method, options=opts)
+        x = result.x.reshape(x.shape)
         if verbose:
-            vet_cost_function(result.x, dev_images, (sectors_in_i, sectors_in_j), _mask, smooth_gain,
-                              debug=True)
-        if indexing == "yx":
-            scaling_guesses.append(first_guess[::-1, ...])
-        else:
-            scaling_guesses.append(first_guess)
+            residuals, smoothness_penalty = obj.parts(result.x)
+            say("\nresiduals", residuals)
+            say("smoothness_penalty", smoothness_penalty)
+        history.append(x[::-1, ...] if indexing == "yx" else x)
 
-        previous_sectors_in_i = sectors_in_i
-        previous_sectors_in_j = sectors_in_j
-
-    # final zoom to the image grid (vet.py:621-630) on the device
-    ni, nj = int(_shape[1]), int(_shape[2])
-    oh = int(round(first_guess.shape[1] * (ni / sectors_in_i)))
-    ow = int(round(first_guess.shape[2] * (nj / sectors_in_j)))
-    d_fg = _device.to_device(numpy.ascontiguousarray(first_guess, dtype=numpy.float64))
-    d_full = torch.empty((2, oh, ow), dtype=torch.float64, device="cuda")
-    _lib.call("b200_zoom_bilinear", d_fg.data_ptr(), 2, int(first_guess.shape[1]), int(first_guess.shape[2]),
-              oh, ow, d_full.data_ptr(), _device.stream_ptr())
-    first_guess = _device.to_host(d_full)
-
-    first_guess = first_guess[:, pad_i[0]: ni - pad_i[1], pad_j[0]: nj - pad_j[1]]
+    # sector field -> pixel grid of the level frame (vet.py:621-630), then everything the reference
+    # undoes on the host -- level padding, axis order, global padding -- as one view of the device
+    # tensor; a single D2H of the result
+    M, N = level.shape[1], level.shape[2]
+    bi, bj = x.shape[1], x.shape[2]
+    full = _zoom_on_device(x, int(round(bi * (M / bi))), int(round(bj * (N / bj))))
+    (pi0, pi1), (pj0, pj1) = pads
+    full = full[:, pi0: M - pi1, pj0: N - pj1]
     if indexing == "yx":
-        first_guess = first_guess[::-1, ...]
+        full = full.flip(0)
     if padding > 0:
-        first_guess = first_guess[:, padding:-padding, padding:-padding]
+        full = full[:, padding:-padding, padding:-padding]
+    field = _device.remember_result(_device.to_host(full.contiguous()), full.contiguous()) \
+        if full.numel() else full.cpu().numpy()
     if intermediate_steps:
-        return first_guess, scaling_guesses
-    return first_guess
+        return field, history
+    return field

@@ -42,6 +42,7 @@ class _BaseField:
 
     def __init__(self, V):
         self.host = None if isinstance(V, torch.Tensor) else V
+        self.fp = None if isinstance(V, torch.Tensor) else _fingerprint(V)
         if isinstance(V, torch.Tensor):
             t = V if V.dtype in (torch.float32, torch.float64) else V.to(torch.float64)
             self.tensor = _device.to_device(t)
@@ -49,7 +50,8 @@ class _BaseField:
             a = np.asarray(V)
             if a.dtype not in (np.float32, np.float64):
                 a = a.astype(np.float64)  # scipy.linalg.norm promotes integer input
-            self.tensor = _device.to_device(a)
+            kept = _device.recall_result(a)  # the field a pysteps_b200 motion method returned
+            self.tensor = kept if kept is not None else _device.to_device(a)
         self.shape = tuple(self.tensor.shape)
         # scipy.linalg.norm(check_finite=True), motion.py:134
         st = torch.empty(4, dtype=torch.float64, device="cuda")
@@ -91,9 +93,11 @@ def _base_field(V):
         return hit[2]
     bf = _BaseField(V)
     try:
+        # the entry (and with it the device copy) goes when the host array does
+        ref = weakref.ref(V, lambda _r, key=key, d=_fields: d.pop(key, None))
         if len(_fields) > 16:
             _fields.clear()
-        _fields[key] = (weakref.ref(V), fp, bf)
+        _fields[key] = (ref, fp, bf)
     except TypeError:
         pass
     return bf
@@ -148,7 +152,11 @@ class Perturbation(_Handle):
         return self.field.run(self.a, self.b, self.vsf, _PERTURBATION)
 
     def _add(self, other):
-        if other is self.field.host or (isinstance(other, torch.Tensor) and other is self.field.tensor):
+        if isinstance(other, torch.Tensor) and other is self.field.tensor:
+            return PerturbedVelocity(self)
+        # the host array the perturbator was initialised with -- unless it was rewritten in place
+        # since (then the reference would add the perturbation to the CURRENT field: materialise)
+        if other is self.field.host and _fingerprint(other) == self.field.fp:
             return PerturbedVelocity(self)
         if isinstance(other, torch.Tensor):
             return other + self.device_planar()

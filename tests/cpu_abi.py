@@ -178,6 +178,42 @@ def _vet_cost(sd, templ, inp, mask, xs, ys, nx, ny, smooth_gain, gradient, out, 
         _view(out, (2,))[...] = r
 
 
+def _vet_value_and_gradient(x_host, images, nframes, mask, xs, ys, nx, ny, smooth_gain, work, value_host,
+                            gradient_host, stream):
+    """vet.py:257-293 with the oracle's _cost_function: pairs (centre, next) then (previous, centre)"""
+    from oracle import vet as ora_vet
+    sd = _view(x_host, (2, xs, ys)).copy()
+    im = _view(images, (nframes, nx, ny))
+    mk = _view(mask, (nx, ny), np.int8).copy()
+    pairs = ((1, 2), (0, 1)) if nframes == 3 else ((0, 1),)
+    parts = [(ora_vet.cost_function(sd, im[a].copy(), im[b].copy(), mk, smooth_gain, gradient=False),
+              ora_vet.cost_function(sd, im[a].copy(), im[b].copy(), mk, smooth_gain, gradient=True))
+             for a, b in pairs]
+    res, smo = parts[0][0][0], parts[0][0][1]
+    grad = parts[0][1]
+    if nframes == 3:
+        res = res + parts[1][0][0]
+        smo = smo + parts[1][0][1]
+        grad = grad + parts[1][1]
+    _view(value_host, (2,))[...] = (res, smo)
+    _view(gradient_host, (2, xs, ys))[...] = grad
+
+
+def _vet_level_images(frames, umask, T, m, n, gpad, pi0, pj0, M, N, images, mask, stream):
+    """vet.py:500-523 and :548-561, literally (numpy.pad), as the check of the device kernel's indexing"""
+    fr = _view(frames, (T, m, n)).copy()
+    bad = ~np.isfinite(fr) if _addr(umask) is None else _view(umask, (T, m, n), np.uint8).astype(bool)
+    if gpad > 0:
+        tup = ((0, 0), (gpad, gpad), (gpad, gpad))
+        fr = np.pad(fr, tup, "constant", constant_values=np.nan)
+        bad = np.pad(bad, tup, "constant", constant_values=True)
+    fr[bad] = 0
+    mk = np.any(bad, axis=0).astype(np.int8)
+    pi1, pj1 = M - fr.shape[1] - pi0, N - fr.shape[2] - pj0
+    _view(images, (T, M, N))[...] = np.pad(fr, ((0, 0), (pi0, pi1), (pj0, pj1)), "edge")
+    _view(mask, (M, N), np.int8)[...] = np.pad(mk, ((pi0, pi1), (pj0, pj1)), "constant", constant_values=1)
+
+
 def _vet_warp(image, mask, disp, nx, ny, out, omask, grad, stream):
     from oracle import vet as ora_vet
     g = _addr(grad) is not None
@@ -366,7 +402,8 @@ _TABLE_LK = {"b200_mask_invalid": _lk_mask_invalid, "b200_morph_opening": _lk_mo
              "b200_compact_rows": _lk_compact_rows, "b200_decluster": _lk_decluster,
              "b200_idw_fill": _lk_idw_fill, "b200_idw_fill_ckdtree": _lk_idw_fill_ckdtree, "b200_fill_f64": _fill_f64}
 
-_TABLE = {"b200_vet_cost": _vet_cost, "b200_vet_warp": _vet_warp, "b200_zoom_bilinear": _zoom,
+_TABLE = {"b200_vet_cost": _vet_cost, "b200_vet_value_and_gradient": _vet_value_and_gradient,
+          "b200_vet_level_images": _vet_level_images, "b200_vet_warp": _vet_warp, "b200_zoom_bilinear": _zoom,
           "b200_gaussian_filter": _gaussian_filter, "b200_proesmans_scale": _proesmans_scale, "b200_proesmans_field": _proesmans_field,
           "b200_sl_trajectories": _sl_trajectories, "b200_spline_prepare": _spline_prepare,
           "b200_spline_sample": _spline_sample, "b200_field_stats": _field_stats, "b200_sl_extrapolate_rows": _sl_rows,

@@ -71,3 +71,29 @@ def test_config4_composite_4096_vs_oracle(api):
     # row bands (the multi-GPU partitioning of this config) are the rows of the full result
     band = extrap(P, Vo, 24, b200_rows=(1024, 1536))
     assert_bits_equal(band, want[:, 1024:1536], "row band")
+
+
+def test_config2_vet_2048_vs_oracle():
+    """BASELINE config[2]: VET at 2048^2.  One cost / gradient evaluation at every level's sector
+    grid against the oracle (relative 1e-12), and the optimised field after a bounded number of CG
+    iterations within 1e-6 px of the oracle run with the same options."""
+    import pysteps_b200
+    from oracle import vet as ora
+    from pysteps_b200 import _synthetic as syn
+    from pysteps_b200.motion import vet as b200_vet
+    fr = syn.rain_frames(2048, 2048, 2, 0)
+    mask = np.zeros((2048, 2048), np.int8)
+    rng = np.random.default_rng(3)
+    for bs in ((2, 2), (4, 4), (16, 16), (32, 32)):
+        x = rng.normal(size=(2,) + bs).ravel() * 2.0
+        c = b200_vet.vet_cost_function(x, fr, bs, mask, 1e6)
+        g = b200_vet.vet_cost_function_gradient(x, fr, bs, mask, 1e6)
+        co = ora.vet_cost_function(x, fr, bs, mask, 1e6)
+        go = ora.vet_cost_function_gradient(x, fr, bs, mask, 1e6)
+        assert abs(c - co) <= 1e-12 * abs(co), bs
+        assert np.abs(g - go).max() <= 1e-12 * np.abs(go).max(), bs
+    opts = {"maxiter": 4}
+    V = pysteps_b200.motion.get_method("vet")(fr, verbose=False, options=opts)
+    Vo = ora.vet(fr, verbose=False, options=opts)
+    assert V.shape == Vo.shape == (2, 2048, 2048)
+    assert np.abs(V - Vo).max() <= 1e-6

@@ -11,6 +11,7 @@ from pysteps_b200.noise import motion as bps
 class _FakeField:
     def __init__(self, V):
         self.host = V
+        self.fp = bps._fingerprint(V)
         self.tensor = None
         self.shape = V.shape
         self.calls = []
@@ -47,6 +48,21 @@ def test_adding_the_perturbators_own_field_stays_lazy():
     assert h.device_planar() == ("device", bps._PERTURBATION)
     assert [c[3] for c in f.calls] == [bps._FIELD_INTERLEAVED, bps._FIELD_PLANAR, bps._PERTURBATION]
     assert all(c[:3] == (0.5, -0.25, 60.0) for c in f.calls)
+
+
+def test_a_field_rewritten_in_place_is_not_taken_for_the_initial_one():
+    """velocity + generate_bps(...) is fused only while `velocity` still holds what initialize_bps
+    saw; after an in-place edit the sum is materialised from the CURRENT array, as the reference
+    would compute it."""
+    V = np.ones((2, 5, 7))
+    f = _FakeField(V)
+    h = bps.Perturbation(f, 0.5, -0.25, 60.0)
+    assert isinstance(V + h, bps.PerturbedVelocity)
+    V[0, 0, 0] = 7.0
+    f.run = lambda *a, **k: (_ for _ in ()).throw(AssertionError("materialise through np.asarray instead"))
+    h.__class__ = type("P", (bps.Perturbation,), {"__array__": lambda self, dtype=None, copy=None: np.zeros((2, 5, 7))})
+    s = V + h
+    assert isinstance(s, np.ndarray) and s[0, 0, 0] == 7.0
 
 
 def test_ndarray_defers_to_the_handle():

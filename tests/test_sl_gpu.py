@@ -91,8 +91,10 @@ def test_errors(sl):
         sl.extrapolate(P, np.full((2, 8, 8), np.nan), 1, allow_nonfinite_values=True)
     with pytest.raises(ValueError, match="return_displacement is False"):
         sl.extrapolate(None, V, 1)
+    with pytest.raises(RuntimeError, match="spline order not supported"):
+        sl.extrapolate(P, V, 1, interp_order=6)
     with pytest.raises(NotImplementedError):
-        sl.extrapolate(P, V, 1, interp_order=3)
+        sl.extrapolate(P, V, 1, map_coordinates_mode="wrap")
     with pytest.warns(UserWarning, match="D_prev"):
         sl.extrapolate(P, V, 1, D_prev=None)
     out = sl.extrapolate(P, V, 1, some_unknown_kwarg=5)  # unknown kwargs ignored (:29,129-134)

@@ -81,6 +81,71 @@ def test_morph_and_zoom(vet, golden):
         assert_bits_equal(out.cpu().numpy(), ora.zoom_o1(a, oh, ow_), f"zoom {(c, h, w_, oh, ow_)}")
 
 
+def test_fused_pair_equals_separate_evaluations(vet):
+    """b200_vet_value_and_gradient (one pass, value + gradient) is bitwise b200_vet_cost's value and
+    b200_vet_cost's gradient, two and three frames (pairs summed in vet.py:257-293's order)."""
+    import torch
+    from pysteps_b200 import _lib
+    from vet_cases import EVAL_CASES, eval_case
+    s = torch.cuda.current_stream().cuda_stream
+    for name in EVAL_CASES:
+        sd, images, mask, gain = eval_case(name)
+        T, nx, ny = images.shape
+        _, xs, ys = sd.shape
+        d_im, d_mk, d_sd = torch.from_numpy(images).cuda(), torch.from_numpy(mask).cuda(), torch.from_numpy(sd).cuda()
+        pairs = ((1, 2), (0, 1)) if T == 3 else ((0, 1),)
+        res = smo = grad = None
+        for a, b in pairs:
+            oc = torch.empty(2, dtype=torch.float64, device="cuda")
+            og = torch.empty((2, xs, ys), dtype=torch.float64, device="cuda")
+            for mode, out in ((0, oc), (1, og)):
+                _lib.call("b200_vet_cost", d_sd.data_ptr(), d_im[a].data_ptr(), d_im[b].data_ptr(), d_mk.data_ptr(),
+                          xs, ys, nx, ny, gain, mode, out.data_ptr(), s)
+            c, g = oc.cpu().numpy(), og.cpu().numpy()
+            res, smo, grad = (c[0], c[1], g) if res is None else (res + c[0], smo + c[1], grad + g)
+        work = torch.empty(3 * sd.size + 4, dtype=torch.float64, device="cuda")
+        val, gout = np.zeros(2), np.zeros(sd.size)
+        _lib.call("b200_vet_value_and_gradient", sd.ctypes.data, d_im.data_ptr(), T, d_mk.data_ptr(), xs, ys, nx, ny,
+                  gain, work.data_ptr(), val.ctypes.data, gout.ctypes.data, s)
+        assert val[0] == res and val[1] == smo, name
+        assert np.array_equal(gout.reshape(2, xs, ys), grad), name
+
+
+def test_level_images_kernel_equals_numpy_pad(vet):
+    """b200_vet_level_images against vet.py:500-523 / :548-561 spelled with numpy.pad."""
+    import torch
+    from pysteps_b200 import _lib
+    rng = np.random.default_rng(5)
+    s = torch.cuda.current_stream().cuda_stream
+    for T, m, n, gpad, (pi0, pi1), (pj0, pj1), masked in ((2, 37, 41, 0, (0, 0), (0, 0), False),
+                                                         (3, 50, 33, 0, (3, 4), (1, 2), False),
+                                                         (2, 29, 64, 5, (2, 3), (0, 0), False),
+                                                         (3, 31, 45, 2, (1, 1), (7, 8), True)):
+        fr = rng.standard_normal((T, m, n))
+        fr[rng.random((T, m, n)) < 0.05] = np.nan
+        fr[0, 3, 4] = np.inf
+        um = rng.random((T, m, n)) < 0.1
+        bad = um if masked else ~np.isfinite(fr)
+        ref, rbad = fr.copy(), bad.copy()
+        if gpad:
+            tup = ((0, 0), (gpad, gpad), (gpad, gpad))
+            ref = np.pad(ref, tup, "constant", constant_values=np.nan)
+            rbad = np.pad(rbad, tup, "constant", constant_values=True)
+        ref[rbad] = 0
+        want = np.pad(ref, ((0, 0), (pi0, pi1), (pj0, pj1)), "edge")
+        wmask = np.pad(np.any(rbad, axis=0).astype(np.int8), ((pi0, pi1), (pj0, pj1)), "constant", constant_values=1)
+        M, N = want.shape[1:]
+        d_fr = torch.from_numpy(fr).cuda()
+        d_um = torch.from_numpy(um.astype(np.uint8)).cuda() if masked else None
+        out = torch.empty((T, M, N), dtype=torch.float64, device="cuda")
+        omask = torch.empty((M, N), dtype=torch.int8, device="cuda")
+        _lib.call("b200_vet_level_images", d_fr.data_ptr(), None if d_um is None else d_um.data_ptr(), T, m, n,
+                  gpad, pi0, pj0, M, N, out.data_ptr(), omask.data_ptr(), s)
+        from conftest import assert_bits_equal
+        assert_bits_equal(out.cpu().numpy(), want, "level images")
+        assert np.array_equal(omask.cpu().numpy(), wmask)
+
+
 def test_optimised_fields(vet, golden):
     from oracle import vet as ora
     from vet_cases import FIELD_CASES, field_case

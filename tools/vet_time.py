@@ -9,13 +9,13 @@ torch.cuda.synchronize()
 calls = {"n": 0}
 orig = _lib.call
 def counting(name, *a):
-    if name == "b200_vet_cost": calls["n"] += 1
+    if name in ("b200_vet_cost", "b200_vet_value_and_gradient"): calls["n"] += 1
     return orig(name, *a)
 _lib.call = counting
 import pysteps_b200.motion.vet as vm
 t = time.time(); V = vet(fr, verbose=False); torch.cuda.synchronize(); dt = time.time() - t
 wet = fr[1] > 0
-print("VET 2048^2: %.3f s, %d cost/grad evaluations, mean V in rain (%.4f, %.4f)" % (dt, calls["n"], V[0][wet].mean(), V[1][wet].mean()))
+print("VET 2048^2: %.3f s, %d fused value+gradient evaluations, mean V in rain (%.4f, %.4f)" % (dt, calls["n"], V[0][wet].mean(), V[1][wet].mean()))
 with _lib.Trace() as tr:
     V = vet(fr, verbose=False)
 s = tr.summary()
