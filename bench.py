@@ -207,12 +207,35 @@ def stage_rooflines(trace_ms, steps, m, n, peak_gbs, sl_bytes):
 
 
 # ----------------------------------------------------------------------------- CPU legs
+_THREADS = {}
+
+
 def host_threads():
-    """All host cores for the CPU legs, whatever the launcher exported (torchrun sets
-    OMP_NUM_THREADS=1)."""
+    """Thread count of the CPU legs, set explicitly whatever the launcher exported (torchrun sets
+    OMP_NUM_THREADS=1): all logical CPUs, or half of them (one per physical core of an SMT-2
+    host) when that runs the oracle's advection kernel faster -- measured once per process."""
     import oracle
-    want = int(os.environ.get("BENCH_CPU_THREADS", "0")) or (os.cpu_count() or 1)
-    return oracle.set_num_threads(want)
+    if "n" in _THREADS:
+        return oracle.set_num_threads(_THREADS["n"])
+    forced = int(os.environ.get("BENCH_CPU_THREADS", "0"))
+    ncpu = os.cpu_count() or 1
+    if forced or ncpu < 4:
+        _THREADS["n"] = forced or ncpu
+        return oracle.set_num_threads(_THREADS["n"])
+    from oracle import semilagrangian as ora
+    from pysteps_b200 import _synthetic as syn
+    P, V = syn.rain_field(1024, 1024, 0), syn.velocity_field(1024, 1024, 0)
+    best = None
+    for cand in (ncpu, ncpu // 2):
+        oracle.set_num_threads(cand)
+        ora.extrapolate(P, V, 2)
+        t0 = time.perf_counter()
+        ora.extrapolate(P, V, 4)
+        dt = time.perf_counter() - t0
+        if best is None or dt < best[0]:
+            best = (dt, cand)
+    _THREADS["n"] = best[1]
+    return oracle.set_num_threads(best[1])
 
 
 def cpu_step(w, frames, precip, V, lk):
@@ -246,15 +269,65 @@ def cpu_step(w, frames, precip, V, lk):
 
 
 def cpu_baseline(w, frames, precip, V, lk, reps=2):
+    """On the GPU box's host cores: the REFERENCE itself when it travelled (oracle/_ref) on a
+    bounded crop (~15 s of CPU work), and the oracle's OpenMP port on the full frame beside it."""
     threads = host_threads()
     times = [cpu_step(w, frames, precip, V, lk) for _ in range(reps)]
     best = min(times)
-    return {"value": (w["members"] or 1) * w["T"] * w["m"] * w["n"] / best / 1e6, "unit": UNIT, "cores": threads,
+    port = {"value": (w["members"] or 1) * w["T"] * w["m"] * w["n"] / best / 1e6, "unit": UNIT, "cores": threads,
             "kind": "port",
             "sample": f"{reps} full step(s) of {workload_name(lk, w)} (oracle C/NumPy port, "
                       f"OpenMP {threads} threads, exhaustive k-NN mode), best of {reps}: "
                       + " / ".join(f"{t:.2f}" for t in times) + " s"
                       + (f" (1 of {w['members']} members run, scaled)" if w["members"] else "")}
+    if not have_reference():
+        return port
+    side = 1024 if w["m"] >= 2048 else w["m"] // 2
+    r0, c0 = (w["m"] - side) // 2, (w["n"] - side) // 2
+    crop = (slice(None), slice(r0, r0 + side), slice(c0, c0 + side))
+    t = reference_step(w, np.ascontiguousarray(frames[crop]), np.ascontiguousarray(precip[crop[1:]]),
+                       np.ascontiguousarray(V[crop]), lk)
+    return {"value": (w["members"] or 1) * w["T"] * side * side / t / 1e6, "unit": UNIT, "cores": threads,
+            "kind": "reference",
+            "sample": f"1 step of pysteps v1.21.3 itself (oracle/_ref) on a centred {side}x{side} crop of the "
+                      f"workload's frames: {t:.1f} s", "port": port}
+
+
+def reference_step(w, frames, precip, V, lk):
+    """One step by the REFERENCE ITSELF (pysteps v1.21.3, unmodified, imported from its compiled form
+    oracle/_ref -- or /root/reference where that exists): seconds of the whole step."""
+    import contextlib
+    import io
+    import warnings
+    from oracle import refimport
+    sl = refimport.ref_module("pysteps.extrapolation.semilagrangian").extrapolate
+    with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+        warnings.simplefilter("ignore")
+        t0 = time.perf_counter()
+        if lk and w["motion"] == "vet":
+            V = refimport.ref_module("pysteps.motion.vet").vet(frames, verbose=False)
+        elif lk:
+            V = refimport.ref_module("pysteps.motion.lucaskanade").dense_lucaskanade(frames)
+        if w["members"]:
+            bps = refimport.ref_module("pysteps.noise.motion")
+            t1 = time.perf_counter()
+            pert = bps.initialize_bps(V, 1.0, 5.0, randstate=np.random.RandomState(1000))
+            disp = None
+            for t in range(w["T"]):
+                Vm = V + bps.generate_bps(pert, (t + 1) * 5.0)
+                _, disp = sl(precip, Vm, [1.0], displacement_prev=disp, return_displacement=True)
+            member = time.perf_counter() - t1
+            return (t1 - t0) + w["members"] * member
+        sl(precip, V, w["T"])
+        return time.perf_counter() - t0
+
+
+def have_reference():
+    try:
+        from oracle import refimport
+        return refimport.available(extensions=True)
+    except Exception:
+        return False
 
 
 def run_reference(args, w):
@@ -264,31 +337,40 @@ def run_reference(args, w):
     lk = have_lk_oracle()
     frames, precip, V = make_inputs(w, 0)
     threads = host_threads()
+    real = have_reference() and not os.environ.get("BENCH_REFERENCE_PORT_ONLY")
+    step = reference_step if real else cpu_step
+    kind = "reference" if real else "port"
+    what = ("pysteps v1.21.3 itself (oracle/_ref: its modules as bytecode + its Cython extensions built with "
+            "setup.py's flags), stock dense_lucaskanade / extrapolate: SciPy cKDTree and map_coordinates are "
+            "single-threaded by construction, OpenCV and the extensions use the host's threads") if real else \
+        f"oracle port of the reference path, OpenMP {threads} threads (set explicitly), exhaustive k-NN mode"
     small = (slice(None), slice(0, 256), slice(0, 256))
     for _ in range(args.warmup):
-        cpu_step(w, np.ascontiguousarray(frames[small]), np.ascontiguousarray(precip[small[1:]]),
-                 np.ascontiguousarray(V[small]), lk)
+        step(w, np.ascontiguousarray(frames[small]), np.ascontiguousarray(precip[small[1:]]),
+             np.ascontiguousarray(V[small]), lk)
     # Every step is a bounded sample of the workload: the full frame when the host is fast enough
-    # for the whole run to end within a few minutes (64 cores: ~2.5 s per step), else a centred
-    # crop sized from the first step's time (stated in `sample`); the metric is per advected pixel.
+    # for the whole run to end within a few minutes, else a centred crop sized from the first
+    # step's time (stated in `sample`); the metric is per advected pixel.
     budget_s = float(os.environ.get("BENCH_REFERENCE_BUDGET_S", "240"))
-    dt = cpu_step(w, frames, precip, V, lk)
+    dt = step(w, frames, precip, V, lk)
+    first = dt
     m, n = w["m"], w["n"]
     pixels = m * n
     sample = f"every step on the full {m}x{n} frame"
     side_m, side_n = m, n
+    fr_c, pr_c, V_c = frames, precip, V
     if dt * args.steps > budget_s and args.steps > 1:
         frac = max((budget_s - dt) / (dt * (args.steps - 1)), 1.0 / 64.0)
         side_m = max(256, int(m * frac ** 0.5) // 32 * 32)
         side_n = max(256, int(n * frac ** 0.5) // 32 * 32)
         r0, c0 = (m - side_m) // 2, (n - side_n) // 2
-        frames = np.ascontiguousarray(frames[:, r0:r0 + side_m, c0:c0 + side_n])
-        precip = np.ascontiguousarray(precip[r0:r0 + side_m, c0:c0 + side_n])
-        V = np.ascontiguousarray(V[:, r0:r0 + side_m, c0:c0 + side_n])
+        fr_c = np.ascontiguousarray(frames[:, r0:r0 + side_m, c0:c0 + side_n])
+        pr_c = np.ascontiguousarray(precip[r0:r0 + side_m, c0:c0 + side_n])
+        V_c = np.ascontiguousarray(V[:, r0:r0 + side_m, c0:c0 + side_n])
         sample = (f"first step on the full frame ({dt:.1f} s), the other {args.steps - 1} on a centred "
                   f"{side_m}x{side_n} crop to stay within {budget_s:.0f} s")
     for _ in range(args.steps - 1):
-        dt += cpu_step(w, frames, precip, V, lk)
+        dt += step(w, fr_c, pr_c, V_c, lk)
         pixels += side_m * side_n
     val = (w["members"] or 1) * w["T"] * pixels / dt / 1e6
     line = {"impl": "reference", "metric": w["metric"], "value": val, "unit": UNIT, "n_gpus": args.gpus,
@@ -297,10 +379,14 @@ def run_reference(args, w):
             "dtype": "f64", "data": "synthetic", "config": config_of(w),
             "note": "host throughput: N independent nowcasts take N times as long on the same cores, so the "
                     "Mpix/s of this arm is the same at every --gpus N",
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": f"{args.steps} step(s), {sample}; oracle port of the reference "
-                                       f"path, OpenMP {threads} threads (set explicitly), exhaustive k-NN mode"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind,
+                             "sample": f"{args.steps} step(s), {sample}; {what}"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if real:
+        # the tougher figure beside it: the oracle's OpenMP C/NumPy port of the same path, one full step
+        tp = cpu_step(w, frames, precip, V, lk)
+        line["port"] = {"value": (w["members"] or 1) * w["T"] * m * n / tp / 1e6, "unit": UNIT, "cores": threads,
+                        "kind": "port", "sample": f"1 full step, {tp:.2f} s (first reference step: {first:.1f} s)"}
     print(json.dumps(line))
     return 0
 
@@ -446,8 +532,9 @@ def build_standard(b, w, active=None):
     def step_host():
         """public NumPy API: H2D of inputs and D2H of the result inside."""
         if lk and strong and world > 1 and w["motion"] == "lk":
-            Vband = motion(frames_h, interp_kwargs={"b200_rows": band})  # NumPy band
-            Vh = b.shard.gather_row_bands(torch.from_numpy(Vband).cuda(), m, world, rank).cpu().numpy()
+            # host frames in, host result out; the motion-field bands meet on the devices (NCCL)
+            Vband = motion(torch.from_numpy(frames_h).cuda(non_blocking=True), interp_kwargs={"b200_rows": band})
+            Vh = b.shard.gather_row_bands(Vband, m, world, rank)
         elif lk:
             Vh = motion(frames_h)  # NumPy (2,m,n) float64, as pysteps returns it
         else:
@@ -459,7 +546,7 @@ def build_standard(b, w, active=None):
     # the second upload is served from the device copy the motion call left behind, see
     # pysteps_b200/_device.py: recent_results)
     h2d = precip_h.nbytes + (frames_h.nbytes if lk else V_h.nbytes)
-    d2h = rows_here * n * 4 * T + (2 * (rows_here if (strong and world > 1) else m) * n * 8 if lk else 0)
+    d2h = rows_here * n * 4 * T + (2 * m * n * 8 if (lk and not (strong and world > 1)) else 0)
     info = dict(h2d=h2d, d2h=d2h, rows_here=rows_here, lk=lk, inputs=(frames_h, precip_h, V_h),
                 dev_inputs=(frames_d, precip_d, V_d), nfields=(world if w["scaling"] == "weak" else 1))
     return step_device, step_host, info

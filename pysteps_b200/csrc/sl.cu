@@ -89,14 +89,31 @@ __device__ __forceinline__ Axis make_axis(double c, int L) {
     return a;
 }
 
+// 0.0 + p for a finite or non-finite double WITHOUT the FP64 pipe: the addition only changes
+// p = -0.0 (to +0.0); everything else, NaN payloads included, passes through.
+__device__ __forceinline__ double plus_zero(double p) {
+    const int hi = __double2hiint(p), lo = __double2loint(p);
+    return ((hi ^ (int)0x80000000) | lo) == 0 ? 0.0 : p;
+}
+
 // sum_{taps} ((a * wy) * wx), left to right from 0.0 (scipy accumulation order)
 __device__ __forceinline__ double bilin(double a00, double a01, double a10, double a11,
                                         double wy0, double wy1, double wx0, double wx1) {
-    double t = __dadd_rn(0.0, __dmul_rn(__dmul_rn(a00, wy0), wx0));
+    double t = plus_zero(__dmul_rn(__dmul_rn(a00, wy0), wx0));
     t = __dadd_rn(t, __dmul_rn(__dmul_rn(a01, wy0), wx1));
     t = __dadd_rn(t, __dmul_rn(__dmul_rn(a10, wy1), wx0));
     t = __dadd_rn(t, __dmul_rn(__dmul_rn(a11, wy1), wx1));
     return t;
+}
+
+// u * 0.5 on the integer pipe: for a normal u whose half is normal too the product is u with the
+// exponent field one lower (exact); zeros, subnormals, the smallest normals, infinities and NaN
+// take the multiplication.
+__device__ __forceinline__ double half_of(double u) {
+    const int hi = __double2hiint(u);
+    const unsigned e = ((unsigned)hi >> 20) & 0x7ffu;
+    if (e >= 2u && e <= 2046u) return __hiloint2double(hi - 0x00100000, __double2loint(u));
+    return __dmul_rn(u, 0.5);
 }
 
 // ---- slow (generic) path: any coordinate, per-tap index clamping --------------------
@@ -246,8 +263,8 @@ sl_multistep_kernel(const __grid_constant__ SLParams p) {
         if (n_iter > 0) {
             for (int k = 0; k < n_iter; k++) {  // :211-214
                 // velocity_inc / 2.0 == velocity_inc * 0.5 exactly
-                const double hx = __dsub_rn(dx, __dmul_rn(ux, 0.5));
-                const double hy = __dsub_rn(dy, __dmul_rn(uy, 0.5));
+                const double hx = __dsub_rn(dx, half_of(ux));
+                const double hy = __dsub_rn(dy, half_of(uy));
                 sample_velocity(Vi, m, n, ymax, xmax, __dadd_rn(gy, hy), __dadd_rn(gx, hx), scale,
                                 n_iter, vel_f32, ux, uy);
                 dx = __dsub_rn(dx, ux);
