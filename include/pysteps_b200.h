@@ -211,6 +211,16 @@ int b200_masked_minmax(const double *img, const uint8_t *mask, int m, int n, int
 int b200_quantise_u8(const double *img, const uint8_t *mask, int m, int n, int mode, int dilate,
                      const double *stats, const double *fill_dev, uint8_t *out, uint8_t *valid,
                      void *stream);
+/* The four stages above for one frame in three passes (mask + raw min; opening + statistics;
+ * opening + both uint8 images), the opened float64 image never written to HBM: the stencil
+ * passes stage (64+4) x (16+4) float64 halo tiles in shared memory with TMA
+ * (cp.async.bulk.tensor.2d, two-deep mbarrier ring, persistent CTAs; csrc/lk_frontend.cu).
+ * Results are those of b200_mask_invalid -> b200_morph_opening -> b200_masked_minmax ->
+ * b200_quantise_u8 (mode 0 into q_track; mode 1 into q_det / valid when q_det is not NULL).
+ * Needs an even n (16-byte rows for the copy engine) and buffer_mask <= 5. */
+int b200_lk_frontend(const double *img, const uint8_t *user_mask, int m, int n, int size_opening,
+                     int buffer_mask, int flags, uint8_t *mask, double *stats0, double *stats,
+                     uint8_t *q_track, uint8_t *q_det, uint8_t *valid, void *stream);
 
 /* cv::pyrDown (uint8, BORDER_REFLECT_101) and the int16 Scharr pair image of
  * cv::calcOpticalFlowPyrLK's pyramid (dst holds (Ix, Iy) interleaved). */
@@ -273,7 +283,9 @@ int b200_decluster(const double *xy, const double *uv, const int *n_dev, int n_c
  * stream), so the neighbour SET is the reference's everywhere (interpolate.py:78-81).
  * coords_on_16th_grid != 0 is the caller's promise that every vector and grid coordinate is
  * a multiple of 1/16 with magnitude < 2^14 (true for dense_lucaskanade: pixel grids and
- * medians of integer corners); it enables a faster, result-identical key packing. */
+ * medians of integer corners); it enables a faster, result-identical key packing.  The value 2
+ * promises more: vectors on multiples of 1/2 and INTEGER grid coordinates -- the search then runs
+ * on exact 32-bit integer keys. */
 int b200_idw_fill(const double *xy, const double *vals, const int *npts_dev, int npts_cap,
                   int nvar, int k, double power, double dist_offset, double mean_res,
                   const double *xgrid, int nx, const double *ygrid, int ny,

@@ -67,6 +67,8 @@ _SIGNATURES = {
     "b200_lk_pyramid_layout": (c_int, [c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_int),
                                        ctypes.POINTER(c_i64), ctypes.POINTER(c_int),
                                        ctypes.POINTER(c_int), ctypes.POINTER(c_i64)]),
+    "b200_lk_frontend": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200_lk_build_pyramid": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                       c_void_p]),
     "b200_lk_track": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
@@ -142,8 +144,12 @@ class Trace:
     """Records (name, start_event, end_event) for each traced C-ABI call on the current
     torch stream.  ``summary()`` synchronises and returns {name: [ms, ...]}."""
 
-    def __init__(self):
+    def __init__(self, only=None):
+        """only: trace just these entry points (two CUDA events per traced call cost ~15 us of host
+        time; a timed region traces the one kernel it rates, the per-stage table comes from
+        untimed steps)."""
         self.records = []
+        self.only = None if only is None else frozenset(only)
 
     def __enter__(self):
         global _trace
@@ -168,7 +174,7 @@ def call(name, *args):
     """Invoke a C-ABI function by name, raising on failure; traced when a Trace is active."""
     fn = getattr(load(), name)
     tr = _trace
-    if tr is None:
+    if tr is None or (tr.only is not None and name not in tr.only):
         check(fn(*args))
         return
     import torch

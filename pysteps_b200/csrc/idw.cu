@@ -41,6 +41,7 @@ struct IDWParams {
     double *out;  // (nvar, ny, nx)
     int *tie_list;   // grid points whose k-th and (k+1)-th neighbours are equidistant (or null)
     int *tie_count;
+    uint8_t *tile_done;  // per pixel tile: filled by the 32-bit-key kernel (or null)
 };
 
 // numpy's pairwise summation for n < 128 (8 accumulators, then the remainder)
@@ -174,31 +175,33 @@ __device__ __forceinline__ void topk_scan(const double2 *__restrict__ spt, const
     }
 }
 
-// FASTW: the weighting of dense_lucaskanade's call (two variables, power 1/2, unit resolution,
-// positive offset) from rsqrt; otherwise the general NumPy-order epilogue.
-template <int K, bool EXACT, bool PACKED, bool FASTW>
-__global__ void __launch_bounds__(IDW_THREADS, FASTW ? 3 : 1) idw_kernel(const IDWParams p) {
-    __shared__ double2 spt[IDW_CHUNK];
-    __shared__ int sidx[IDW_CHUNK];
-    __shared__ int hist[IDW_BINS];   // counts, then exclusive offsets
-    __shared__ int fill[IDW_BINS];
-    __shared__ unsigned char sbin[IDW_CHUNK];  // bin of the first IDW_CHUNK vectors
-    __shared__ int s_bmax, s_total;
-    const int npts = p.npts_dev ? min(*p.npts_dev, p.npts_cap) : p.npts_cap;
-    const int k = min(min(p.k, npts), K);
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    // a warp covers a compact 8x4 pixel patch: its lanes agree on most insert decisions
-    const int j = blockIdx.x * IDW_TX + (wid & 1) * 8 + (lane & 7);   // column
-    const int i = blockIdx.y * IDW_TY + (wid >> 1) * 4 + (lane >> 3);  // row
-    const double2 *__restrict__ pts = reinterpret_cast<const double2 *>(p.xy);
-    const bool active = j < p.nx && i < p.ny;
-    const double qx = p.gx[min(j, p.nx - 1)], qy = p.gy[min(i, p.ny - 1)];
+// Search bound of one pixel tile (see the comment above idw_kernel): histogram of the vectors'
+// distances to the tile centre, bin of the k-th, candidate bins [0, bmax]; leaves the exclusive
+// bin offsets in `hist`, zeroes `fill`, caches the bins of the first IDW_CHUNK vectors in `sbin`.
+struct TileBound {
+    int bmax, total;
+    double cx, cy, rt, binw;
+    float inv_binw_f;
+    __device__ __forceinline__ int bin_of(const double2 *__restrict__ pts, int t) const {
+        const double2 s = pts[t];
+        const float dx = (float)(s.x - cx), dy = (float)(s.y - cy);
+        const float d = sqrtf(dx * dx + dy * dy) * inv_binw_f;
+        return d < (float)(IDW_BINS - 1) ? (int)d : IDW_BINS - 1;
+    }
+};
 
+__device__ __forceinline__ TileBound tile_bound(const IDWParams &p, const double2 *__restrict__ pts, int npts, int k,
+                                                int *hist, int *fill, unsigned char *sbin, int *s_bmax,
+                                                int *s_total) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    TileBound tb;
     // ---- tile centre, half diagonal, histogram of centre distances ---------------------
     const int j0 = blockIdx.x * IDW_TX, j1 = min(j0 + IDW_TX, p.nx) - 1;
     const int i0 = blockIdx.y * IDW_TY, i1 = min(i0 + IDW_TY, p.ny) - 1;
     const double xa = p.gx[j0], xb = p.gx[j1], ya = p.gy[i0], yb = p.gy[i1];
-    const double cx = 0.5 * (xa + xb), cy = 0.5 * (ya + yb);
+    tb.cx = 0.5 * (xa + xb);
+    tb.cy = 0.5 * (ya + yb);
+    const double cx = tb.cx, cy = tb.cy;
     // grids are monotonic (np.arange in dense_lucaskanade); the tile extent bounds the radius
     const double rt = sqrt(0.25 * (xb - xa) * (xb - xa) + 0.25 * (yb - ya) * (yb - ya));
     const double binw = fmax(rt, 1e-300) * 0.5;
@@ -208,12 +211,8 @@ __global__ void __launch_bounds__(IDW_THREADS, FASTW ? 3 : 1) idw_kernel(const I
     // The bin only has to be CONSERVATIVE (never below the true distance bin) and the same in
     // both passes, so it is computed in float32 with 1e-5 slack instead of an FP64 sqrt.
     const float inv_binw_f = (float)inv_binw * (1.0f + 1e-5f);
-    auto bin_of = [&](int t) -> int {
-        const double2 s = pts[t];
-        const float dx = (float)(s.x - cx), dy = (float)(s.y - cy);
-        const float d = sqrtf(dx * dx + dy * dy) * inv_binw_f;
-        return d < (float)(IDW_BINS - 1) ? (int)d : IDW_BINS - 1;
-    };
+    tb.inv_binw_f = inv_binw_f;
+    auto bin_of = [&](int t) -> int { return tb.bin_of(pts, t); };
     for (int t = tid; t < npts; t += IDW_THREADS) {
         const int b = bin_of(t);
         if (t < IDW_CHUNK) sbin[t] = (unsigned char)b;
@@ -247,14 +246,47 @@ __global__ void __launch_bounds__(IDW_THREADS, FASTW ? 3 : 1) idw_kernel(const I
                 const double bb = R * inv_binw * (1.0 + 1e-9);
                 bmax = bb < (double)(IDW_BINS - 1) ? (int)bb : IDW_BINS - 1;
             }
-            s_bmax = bmax;
+            *s_bmax = bmax;
         }
     }
     __syncthreads();
-    const int bmax = s_bmax;
-    if (tid == 0) s_total = (bmax == IDW_BINS - 1) ? npts : hist[bmax + 1];
+    const int bmax = *s_bmax;
+    if (tid == 0) *s_total = (bmax == IDW_BINS - 1) ? npts : hist[bmax + 1];
     __syncthreads();
-    const int total = s_total;
+    const int total = *s_total;
+
+    tb.bmax = bmax;
+    tb.total = total;
+    tb.rt = rt;
+    tb.binw = binw;
+    tb.inv_binw_f = inv_binw_f;
+    return tb;
+}
+
+// FASTW: the weighting of dense_lucaskanade's call (two variables, power 1/2, unit resolution,
+// positive offset) from rsqrt; otherwise the general NumPy-order epilogue.
+template <int K, bool EXACT, bool PACKED, bool FASTW>
+__global__ void __launch_bounds__(IDW_THREADS, FASTW ? 3 : 1) idw_kernel(const IDWParams p) {
+    __shared__ double2 spt[IDW_CHUNK];
+    __shared__ int sidx[IDW_CHUNK];
+    __shared__ int hist[IDW_BINS];   // counts, then exclusive offsets
+    __shared__ int fill[IDW_BINS];
+    __shared__ unsigned char sbin[IDW_CHUNK];  // bin of the first IDW_CHUNK vectors
+    __shared__ int s_bmax, s_total;
+    if (p.tile_done && p.tile_done[blockIdx.y * gridDim.x + blockIdx.x]) return;
+    const int npts = p.npts_dev ? min(*p.npts_dev, p.npts_cap) : p.npts_cap;
+    const int k = min(min(p.k, npts), K);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    // a warp covers a compact 8x4 pixel patch: its lanes agree on most insert decisions
+    const int j = blockIdx.x * IDW_TX + (wid & 1) * 8 + (lane & 7);   // column
+    const int i = blockIdx.y * IDW_TY + (wid >> 1) * 4 + (lane >> 3);  // row
+    const double2 *__restrict__ pts = reinterpret_cast<const double2 *>(p.xy);
+    const bool active = j < p.nx && i < p.ny;
+    const double qx = p.gx[min(j, p.nx - 1)], qy = p.gy[min(i, p.ny - 1)];
+
+    const TileBound tb = tile_bound(p, pts, npts, k, hist, fill, sbin, &s_bmax, &s_total);
+    const int bmax = tb.bmax, total = tb.total;
+    auto bin_of = [&](int t) -> int { return tb.bin_of(pts, t); };
 
     unsigned long long bd[K];  // squared distances as ordered bit patterns
     int bi[K];
@@ -356,6 +388,107 @@ __global__ void __launch_bounds__(IDW_THREADS, FASTW ? 3 : 1) idw_kernel(const I
     }
 }
 
+// ---- 32-bit integer keys ---------------------------------------------------------------------
+// dense_lucaskanade's vectors sit on the half-pixel grid (medians of integer corners) and the
+// target grid on integers, so 4 * squared distance is a small INTEGER: with coordinates doubled,
+// (dx2*dx2 + dy2*dy2) in int32 is exact, and while it stays below 2^21 (neighbours within 724 px)
+// the pair (distance, vector index < 2048) is ONE 32-bit key.  The whole search then runs on the
+// integer pipe with single-register compares and selects -- half the instructions of the 64-bit
+// list, and no FP64 until the weights.  A tile whose search radius does not fit leaves its
+// `tile_done` flag clear and is filled by the 64-bit kernel launched behind this one.
+constexpr int IDW_KEY32_LIMIT = 1 << 21;
+
+template <int K>
+__global__ void __launch_bounds__(IDW_THREADS, 4) idw32_kernel(const IDWParams p) {
+    __shared__ int2 spi[IDW_CHUNK];   // doubled coordinates of the candidates
+    __shared__ int sidx[IDW_CHUNK];
+    __shared__ int hist[IDW_BINS];
+    __shared__ int fill[IDW_BINS];
+    __shared__ unsigned char sbin[IDW_CHUNK];
+    __shared__ int s_bmax, s_total;
+    const int npts = p.npts_cap;
+    const int k = K;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int j = blockIdx.x * IDW_TX + (wid & 1) * 8 + (lane & 7);   // column
+    const int i = blockIdx.y * IDW_TY + (wid >> 1) * 4 + (lane >> 3);  // row
+    const double2 *__restrict__ pts = reinterpret_cast<const double2 *>(p.xy);
+    const bool active = j < p.nx && i < p.ny;
+    const double qx = p.gx[min(j, p.nx - 1)], qy = p.gy[min(i, p.ny - 1)];
+    const TileBound tb = tile_bound(p, pts, npts, k, hist, fill, sbin, &s_bmax, &s_total);
+    const int bmax = tb.bmax, total = tb.total;
+    // every candidate lies within (bmax + 1) bins of the centre, every pixel within rt of it
+    const double reach = 2.0 * ((double)(bmax + 1) * tb.binw + tb.rt) * (1.0 + 1e-6);
+    if (total > IDW_CHUNK || bmax == IDW_BINS - 1 || !(reach * reach < (double)IDW_KEY32_LIMIT)) return;
+    for (int t = tid; t < npts; t += IDW_THREADS) {
+        const int b = t < IDW_CHUNK ? (int)sbin[t] : tb.bin_of(pts, t);
+        if (b <= bmax) {
+            const int o = hist[b] + atomicAdd(&fill[b], 1);
+            const double2 s = pts[t];
+            spi[o] = make_int2((int)(2.0 * s.x), (int)(2.0 * s.y));   // exact: multiples of 1/2
+            sidx[o] = t;
+        }
+    }
+    __syncthreads();
+    unsigned bd[K];
+    unsigned rej = ~0u;
+    if (active) {
+        const int qx2 = (int)(2.0 * qx), qy2 = (int)(2.0 * qy);
+        auto key_of = [&](int t) -> unsigned {
+            const int2 s = spi[t];
+            const int dx = s.x - qx2, dy = s.y - qy2;
+            return ((unsigned)(dx * dx + dy * dy) << 11) | (unsigned)sidx[t];
+        };
+#pragma unroll
+        for (int q = 0; q < K; q++) bd[q] = key_of(q);   // total >= k == K
+#pragma unroll
+        for (int c = 0; c < net_size<K>(); c++) {
+            const int a = net_a<K>(c), b = net_b<K>(c);
+            const unsigned va = bd[a], vb = bd[b];
+            bd[a] = min(va, vb);
+            bd[b] = max(va, vb);
+        }
+        for (int t = K; t < total; t++) {
+            const unsigned d2 = key_of(t);
+            const unsigned wd = bd[K - 1];
+            const bool better = d2 < wd;
+            const unsigned gone = better ? wd : d2;
+            rej = min(rej, gone);
+            if (better) {
+#pragma unroll
+                for (int q = K - 1; q >= 1; q--) bd[q] = d2 < bd[q - 1] ? bd[q - 1] : (d2 < bd[q] ? d2 : bd[q]);
+                if (d2 < bd[0]) bd[0] = d2;
+            }
+        }
+    }
+    if (p.tie_list != nullptr) {
+        const bool tie = active && ((bd[K - 1] >> 11) == (rej >> 11));
+        const unsigned bal = __ballot_sync(0xffffffffu, tie);
+        if (bal) {
+            int base = 0;
+            if (lane == __ffs(bal) - 1) base = atomicAdd(p.tie_count, __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+            if (tie) p.tie_list[base + __popc(bal & ((1u << lane) - 1u))] = i * p.nx + j;
+        }
+    }
+    if (tid == 0) p.tile_done[blockIdx.y * gridDim.x + blockIdx.x] = 1;
+    if (!active) return;
+    double ws = 0.0, ax = 0.0, ay = 0.0;
+    const double2 *__restrict__ v2 = reinterpret_cast<const double2 *>(p.vals);
+#pragma unroll
+    for (int q = 0; q < K; q++) {
+        const double d2 = (double)(bd[q] >> 11) * 0.25;
+        const double dist = d2 > 0.0 ? d2 * rsqrt(d2) : 0.0;
+        const double w = rsqrt(dist + p.offset);
+        const double2 v = v2[bd[q] & 2047u];
+        ws += w;
+        ax = fma(w, v.x, ax);
+        ay = fma(w, v.y, ay);
+    }
+    const double inv = 1.0 / ws;
+    p.out[((size_t)0 * p.ny + i) * p.nx + j] = ax * inv;
+    p.out[((size_t)1 * p.ny + i) * p.nx + j] = ay * inv;
+}
+
 // library-internal side stream of the calling thread's device + fork/join events: the tree build
 // (one CTA, latency bound) overlaps the exhaustive fill, the recomputation of the listed grid
 // points waits for both
@@ -415,6 +548,7 @@ extern "C" int b200_idw_fill(const double *xy, const double *vals, const int *np
     p.gx = xgrid; p.gy = ygrid; p.nx = nx; p.ny = ny;
     p.power = power; p.offset = dist_offset; p.mean_res = mean_res; p.out = out;
     p.tie_list = tie_list; p.tie_count = tie_count;
+    p.tile_done = nullptr;
     dim3 grid(b200::ceil_div(nx, IDW_TX), b200::ceil_div(ny, IDW_TY));
     dim3 block(IDW_THREADS);
     // the host knows npts only as a capacity when npts_dev is given; EXACT needs k == K <= npts
@@ -423,6 +557,17 @@ extern "C" int b200_idw_fill(const double *xy, const double *vals, const int *np
     // magnitude < 2^14; with <= 2048 vectors the index fits the zero low bits of the distance
     const bool packed = coords_on_16th_grid != 0 && exact_ok && npts_cap <= IDW_CHUNK;
     const bool fastw = nvar == 2 && power == 0.5 && mean_res == 1.0 && dist_offset > 0.0;
+    b200::Scratch done;
+    if (k == 20 && packed && fastw && coords_on_16th_grid == 2) {
+        // vectors on the half-pixel grid, grid on integers: 32-bit integer keys wherever the search
+        // radius allows, the 64-bit kernel behind it for the tiles it left
+        const size_t ntiles = (size_t)grid.x * grid.y;
+        B200_CUDA(done.alloc(ntiles, s));
+        B200_CUDA(cudaMemsetAsync(done.p, 0, ntiles, s));
+        p.tile_done = (uint8_t *)done.p;
+        idw32_kernel<20><<<grid, block, 0, s>>>(p);
+        B200_LAUNCH_CHECK();
+    }
     if (k == 20 && packed && fastw) idw_kernel<20, true, true, true><<<grid, block, 0, s>>>(p);
     else if (k == 20 && packed) idw_kernel<20, true, true, false><<<grid, block, 0, s>>>(p);
     else if (k == 20 && exact_ok && fastw) idw_kernel<20, true, false, true><<<grid, block, 0, s>>>(p);

@@ -14,6 +14,7 @@
 #include <math_constants.h>
 
 #include "common.cuh"
+#include "lk_common.cuh"
 #include "quantise_body.cuh"
 
 namespace {
@@ -27,67 +28,6 @@ __device__ __forceinline__ int reflect101(int i, int L) {
         if (i >= L) i = 2 * L - 2 - i;
     }
     return i;
-}
-
-// ---------------------------------------------------------------- block min/max reduce
-struct MM {
-    double mn, mx;
-    unsigned long long cnt;
-};
-
-__device__ __forceinline__ MM mm_merge(MM a, const MM &b) {
-    a.mn = fmin(a.mn, b.mn);
-    a.mx = fmax(a.mx, b.mx);
-    a.cnt += b.cnt;
-    return a;
-}
-
-__device__ __forceinline__ MM mm_warp(MM v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        MM t;
-        t.mn = __shfl_xor_sync(0xffffffffu, v.mn, o);
-        t.mx = __shfl_xor_sync(0xffffffffu, v.mx, o);
-        t.cnt = __shfl_xor_sync(0xffffffffu, v.cnt, o);
-        v = mm_merge(v, t);
-    }
-    return v;
-}
-
-__device__ __forceinline__ MM mm_block(MM v, MM *sm) {
-    v = mm_warp(v);
-    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-    const int w = tid >> 5, l = tid & 31;
-    const int nw = (blockDim.x * blockDim.y + 31) >> 5;
-    __syncthreads();
-    if (l == 0) sm[w] = v;
-    __syncthreads();
-    if (w == 0) {
-        MM t;
-        t.mn = CUDART_INF; t.mx = -CUDART_INF; t.cnt = 0;
-        if (l < nw) t = sm[l];
-        v = mm_warp(t);
-    }
-    return v;
-}
-
-// stats layout written by the final kernel: [min, max, count] (+3 per set)
-__global__ void __launch_bounds__(256) mm_final_kernel(const MM *__restrict__ part, int nparts, int nsets,
-                                                       double *__restrict__ stats) {
-    __shared__ MM sm[32];
-    for (int s = 0; s < nsets; s++) {
-        MM v;
-        v.mn = CUDART_INF; v.mx = -CUDART_INF; v.cnt = 0;
-        for (int i = threadIdx.x; i < nparts; i += blockDim.x) v = mm_merge(v, part[(size_t)s * nparts + i]);
-        v = mm_block(v, sm);
-        if (threadIdx.x == 0) {
-            // numpy's masked min()/max() of an all-masked array is `masked`; report NaN
-            stats[3 * s + 0] = v.cnt ? v.mn : CUDART_NAN;
-            stats[3 * s + 1] = v.cnt ? v.mx : CUDART_NAN;
-            stats[3 * s + 2] = (double)v.cnt;
-        }
-        __syncthreads();
-    }
 }
 
 // mask = user_mask | !isfinite(img) (np.ma.masked_invalid); min/max over unmasked
@@ -186,13 +126,6 @@ masked_minmax_kernel(const double *__restrict__ img, const uint8_t *__restrict__
         const MM r = mm_block(a[k], sm);
         if (threadIdx.x == 0 && threadIdx.y == 0) part[(size_t)k * nparts + blockIdx.x] = r;
     }
-}
-
-// (x - im_min) / (im_max - im_min) * 255 -> astype(uint8): truncation toward zero, and the
-// x86-64 behaviour of NumPy for out-of-range values (through int32, low byte kept)
-__device__ __forceinline__ uint8_t cast_u8(double v) {
-    if (!(v > -2147483649.0 && v < 2147483648.0)) return 0;  // cvttsd2si -> INT_MIN -> low byte 0
-    return (uint8_t)((int)v & 0xff);
 }
 
 // mode 0 (tracking/lucaskanade.py:144-160): masked pixels take the fill value, min/max over
@@ -370,20 +303,27 @@ box_chain_kernel(const double *__restrict__ rs, int h, int w, float *__restrict_
         cp_async_commit();  // one (possibly empty) group per row keeps the group count uniform
     };
     for (int y = 0; y < BOX_R; y++) issue(y);
-    for (int y0 = 0; y0 < h; y0 += 4) {
+    // BOX_U rows per round: ONE wait for the whole group, the BOX_U entering rows read from the ring
+    // into registers (independent loads), then the dependent add / subtract chain alone on the
+    // critical path -- the wait and the shared-memory latency are paid once per round, not per row
+    constexpr int BOX_U = 8;
+    for (int y0 = 0; y0 < h; y0 += BOX_U) {
+        cp_async_wait<BOX_R - BOX_U>();  // rows y0 .. y0 + BOX_U - 1 have landed
+        double in[BOX_U];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < BOX_U; u++) in[u] = ring_s[(y0 + u) % BOX_R][lane];
+#pragma unroll
+        for (int u = 0; u < BOX_U; u++) {
             const int y = y0 + u;
-            cp_async_wait<BOX_R - 1>();  // the oldest outstanding row (y) has landed
             if (y < h) {
-                const double in = ring_s[y % BOX_R][lane];
-                const double a = __dadd_rn(S, in);
-                S = __dsub_rn(a, delay[u]);  // y0 is a multiple of 4
-                delay[u] = in;
+                const double a = __dadd_rn(S, in[u]);
+                S = __dsub_rn(a, delay[u & 3]);  // y0 is a multiple of 4
+                delay[u & 3] = in[u];
                 if (x < w) dst[(size_t)y * w + x] = __double2float_rn(a);
             }
-            issue(y + BOX_R);  // refill the slot just consumed
         }
+#pragma unroll
+        for (int u = 0; u < BOX_U; u++) issue(y0 + u + BOX_R);  // refill the slots just consumed
     }
 }
 

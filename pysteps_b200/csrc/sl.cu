@@ -117,15 +117,17 @@ __device__ __forceinline__ double half_of(double u) {
 }
 
 // ---- slow (generic) path: any coordinate, per-tap index clamping --------------------
-__device__ __noinline__ void slow_velocity(const double2 *__restrict__ Vi, int m, int n, double cy,
-                                           double cx, double &vx, double &vy) {
+// (results by value: reference parameters of a non-inlined function would pin the caller's
+// velocity registers to the local-memory stack -- one STL pair per sample on the FAST path too)
+__device__ __noinline__ double2 slow_velocity(const double2 *__restrict__ Vi, int m, int n, double cy,
+                                              double cx) {
     const Axis ay = make_axis(cy, m), ax = make_axis(cx, n);
     const double2 *r0 = Vi + (size_t)ay.i0 * n;
     const double2 *r1 = Vi + (size_t)ay.i1 * n;
     const double2 a00 = __ldg(r0 + ax.i0), a01 = __ldg(r0 + ax.i1);
     const double2 a10 = __ldg(r1 + ax.i0), a11 = __ldg(r1 + ax.i1);
-    vx = bilin(a00.x, a01.x, a10.x, a11.x, ay.w0, ay.w1, ax.w0, ax.w1);
-    vy = bilin(a00.y, a01.y, a10.y, a11.y, ay.w0, ay.w1, ax.w0, ax.w1);
+    return make_double2(bilin(a00.x, a01.x, a10.x, a11.x, ay.w0, ay.w1, ax.w0, ax.w1),
+                        bilin(a00.y, a01.y, a10.y, a11.y, ay.w0, ay.w1, ax.w0, ax.w1));
 }
 
 // map_coordinates(precip, order=1, mode, cval) for one pixel (:221-232), generic path
@@ -184,7 +186,9 @@ __device__ __forceinline__ Foot sample_velocity(const double2 *__restrict__ Vi, 
         vx = bilin(a00.x, a01.x, a10.x, a11.x, f.wy0, f.wy1, f.wx0, f.wx1);
         vy = bilin(a00.y, a01.y, a10.y, a11.y, f.wy0, f.wy1, f.wx0, f.wx1);
     } else {
-        slow_velocity(Vi, m, n, cy, cx, vx, vy);
+        const double2 v = slow_velocity(Vi, m, n, cy, cx);
+        vx = v.x;
+        vy = v.y;
     }
     if (vel_f32) {
         // float32 velocity: map_coordinates returns the input dtype, so the reference

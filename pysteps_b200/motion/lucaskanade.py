@@ -45,9 +45,9 @@ class _Frame:
     are allocated up front (on the caller's stream) so that the work itself can be enqueued on
     either stream without involving the caching allocator."""
     __slots__ = ("img", "user_mask", "mask", "stats0", "opened", "stats", "q_track",
-                 "prepared", "have_stats", "have_q", "qflag")
+                 "prepared", "have_stats", "have_q", "qflag", "q_det", "valid")
 
-    def __init__(self, img_d, user_mask_d, m, n, size_opening, f32=False):
+    def __init__(self, img_d, user_mask_d, m, n, size_opening, f32=False, fused=False, detect=False):
         # frames that were float32 at the API are scaled to uint8 in float32 arithmetic, as NumPy
         # does for a float32 array (tracking/lucaskanade.py:144-160, feature/shitomasi.py:141-151)
         self.qflag = 2 if f32 else 0
@@ -55,10 +55,27 @@ class _Frame:
         self.user_mask = user_mask_d
         self.mask = torch.empty((m, n), dtype=torch.uint8, device="cuda")
         self.stats0 = torch.empty(3, dtype=torch.float64, device="cuda")
-        self.opened = torch.empty((m, n), dtype=torch.float64, device="cuda") if size_opening > 0 else img_d
+        # fused front end (csrc/lk_frontend.cu): the opened float64 image is never materialised
+        self.opened = None if fused else (torch.empty((m, n), dtype=torch.float64, device="cuda")
+                                          if size_opening > 0 else img_d)
         self.stats = torch.empty(12, dtype=torch.float64, device="cuda")
         self.q_track = torch.empty((m, n), dtype=torch.uint8, device="cuda")
+        self.q_det = torch.empty((m, n), dtype=torch.uint8, device="cuda") if (fused and detect) else None
+        self.valid = torch.empty((m, n), dtype=torch.uint8, device="cuda") if (fused and detect) else None
         self.prepared = self.have_stats = self.have_q = False
+
+
+def _front_end(f, m, n, size_opening, buffer_mask):
+    """Everything dense_lucaskanade does to a frame before looking for features, three passes over
+    it (csrc/lk_frontend.cu: TMA-staged halo tiles): mask, opening, the four min/max sets, the
+    tracker's and -- for a frame that is the first of a pair -- the detector's uint8 image."""
+    if f.prepared:
+        return f
+    _call("b200_lk_frontend", f.img.data_ptr(), _device.ptr(f.user_mask), m, n, int(size_opening),
+          int(buffer_mask), f.qflag, f.mask.data_ptr(), f.stats0.data_ptr(), f.stats.data_ptr(),
+          f.q_track.data_ptr(), _device.ptr(f.q_det), _device.ptr(f.valid), _s())
+    f.prepared = f.have_stats = f.have_q = True
+    return f
 
 
 def _prepare_frame(f, m, n, size_opening):
@@ -217,10 +234,15 @@ def dense_lucaskanade(input_images, lk_kwargs=None, fd_method="shitomasi", fd_kw
     # while the side stream prepares the next frame and builds both pyramids.
     main = torch.cuda.current_stream()
     side = _side_stream()
-    frames = [_Frame(frames_d[t], None if user_mask_d is None else user_mask_d[t], m, n, size_opening, f32)
+    # fused, TMA-tiled front end whenever the copy engine can address the frame (16-byte rows)
+    fused = n % 2 == 0 and 0 <= buffer_mask <= 5
+    frames = [_Frame(frames_d[t], None if user_mask_d is None else user_mask_d[t], m, n, size_opening, f32,
+                     fused, t < nr_fields - 1)
               for t in range(nr_fields)]
 
     def prepare(t):
+        if fused:
+            return _front_end(frames[t], m, n, size_opening, buffer_mask)
         return _prepare_frame(frames[t], m, n, size_opening)
 
     pool_cap = max_corners * max(nr_fields - 1, 1)
@@ -255,13 +277,16 @@ def dense_lucaskanade(input_images, lk_kwargs=None, fd_method="shitomasi", fd_kw
         f = frames[t]
         st = _frame_stats(f, m, n, buffer_mask)
         # ---- main stream: feature detection on the previous frame (:227) -------------------
-        q_det = torch.empty((m, n), dtype=torch.uint8, device="cuda")
-        valid = torch.empty((m, n), dtype=torch.uint8, device="cuda")
         eig = torch.empty((m, n), dtype=torch.float32, device="cuda")
         ev_stats = torch.cuda.Event()
         ev_stats.record(main)
-        _call("b200_quantise_u8", f.opened.data_ptr(), f.mask.data_ptr(), m, n, 1 | f.qflag, buffer_mask,
-              st.data_ptr(), st.data_ptr(), q_det.data_ptr(), valid.data_ptr(), _s())
+        if fused:
+            q_det, valid = f.q_det, f.valid
+        else:
+            q_det = torch.empty((m, n), dtype=torch.uint8, device="cuda")
+            valid = torch.empty((m, n), dtype=torch.uint8, device="cuda")
+            _call("b200_quantise_u8", f.opened.data_ptr(), f.mask.data_ptr(), m, n, 1 | f.qflag, buffer_mask,
+                  st.data_ptr(), st.data_ptr(), q_det.data_ptr(), valid.data_ptr(), _s())
         _call("b200_min_eig", q_det.data_ptr(), m, n, eig.data_ptr(), _s())
         # ---- side stream: next frame + both pyramids (needs this frame's stats only).  Enqueued
         # after the eigenvalue map so that it fills the SMs the sequential box-filter chains,
@@ -361,12 +386,14 @@ def dense_lucaskanade(input_images, lk_kwargs=None, fd_method="shitomasi", fd_kw
         xgrid, ygrid = _pixel_grid(0, n), _pixel_grid(r0, r1)
         # integer pixel grid + corner coordinates that are integers or cell medians (multiples
         # of 1/2): squared distances are exact small multiples of 1/256 -> packed-key fast path
-        on_grid = bool(np.all(xy_h * 16.0 == np.rint(xy_h * 16.0)) and np.abs(xy_h).max() < 16384.0
-                       and max(m, n) < 16384)
+        on_grid = int(bool(np.all(xy_h * 16.0 == np.rint(xy_h * 16.0)) and np.abs(xy_h).max() < 16384.0
+                           and max(m, n) < 16384))
+        if on_grid and np.all(xy_h * 2.0 == np.rint(xy_h * 2.0)):
+            on_grid = 2  # half-pixel grid (the usual case: medians of integers): 32-bit integer keys
         # exhaustive tile search; grid points whose neighbour set depends on cKDTree's tie order are
         # recomputed from its query (csrc/idw.cu, knn.cu)
         _call("b200_idw_fill", dec_xy.data_ptr(), dec_uv.data_ptr(), None, n_dec, 2, int(min(int(k), n_dec)),
-              power, dist_offset, 1.0, xgrid.data_ptr(), n, ygrid.data_ptr(), mb, int(on_grid),
+              power, dist_offset, 1.0, xgrid.data_ptr(), n, ygrid.data_ptr(), mb, on_grid,
               out.data_ptr(), _s())
 
     if verbose:

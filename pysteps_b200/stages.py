@@ -248,6 +248,10 @@ def idwinterp2d(xy_coord, values, xgrid, ygrid, power=0.5, k=20, dist_offset=0.5
         on_grid = bool(np.all(xy_h * 16.0 == np.rint(xy_h * 16.0)) and np.abs(xy_h).max() < 16384.0
                        and np.all(xg * 16.0 == np.rint(xg * 16.0)) and np.all(yg * 16.0 == np.rint(yg * 16.0))
                        and max(np.abs(xg).max(), np.abs(yg).max()) < 16384.0)
+        on_grid = int(on_grid)
+        if on_grid and np.all(xy_h * 2.0 == np.rint(xy_h * 2.0)) and np.all(xg == np.rint(xg)) \
+                and np.all(yg == np.rint(yg)):
+            on_grid = 2  # half-pixel vectors on an integer grid: 32-bit integer keys (csrc/idw.cu)
         dxy = _device.to_device(np.ascontiguousarray(xy_h))
         dv = _device.to_device(np.ascontiguousarray(v2))
         kk = int(min(int(k), npts))

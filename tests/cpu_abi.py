@@ -284,6 +284,22 @@ def _lk_quantise(img, mask, m, n, mode, dilate, stats, fill, out, valid, stream)
     _view(out, (m, n), np.uint8)[...] = q
 
 
+def _lk_frontend(img, user_mask, m, n, size_opening, buffer_mask, flags, mask, stats0, stats, q_track, q_det,
+                 valid, stream):
+    """the four stage entry points in sequence, on host scratch"""
+    opened = np.empty((m, n))
+    op_ptr = opened.ctypes.data
+    _lk_mask_invalid(img, user_mask, m, n, mask, stats0, stream)
+    if size_opening > 0:
+        _lk_morph_opening(img, mask, m, n, size_opening, stats0, stats0, op_ptr, stream)
+    else:
+        opened[...] = _view(img, (m, n))
+    _lk_masked_minmax(op_ptr, mask, m, n, buffer_mask, stats0, stats, stream)
+    _lk_quantise(op_ptr, mask, m, n, 0 | flags, 0, stats, stats, q_track, None, stream)
+    if _addr(q_det) is not None:
+        _lk_quantise(op_ptr, mask, m, n, 1 | flags, buffer_mask, stats, stats, q_det, valid, stream)
+
+
 def _lk_min_eig(q, m, n, eig, stream):
     from oracle import lucaskanade as ora_lk
     img = _view(q, (m, n), np.uint8).copy()
@@ -398,7 +414,7 @@ _TABLE_LK = {"b200_mask_invalid": _lk_mask_invalid, "b200_morph_opening": _lk_mo
              "b200_masked_minmax": _lk_masked_minmax, "b200_quantise_u8": _lk_quantise,
              "b200_min_eig": _lk_min_eig, "b200_good_features": _lk_good_features,
              "b200_lk_build_pyramid": _lk_build_pyramid, "b200_lk_track": _lk_track,
-             "b200_lk_compact_tracks": _lk_compact_tracks, "b200_detect_outliers": _lk_detect_outliers,
+             "b200_lk_compact_tracks": _lk_compact_tracks, "b200_lk_frontend": _lk_frontend, "b200_detect_outliers": _lk_detect_outliers,
              "b200_compact_rows": _lk_compact_rows, "b200_decluster": _lk_decluster,
              "b200_idw_fill": _lk_idw_fill, "b200_idw_fill_ckdtree": _lk_idw_fill_ckdtree, "b200_fill_f64": _fill_f64}
 

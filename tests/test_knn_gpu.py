@@ -101,6 +101,8 @@ def test_grid_fill_equals_the_tree_search_everywhere(env, kind):
         vals = np.stack([2 + rng.standard_normal(npts), -1 + rng.standard_normal(npts)], 1)
         gx, gy = np.arange(nx, dtype=np.float64), np.arange(ny, dtype=np.float64)
         on_grid = int(kind != "real" and xy.max() < 16384)
+        if on_grid and np.all(xy * 2 == np.rint(xy * 2)):
+            on_grid = 2  # half-pixel vectors, integer grid: the 32-bit integer-key kernel
         dxy, dv = torch.from_numpy(xy).cuda(), torch.from_numpy(vals).cuda()
         dgx, dgy = torch.from_numpy(gx).cuda(), torch.from_numpy(gy).cuda()
         for k in (20, 8, 13):
