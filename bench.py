@@ -681,7 +681,7 @@ def load_peaks():
 # 148 SMs at 1.965 GHz -> 68.8, i.e. 64/clk); instruction count per pixel-leadtime of
 # sl_multistep_kernel from its SASS (tools/sass_count.py, profiles/r02_sl_kernel.md)
 FP64_PER_CLK_SM = 64
-SL_FP64_INSTR_PER_PIXEL_LEADTIME = 89
+SL_FP64_INSTR_PER_PIXEL_LEADTIME = 94
 
 
 def measure(b, w, steps, warmup, clocks=None, solo=False):

@@ -119,6 +119,21 @@ front_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ F
     };
     int t = blockIdx.x;
     if (t < tiles && tid == 0) issue(t, 0);
+    // mask bytes of a tile (1 byte per pixel, 2-pixel halo, zero outside the image): fetched into
+    // registers one tile ahead, so their L2 latency hides behind the current tile's arithmetic
+    constexpr int MPT = (BH * BW + FTHREADS - 1) / FTHREADS;
+    uint8_t mreg[MPT];
+    auto fetch_mask = [&](int tt) {
+        const int x0 = (tt % tiles_x) * FW, y0 = (tt / tiles_x) * FH;
+#pragma unroll
+        for (int k = 0; k < MPT; k++) {
+            const int e = tid + k * FTHREADS;
+            const int ly = e / BW, lx = e - ly * BW;
+            const int y = y0 + ly - HALO, x = x0 + lx - HALO;
+            mreg[k] = (e < BH * BW && y >= 0 && y < m && x >= 0 && x < n) ? p.mask[(size_t)y * n + x] : 0;
+        }
+    };
+    if (t < tiles) fetch_mask(t);
 
     const double minval = p.stats0[0];
     const bool opening = p.opening != 0;
@@ -137,12 +152,12 @@ front_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ F
         G.x0 = (t % tiles_x) * FW; G.y0 = (t / tiles_x) * FH; G.m = m; G.n = n;
         const double *img = s_img[slot];
         uint8_t *msk = s_msk[slot];
-        // mask tile (1 byte per pixel, 2-pixel halo) by ordinary loads; zero outside the image
-        for (int e = tid; e < BH * BW; e += FTHREADS) {
-            const int ly = e / BW, lx = e - ly * BW;
-            const int y = G.y0 + ly - HALO, x = G.x0 + lx - HALO;
-            msk[ly * MW + lx] = (y >= 0 && y < m && x >= 0 && x < n) ? p.mask[(size_t)y * n + x] : 0;
+#pragma unroll
+        for (int k = 0; k < MPT; k++) {
+            const int e = tid + k * FTHREADS;
+            if (e < BH * BW) msk[(e / BW) * MW + e % BW] = mreg[k];
         }
+        if (tn < tiles) fetch_mask(tn);
         mbar_wait(&s_bar[slot], (unsigned)((it >> 1) & 1));
         __syncthreads();
         if (opening) {

@@ -89,31 +89,17 @@ __device__ __forceinline__ Axis make_axis(double c, int L) {
     return a;
 }
 
-// 0.0 + p for a finite or non-finite double WITHOUT the FP64 pipe: the addition only changes
-// p = -0.0 (to +0.0); everything else, NaN payloads included, passes through.
-__device__ __forceinline__ double plus_zero(double p) {
-    const int hi = __double2hiint(p), lo = __double2loint(p);
-    return ((hi ^ (int)0x80000000) | lo) == 0 ? 0.0 : p;
-}
-
 // sum_{taps} ((a * wy) * wx), left to right from 0.0 (scipy accumulation order)
+// (the leading 0.0 + is scipy's accumulator start: it turns a first product of -0.0 into +0.0.
+// Doing that with integer compares instead, and velocity_inc / 2 by an exponent decrement, was
+// measured: 3 % SLOWER -- the kernel is as much issue-bound as FP64-bound, see profiles/r02_sl_kernel.md)
 __device__ __forceinline__ double bilin(double a00, double a01, double a10, double a11,
                                         double wy0, double wy1, double wx0, double wx1) {
-    double t = plus_zero(__dmul_rn(__dmul_rn(a00, wy0), wx0));
+    double t = __dadd_rn(0.0, __dmul_rn(__dmul_rn(a00, wy0), wx0));
     t = __dadd_rn(t, __dmul_rn(__dmul_rn(a01, wy0), wx1));
     t = __dadd_rn(t, __dmul_rn(__dmul_rn(a10, wy1), wx0));
     t = __dadd_rn(t, __dmul_rn(__dmul_rn(a11, wy1), wx1));
     return t;
-}
-
-// u * 0.5 on the integer pipe: for a normal u whose half is normal too the product is u with the
-// exponent field one lower (exact); zeros, subnormals, the smallest normals, infinities and NaN
-// take the multiplication.
-__device__ __forceinline__ double half_of(double u) {
-    const int hi = __double2hiint(u);
-    const unsigned e = ((unsigned)hi >> 20) & 0x7ffu;
-    if (e >= 2u && e <= 2046u) return __hiloint2double(hi - 0x00100000, __double2loint(u));
-    return __dmul_rn(u, 0.5);
 }
 
 // ---- slow (generic) path: any coordinate, per-tap index clamping --------------------
@@ -174,9 +160,10 @@ __device__ __forceinline__ Foot footprint(double cy, double cx, int n, int ymax,
 
 // interpolate_motion (semilagrangian.py:181-198) for one pixel; returns the footprint so
 // the precip warp at the same coordinates can reuse it
+template <bool VF32>
 __device__ __forceinline__ Foot sample_velocity(const double2 *__restrict__ Vi, int m, int n,
                                                 int ymax, int xmax, double cy, double cx,
-                                                double scale, int n_iter, bool vel_f32,
+                                                double scale, int n_iter,
                                                 double &vx, double &vy) {
     const Foot f = footprint(cy, cx, n, ymax, xmax);
     if (f.interior) {
@@ -190,7 +177,7 @@ __device__ __forceinline__ Foot sample_velocity(const double2 *__restrict__ Vi, 
         vx = v.x;
         vy = v.y;
     }
-    if (vel_f32) {
+    if (VF32) {
         // float32 velocity: map_coordinates returns the input dtype, so the reference
         // stores the sampled increment rounded to float32 (:192-193)
         vx = (double)__double2float_rn(vx);
@@ -211,7 +198,9 @@ template <> __device__ __forceinline__ double from_double<double>(double v) { re
 
 // NITER1: n_iter == 1 (the default and what every nowcast method uses) compiled without
 // the inner loop / division branches.
-template <typename F, bool NITER1, int BY>
+// VF32: the velocity was float32 at the API (a compile-time fact of the launch: the rounding of
+// the sampled increments costs conversion-pipe slots even when predicated off).
+template <typename F, bool NITER1, int BY, bool VF32>
 __global__ void __launch_bounds__(SL_BX *BY)
 sl_multistep_kernel(const __grid_constant__ SLParams p) {
     const int x = blockIdx.x * SL_BX + threadIdx.x;
@@ -227,7 +216,6 @@ sl_multistep_kernel(const __grid_constant__ SLParams p) {
     const double2 *__restrict__ Vi = (const double2 *)p.Vi;
     const double *__restrict__ P = (const double *)p.precip;
     F *__restrict__ out = (F *)p.out + idx;
-    const bool vel_f32 = p.vel_f32 != 0;
     const int n_iter = NITER1 ? 1 : p.n_iter;
     const int mode = p.mode;
     const double cval = p.cval;
@@ -252,8 +240,8 @@ sl_multistep_kernel(const __grid_constant__ SLParams p) {
     } else if (p.init_mode == SL_INIT_PREV) {
         // :205-207
         dx = p.disp_in[idx]; dy = p.disp_in[N + idx];
-        sample_velocity(Vi, m, n, ymax, xmax, __dadd_rn(gy, dy), __dadd_rn(gx, dx), p.scale[0],
-                        n_iter, vel_f32, ux, uy);
+        sample_velocity<VF32>(Vi, m, n, ymax, xmax, __dadd_rn(gy, dy), __dadd_rn(gx, dx), p.scale[0],
+                        n_iter, ux, uy);
     } else {
         dx = p.disp_in[idx]; dy = p.disp_in[N + idx];
         ux = p.vinc_in[idx]; uy = p.vinc_in[N + idx];
@@ -267,22 +255,22 @@ sl_multistep_kernel(const __grid_constant__ SLParams p) {
         if (n_iter > 0) {
             for (int k = 0; k < n_iter; k++) {  // :211-214
                 // velocity_inc / 2.0 == velocity_inc * 0.5 exactly
-                const double hx = __dsub_rn(dx, half_of(ux));
-                const double hy = __dsub_rn(dy, half_of(uy));
-                sample_velocity(Vi, m, n, ymax, xmax, __dadd_rn(gy, hy), __dadd_rn(gx, hx), scale,
-                                n_iter, vel_f32, ux, uy);
+                const double hx = __dsub_rn(dx, __dmul_rn(ux, 0.5));
+                const double hy = __dsub_rn(dy, __dmul_rn(uy, 0.5));
+                sample_velocity<VF32>(Vi, m, n, ymax, xmax, __dadd_rn(gy, hy), __dadd_rn(gx, hx), scale,
+                                n_iter, ux, uy);
                 dx = __dsub_rn(dx, ux);
                 dy = __dsub_rn(dy, uy);
-                f = sample_velocity(Vi, m, n, ymax, xmax, __dadd_rn(gy, dy), __dadd_rn(gx, dx),
-                                    scale, n_iter, vel_f32, ux, uy);
+                f = sample_velocity<VF32>(Vi, m, n, ymax, xmax, __dadd_rn(gy, dy), __dadd_rn(gx, dx),
+                                    scale, n_iter, ux, uy);
             }
             // the precip warp samples at xy + displacement: the coordinates (hence footprint
             // and weights) of the last velocity gather
             have_foot = true;
         } else {  // :215-219
             if (ti + p.ti_offset > 0 || p.has_prev)
-                sample_velocity(Vi, m, n, ymax, xmax, __dadd_rn(gy, dy), __dadd_rn(gx, dx), scale,
-                                n_iter, vel_f32, ux, uy);
+                sample_velocity<VF32>(Vi, m, n, ymax, xmax, __dadd_rn(gy, dy), __dadd_rn(gx, dx), scale,
+                                n_iter, ux, uy);
             dx = __dsub_rn(dx, ux);
             dy = __dsub_rn(dy, uy);
         }
@@ -293,7 +281,7 @@ sl_multistep_kernel(const __grid_constant__ SLParams p) {
             if (f.interior) {
                 const double *q = P + f.base;
                 v = bilin(__ldg(q), __ldg(q + 1), __ldg(q + n), __ldg(q + n + 1), f.wy0, f.wy1,
-                          f.wx0, f.wx1);
+                                  f.wx0, f.wx1);
             } else {
                 v = slow_precip(P, m, n, cy, cx, mode, cval);
             }
@@ -410,10 +398,11 @@ int sl_run(const void *precip, const void *velocity, const double *xy, const dou
         p.disp_out = last ? disp_out : (double *)st_disp.p;
         p.vinc_out = last ? nullptr : (double *)st_vinc.p;
         p.out = precip ? (void *)((F *)out + (size_t)p.ti_offset * NB) : nullptr;
+        constexpr bool VF = sizeof(FV) == 4;
         if (n_iter == 1)
-            sl_multistep_kernel<F, true, SL_BY><<<grid, block, 0, stream>>>(p);
+            sl_multistep_kernel<F, true, SL_BY, VF><<<grid, block, 0, stream>>>(p);
         else
-            sl_multistep_kernel<F, false, SL_BY><<<grid, block, 0, stream>>>(p);
+            sl_multistep_kernel<F, false, SL_BY, VF><<<grid, block, 0, stream>>>(p);
         B200_LAUNCH_CHECK();
     }
     return 0;
@@ -466,10 +455,11 @@ int sl_trajectories(const void *velocity, const double *xy, const double *disp_p
         }
         p.disp_out = disp_steps + (size_t)c * 2 * NB;
         p.vinc_out = (double *)st_vinc.p;
+        constexpr bool VF = sizeof(FV) == 4;
         if (n_iter == 1)
-            sl_multistep_kernel<double, true, SL_BY><<<grid, block, 0, stream>>>(p);
+            sl_multistep_kernel<double, true, SL_BY, VF><<<grid, block, 0, stream>>>(p);
         else
-            sl_multistep_kernel<double, false, SL_BY><<<grid, block, 0, stream>>>(p);
+            sl_multistep_kernel<double, false, SL_BY, VF><<<grid, block, 0, stream>>>(p);
         B200_LAUNCH_CHECK();
     }
     return 0;

@@ -115,6 +115,14 @@ vet_eval_kernel(const double *__restrict__ sd, const double *__restrict__ templ,
     const double xg0 = centre(l0, g.xss), xg1 = centre(l1, g.xss);
     const double yg0 = centre(m0, g.yss), yg1 = centre(m1, g.yss);
     const double area = __dmul_rn(__dsub_rn(xg1, xg0), __dsub_rn(yg1, yg0));
+    // x / area: when the area is a power of two (sector sides 64, 128, ... -- every level of a
+    // 2^k-sized frame) the quotient equals x * (1 / area) exactly, bit for bit, and the four
+    // divisions per pixel become multiplications
+    const long long abits = __double_as_longlong(area);
+    const int aexp = (int)((abits >> 52) & 0x7ff);
+    const bool area_pow2 = (abits & 0x000fffffffffffffll) == 0 && aexp > 64 && aexp < 1983;
+    const double inv_area = area_pow2 ? __ddiv_rn(1.0, area) : 0.0;
+    auto over_area = [&](double num) -> double { return area_pow2 ? __dmul_rn(num, inv_area) : __ddiv_rn(num, area); };
     const size_t S = (size_t)g.xs * g.ys;
     double s00[2], s01[2], s10[2], s11[2];
 #pragma unroll
@@ -136,14 +144,14 @@ vet_eval_kernel(const double *__restrict__ sd, const double *__restrict__ templ,
         const double xi = (double)i, yj = (double)j;
         // _vet.pyx:436-454, expression order as written
         const double xy = __dmul_rn(xi, yj);
-        const double c0 = __ddiv_rn(__dadd_rn(__dsub_rn(__dsub_rn(__dmul_rn(xg1, yg1), __dmul_rn(xi, yg1)),
-                                                        __dmul_rn(xg1, yj)), xy), area);
-        const double c1 = __ddiv_rn(__dsub_rn(__dadd_rn(__dadd_rn(__dmul_rn(-xg1, yg0), __dmul_rn(xi, yg0)),
-                                                        __dmul_rn(xg1, yj)), xy), area);
-        const double c2 = __ddiv_rn(__dsub_rn(__dadd_rn(__dadd_rn(__dmul_rn(-xg0, yg1), __dmul_rn(xi, yg1)),
-                                                        __dmul_rn(xg0, yj)), xy), area);
-        const double c3 = __ddiv_rn(__dadd_rn(__dsub_rn(__dsub_rn(__dmul_rn(xg0, yg0), __dmul_rn(xi, yg0)),
-                                                        __dmul_rn(xg0, yj)), xy), area);
+        const double c0 = over_area(__dadd_rn(__dsub_rn(__dsub_rn(__dmul_rn(xg1, yg1), __dmul_rn(xi, yg1)),
+                                                        __dmul_rn(xg1, yj)), xy));
+        const double c1 = over_area(__dsub_rn(__dadd_rn(__dadd_rn(__dmul_rn(-xg1, yg0), __dmul_rn(xi, yg0)),
+                                                        __dmul_rn(xg1, yj)), xy));
+        const double c2 = over_area(__dsub_rn(__dadd_rn(__dadd_rn(__dmul_rn(-xg0, yg1), __dmul_rn(xi, yg1)),
+                                                        __dmul_rn(xg0, yj)), xy));
+        const double c3 = over_area(__dadd_rn(__dsub_rn(__dsub_rn(__dmul_rn(xg0, yg0), __dmul_rn(xi, yg0)),
+                                                        __dmul_rn(xg0, yj)), xy));
         double disp[2];
 #pragma unroll
         for (int a = 0; a < 2; a++)  // :456-462
