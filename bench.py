@@ -597,6 +597,30 @@ def build_ensemble(b, w, solo=False):
                                        return_displacement=True, b200_resident=resident)
         return last
 
+    from pysteps_b200.extrapolation.semilagrangian import extrapolate_members
+    stack = torch.stack(member_precip) if member_precip else None
+
+    def member_loop_batched(V):
+        """the same member-steps through the batched entry point: all members of this rank in one
+        perturbation launch + one trajectory launch per lead time (b200_sl_step_batched)"""
+        perts = [bps_init(V, 1.0 / KMPP, DT_MIN, randstate=np.random.RandomState(1000 + i)) for i in mine]
+        disp, last = None, None
+        for t in range(T):
+            Vm = [V + bps_gen(pt, (t + 1) * DT_MIN) for pt in perts]
+            last, disp = extrapolate_members(stack, Vm, displacement_prev=disp)
+        return last
+
+    def step_device_batched():
+        if solo and rank != 0:
+            return None
+        if rank == 0:
+            Vd = motion(frames_d)
+        else:
+            Vd = torch.empty((2, m, n), dtype=torch.float64, device="cuda")
+        if not solo:
+            Vd = b.shard.broadcast_field(Vd, src=0)
+        return member_loop_batched(Vd) if mine else None
+
     def step_device():
         """rank 0: motion field; broadcast; member loop on device-resident fields."""
         del marks[:]
@@ -633,7 +657,8 @@ def build_ensemble(b, w, solo=False):
     # per rank: frames + field once, one precipitation field up / one down per member-step
     h2d = frames_h.nbytes + 2 * m * n * 8 + len(mine) * T * precip_h.nbytes
     d2h = 2 * m * n * 8 + len(mine) * T * precip_h.nbytes
-    info = dict(h2d=h2d, d2h=d2h, rows_here=m, lk=True, nfields=members, marks=marks, members_here=len(mine))
+    info = dict(h2d=h2d, d2h=d2h, rows_here=m, lk=True, nfields=members, marks=marks, members_here=len(mine),
+                step_device_batched=step_device_batched)
     return step_device, step_host, info
 
 
@@ -699,6 +724,11 @@ def measure(b, w, steps, warmup, clocks=None, solo=False):
         clocks.__exit__(None, None, None)
     nfields = info["nfields"]
     value = nfields * steps * T * m * n / (dev_ms * 1e-3) / 1e6
+    stage_trace, stage_steps = b.stage_trace, b.stage_steps
+    ms_b = None
+    if w["members"] and not solo:
+        # the same ensemble step with the members of a rank batched into one launch per lead time
+        ms_b, _, _, _ = b.time_device(info["step_device_batched"], steps, warmup)
     e2e_s, out = b.time_host(step_host, steps, warmup)
     e2e_val = nfields * steps * T * m * n / e2e_s / 1e6
     if b.rank != 0:
@@ -717,10 +747,16 @@ def measure(b, w, steps, warmup, clocks=None, solo=False):
            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(info["h2d"]),
                    "d2h_bytes_per_step": int(info["d2h"]), "ms_per_step": 1e3 * e2e_s / steps},
            "gpu_launches": int(launches), "_trace": tr, "_info": info,
-           "_stage_trace": b.stage_trace, "_stage_steps": b.stage_steps}
+           "_stage_trace": stage_trace, "_stage_steps": stage_steps}
     if phases is not None and len(phases) == 2:
         blk["motion_and_broadcast_ms"] = phases[0]
         blk["member_loop_ms"] = phases[1]
+    if ms_b is not None:
+        blk["batched_ms_per_step"] = ms_b / steps
+        blk["batched_value"] = nfields * steps * T * m * n / (ms_b * 1e-3) / 1e6
+        blk["batched_note"] = ("extrapolate_members / b200_sl_step_batched (all members of a rank in one launch "
+                               "per lead time): not a call the unmodified nowcast_main_loop makes; `value` is "
+                               "the per-member call shape")
     return blk
 
 

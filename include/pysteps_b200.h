@@ -150,6 +150,21 @@ int b200_bps_perturb_velocity(const void *velocity, int velocity_dtype, int m, i
                               double a_par, double a_perp, double vsf, int what, double *out,
                               double *n_nonfinite, void *stream);
 
+/* One lead time of EVERY ensemble member of this GPU (nowcasts/utils.py:440-458: per member a
+ * single-step extrapolator call with its own BPS-perturbed motion field, precipitation field and
+ * carried displacement) in one perturbation launch and one trajectory launch per 8 members.
+ *   velocity   (2,m,n) planar base field (device);  pert_coefs  HOST, members x 2: the (a, b) =
+ *              (g_par(t) eps_par, g_perp(t) eps_perp) of noise/motion.py:177-180 per member
+ *   precip     (members,m,n);  disp_prev (members,2,m,n) or NULL at the first lead time
+ *   out        (members,m,n) precip dtype;  disp_out (members,2,m,n)
+ *   n_nonfinite (device, members doubles, may be NULL): non-finite elements of each perturbed field
+ * Each member's results are those of b200_bps_perturb_velocity + b200_sl_extrapolate with
+ * T = 1, n_iter = 1, bit for bit. */
+int b200_sl_step_batched(const void *velocity, int velocity_dtype, int m, int n, int members,
+                         const double *pert_coefs, double vsf, const void *precip, int precip_dtype,
+                         const double *disp_prev, double tdiff, double vel_timestep, double outval,
+                         int mode, void *out, double *disp_out, double *n_nonfinite, void *stream);
+
 /* Same operation on HOST buffers: allocates device scratch from the stream
  * ordered pool, copies in, runs, copies out and synchronises.  This is the
  * call a non-Python binding (cgo / JNI / plain C) would make. */

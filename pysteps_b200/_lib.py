@@ -67,6 +67,9 @@ _SIGNATURES = {
     "b200_lk_pyramid_layout": (c_int, [c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_int),
                                        ctypes.POINTER(c_i64), ctypes.POINTER(c_int),
                                        ctypes.POINTER(c_int), ctypes.POINTER(c_i64)]),
+    "b200_sl_step_batched": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_double, c_void_p, c_int,
+                                     c_void_p, c_double, c_double, c_double, c_int, c_void_p, c_void_p, c_void_p,
+                                     c_void_p]),
     "b200_lk_frontend": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200_lk_build_pyramid": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,

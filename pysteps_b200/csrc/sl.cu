@@ -34,6 +34,8 @@ struct SLParams {
     void *out;              // (T,m,n) planes of this chunk
     int m, n, T, n_iter, ti_offset, init_mode, mode, has_prev, vel_f32;
     int row0, rows;         // output band [row0, row0 + rows): band-shaped out / disp arrays
+    // batched members (blockIdx.z): element strides between consecutive members, 0 when unused
+    size_t zs_vi, zs_precip, zs_disp, zs_out;
     double vts, td0, cval;
     double scale[SL_MAX_T];  // td / vel_timestep per leadtime
 };
@@ -200,7 +202,7 @@ template <> __device__ __forceinline__ double from_double<double>(double v) { re
 // the inner loop / division branches.
 // VF32: the velocity was float32 at the API (a compile-time fact of the launch: the rounding of
 // the sampled increments costs conversion-pipe slots even when predicated off).
-template <typename F, bool NITER1, int BY, bool VF32>
+template <typename F, bool NITER1, int BY, bool VF32, bool BATCH = false>
 __global__ void __launch_bounds__(SL_BX *BY)
 sl_multistep_kernel(const __grid_constant__ SLParams p) {
     const int x = blockIdx.x * SL_BX + threadIdx.x;
@@ -213,9 +215,12 @@ sl_multistep_kernel(const __grid_constant__ SLParams p) {
     const size_t NF = (size_t)m * n;       // plane stride of the full-frame arrays
     const int idx = yl * n + x;            // pixel index inside the band
     const int gidx = y * n + x;            // pixel index inside the full frame
-    const double2 *__restrict__ Vi = (const double2 *)p.Vi;
-    const double *__restrict__ P = (const double *)p.precip;
-    F *__restrict__ out = (F *)p.out + idx;
+    const size_t z = BATCH ? blockIdx.z : 0;  // member of a batched launch
+    const double2 *__restrict__ Vi = (const double2 *)p.Vi + (BATCH ? z * p.zs_vi : 0);
+    const double *__restrict__ P = (const double *)p.precip + (BATCH ? z * p.zs_precip : 0);
+    F *__restrict__ out = (F *)p.out + (BATCH ? z * p.zs_out : 0) + idx;
+    const double *__restrict__ disp_in = p.disp_in + (BATCH ? z * p.zs_disp : 0);
+    double *__restrict__ disp_out = p.disp_out ? p.disp_out + (BATCH ? z * p.zs_disp : 0) : nullptr;
     const int n_iter = NITER1 ? 1 : p.n_iter;
     const int mode = p.mode;
     const double cval = p.cval;
@@ -239,11 +244,11 @@ sl_multistep_kernel(const __grid_constant__ SLParams p) {
         uy = __ddiv_rn(__dmul_rn(v.y, p.td0), p.vts);
     } else if (p.init_mode == SL_INIT_PREV) {
         // :205-207
-        dx = p.disp_in[idx]; dy = p.disp_in[N + idx];
+        dx = disp_in[idx]; dy = disp_in[N + idx];
         sample_velocity<VF32>(Vi, m, n, ymax, xmax, __dadd_rn(gy, dy), __dadd_rn(gx, dx), p.scale[0],
                         n_iter, ux, uy);
     } else {
-        dx = p.disp_in[idx]; dy = p.disp_in[N + idx];
+        dx = disp_in[idx]; dy = disp_in[N + idx];
         ux = p.vinc_in[idx]; uy = p.vinc_in[N + idx];
     }
 
@@ -288,9 +293,9 @@ sl_multistep_kernel(const __grid_constant__ SLParams p) {
             out[(size_t)ti * N] = from_double<F>(v);
         }
     }
-    if (p.disp_out) {
-        p.disp_out[idx] = dx;
-        p.disp_out[N + idx] = dy;
+    if (disp_out) {
+        disp_out[idx] = dx;
+        disp_out[N + idx] = dy;
     }
     if (p.vinc_out) {
         p.vinc_out[idx] = ux;
@@ -665,6 +670,126 @@ static int bps_launch(const void *velocity, size_t N, double a, double b, double
     }
     B200_LAUNCH_CHECK();
     return 0;
+}
+
+// ---- all members of a GPU in one launch per lead time ---------------------------------------
+// nowcasts/utils.py:440-458 advances every ensemble member by one single-step extrapolator call
+// per lead time: its own perturbed motion field, its own precipitation field, its own carried
+// displacement.  The per-member calls cost ~80 us of host time each on top of ~170 us of kernels;
+// here the members of a rank go through ONE perturbation launch and ONE trajectory launch
+// (grid.y / grid.z = member), SL_BATCH members at a time (that bounds the scratch for the
+// perturbed fields to SL_BATCH x 64 MB at 2048^2).
+constexpr int SL_BATCH = 8;
+struct BpsBatch { double a[SL_BATCH], b[SL_BATCH]; };
+
+template <typename F>
+__global__ void __launch_bounds__(256)
+bps_perturb_batched_kernel(const F *__restrict__ V, double2 *__restrict__ out, size_t N, const BpsBatch ab,
+                           double vsf, double *__restrict__ n_nonfinite) {
+    const int mem = blockIdx.y;
+    const double a = ab.a[mem], b = ab.b[mem];
+    double2 *__restrict__ o = out + (size_t)mem * N;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    int bad = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+        const F vx = __ldg(V + i), vy = __ldg(V + N + i);
+        double nx, ny;  // unit vector in the field's own dtype (bps_perturb_kernel)
+        if (sizeof(F) == 4) {
+            const float nrm = __fsqrt_rn(__fadd_rn(__fmul_rn((float)vx, (float)vx), __fmul_rn((float)vy, (float)vy)));
+            const bool ok = nrm > (float)1e-12;
+            nx = ok ? (double)__fdiv_rn((float)vx, nrm) : 0.0;
+            ny = ok ? (double)__fdiv_rn((float)vy, nrm) : 0.0;
+        } else {
+            const double nrm = __dsqrt_rn(__dadd_rn(__dmul_rn((double)vx, (double)vx), __dmul_rn((double)vy, (double)vy)));
+            const bool ok = nrm > 1e-12;
+            nx = ok ? __ddiv_rn((double)vx, nrm) : 0.0;
+            ny = ok ? __ddiv_rn((double)vy, nrm) : 0.0;
+        }
+        const double ox = __dadd_rn((double)vx, __ddiv_rn(__dadd_rn(__dmul_rn(a, nx), __dmul_rn(b, -ny)), vsf));
+        const double oy = __dadd_rn((double)vy, __ddiv_rn(__dadd_rn(__dmul_rn(a, ny), __dmul_rn(b, nx)), vsf));
+        bad += !isfinite(ox);
+        bad += !isfinite(oy);
+        o[i] = make_double2(ox, oy);
+    }
+    if (n_nonfinite != nullptr && __any_sync(0xffffffffu, bad != 0)) {
+        if (bad) atomicAdd(n_nonfinite + mem, (double)bad);
+    }
+}
+
+template <typename FV, typename F>
+static int sl_step_batched(const void *velocity, int m, int n, int members, const double *coefs, double vsf,
+                           const void *precip, const double *disp_prev, double tdiff, double vts, double outval,
+                           int mode, void *out, double *disp_out, double *n_nonfinite, cudaStream_t stream) {
+    const size_t N = (size_t)m * n;
+    const int ch_max = std::min(members, SL_BATCH);
+    b200::Scratch vp, pw;
+    B200_CUDA(vp.alloc((size_t)ch_max * N * sizeof(double2), stream));
+    if (sizeof(F) == 4) B200_CUDA(pw.alloc((size_t)ch_max * N * sizeof(double), stream));
+    if (n_nonfinite) B200_CUDA(cudaMemsetAsync(n_nonfinite, 0, sizeof(double) * members, stream));
+    const int sblocks = (int)std::min<size_t>((N + 255) / 256, (size_t)b200::num_sms() * 8);
+    for (int m0 = 0; m0 < members; m0 += SL_BATCH) {
+        const int ch = std::min(SL_BATCH, members - m0);
+        BpsBatch ab;
+        for (int j = 0; j < SL_BATCH; j++) {
+            ab.a[j] = j < ch ? coefs[2 * (m0 + j)] : 0.0;
+            ab.b[j] = j < ch ? coefs[2 * (m0 + j) + 1] : 0.0;
+        }
+        bps_perturb_batched_kernel<FV><<<dim3(sblocks, ch), 256, 0, stream>>>(
+            (const FV *)velocity, (double2 *)vp.p, N, ab, vsf, n_nonfinite ? n_nonfinite + m0 : nullptr);
+        B200_LAUNCH_CHECK();
+        const void *p_ptr = (const F *)precip + (size_t)m0 * N;
+        if (sizeof(F) == 4) {
+            const int wblocks = (int)std::min<size_t>(((size_t)ch * N + 255) / 256, (size_t)b200::num_sms() * 16);
+            widen_field_kernel<<<wblocks, 256, 0, stream>>>((const float *)p_ptr, (double *)pw.p, (size_t)ch * N);
+            B200_LAUNCH_CHECK();
+            p_ptr = pw.p;
+        }
+        SLParams p;
+        memset(&p, 0, sizeof(p));
+        p.Vi = vp.p;
+        p.precip = p_ptr;
+        p.m = m; p.n = n;
+        p.row0 = 0; p.rows = m;
+        p.n_iter = 1;
+        p.mode = mode;
+        p.vts = vts;
+        p.td0 = tdiff;
+        p.cval = outval;
+        p.has_prev = disp_prev != nullptr;
+        p.vel_f32 = 0;  // the perturbed field is float64 (noise/motion.py:138-139)
+        p.T = 1;
+        p.scale[0] = tdiff / vts;
+        p.init_mode = disp_prev ? SL_INIT_PREV : SL_INIT_FRESH;
+        p.disp_in = disp_prev ? disp_prev + (size_t)m0 * 2 * N : nullptr;
+        p.disp_out = disp_out + (size_t)m0 * 2 * N;
+        p.out = (F *)out + (size_t)m0 * N;
+        p.zs_vi = N; p.zs_precip = N; p.zs_disp = 2 * N; p.zs_out = N;
+        dim3 block(SL_BX, SL_BY);
+        dim3 grid(b200::ceil_div(n, SL_BX), b200::ceil_div(m, SL_BY), ch);
+        sl_multistep_kernel<F, true, SL_BY, false, true><<<grid, block, 0, stream>>>(p);
+        B200_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+extern "C" int b200_sl_step_batched(const void *velocity, int velocity_dtype, int m, int n, int members,
+                                    const double *pert_coefs, double vsf, const void *precip, int precip_dtype,
+                                    const double *disp_prev, double tdiff, double vel_timestep, double outval,
+                                    int mode, void *out, double *disp_out, double *n_nonfinite, void *stream) {
+    B200_REQUIRE(velocity && pert_coefs && precip && out && disp_out, "bad arguments");
+    B200_REQUIRE(m >= 1 && n >= 1 && (int64_t)m * n < ((int64_t)1 << 30) && members >= 1, "bad sizes");
+    B200_REQUIRE(mode == B200_MODE_CONSTANT || mode == B200_MODE_NEAREST, "unsupported mode");
+    cudaStream_t s = (cudaStream_t)stream;
+#define SLB(FV, FP)                                                                                         \
+    return sl_step_batched<FV, FP>(velocity, m, n, members, pert_coefs, vsf, precip, disp_prev, tdiff,      \
+                                   vel_timestep, outval, mode, out, disp_out, n_nonfinite, s)
+    if (velocity_dtype == B200_F32 && precip_dtype == B200_F32) SLB(float, float);
+    if (velocity_dtype == B200_F32 && precip_dtype == B200_F64) SLB(float, double);
+    if (velocity_dtype == B200_F64 && precip_dtype == B200_F32) SLB(double, float);
+    if (velocity_dtype == B200_F64 && precip_dtype == B200_F64) SLB(double, double);
+#undef SLB
+    b200::set_error("unknown field dtypes %d / %d", velocity_dtype, precip_dtype);
+    return B200_EINVAL;
 }
 
 extern "C" int b200_bps_perturb_velocity(const void *velocity, int velocity_dtype, int m, int n,

@@ -332,3 +332,66 @@ def _extrapolate_checked(precip, velocity, d_precip, d_vel, stats, on_device, ti
             return out
         return out, disp
     return None, disp
+
+
+def extrapolate_members(precip, perturbed_velocities, displacement_prev=None, timestep=1.0, vel_timestep=1.0,
+                        outval=np.nan, allow_nonfinite_values=False, map_coordinates_mode="constant"):
+    """One lead time for ALL ensemble members of this GPU in two launches (extension; the loop body
+    of nowcasts/utils.py:440-458 for every member at once).
+
+    Equivalent, member by member and bit for bit, to
+        extrapolate(precip[j], perturbed_velocities[j], [timestep], displacement_prev=displacement_prev[j],
+                    return_displacement=True, vel_timestep=vel_timestep, ...)
+    precip: (M, m, n) stack, NumPy or CUDA tensor (float32 / float64);
+    perturbed_velocities: M values of ``velocity + generate_bps(perturbator_j, t)`` from
+        ``pysteps_b200.noise`` for perturbators initialised with the SAME velocity array;
+    displacement_prev: (M, 2, m, n) from the previous lead time (NumPy, CUDA tensor or the
+        DeviceField this function returned) or None at the first.
+    Returns (fields (M, m, n), displacement (M, 2, m, n)); CUDA tensors when precip is one.
+    """
+    _device.require_cuda()
+    M = len(perturbed_velocities)
+    if M < 1 or not all(isinstance(v, _bps.PerturbedVelocity) for v in perturbed_velocities):
+        raise TypeError("perturbed_velocities must be `velocity + generate_bps(...)` handles of pysteps_b200.noise")
+    field = perturbed_velocities[0].pert.field
+    vsf = perturbed_velocities[0].pert.vsf
+    if any(v.pert.field is not field or v.pert.vsf != vsf for v in perturbed_velocities):
+        raise ValueError("all members must perturb the same velocity field")
+    if map_coordinates_mode not in _MODES:
+        raise NotImplementedError("map_coordinates_mode must be 'constant' or 'nearest'")
+    if precip.ndim != 3 or precip.shape[0] != M:
+        raise ValueError("precip must be an (M, m, n) stack with one field per member")
+    _, m, n = (int(v) for v in field.shape)
+    if tuple(int(v) for v in precip.shape[1:]) != (m, n):
+        raise ValueError("precip and velocity have incompatible shapes")
+    on_device = _device.is_device_tensor(precip)
+    d_precip = _field_tensor(precip)
+    stats = _Stats(d_precip)
+    coefs = np.ascontiguousarray([[v.pert.a, v.pert.b] for v in perturbed_velocities], dtype=np.float64)
+    d_prev = None
+    if displacement_prev is not None:
+        d_prev = _device.to_device(displacement_prev, torch.float64)
+        if tuple(d_prev.shape) != (M, 2, m, n):
+            raise ValueError("displacement_prev must have shape (M, 2, m, n)")
+    d_out = torch.empty((M, m, n), dtype=d_precip.dtype, device="cuda")
+    d_disp = torch.empty((M, 2, m, n), dtype=torch.float64, device="cuda")
+    d_bad = torch.empty(M, dtype=torch.float64, device="cuda")
+    if isinstance(outval, str) and outval == "min":
+        outval = stats.get()[0][1]
+    _lib.call("b200_sl_step_batched", field.tensor.data_ptr(), _device.dtype_code(field.tensor.dtype), m, n, M,
+              coefs.ctypes.data_as(_lib.c_dp), float(vsf), d_precip.data_ptr(), _device.dtype_code(d_precip.dtype),
+              _device.ptr(d_prev), float(timestep), float(vel_timestep), float(outval),
+              _MODES[map_coordinates_mode], d_out.data_ptr(), d_disp.data_ptr(), d_bad.data_ptr(),
+              _device.stream_ptr())
+    st_p = stats.get()[0]
+    bad_v = d_bad.cpu().numpy()
+    if not allow_nonfinite_values:
+        if st_p[0] > 0:
+            raise ValueError("precip contains non-finite values")
+        if bad_v.any():
+            raise ValueError("velocity contains non-finite values")
+    if st_p[0] == d_precip.numel():
+        raise ValueError("precip contains only non-finite values")
+    if on_device:
+        return d_out, d_disp
+    return _device.to_host(d_out), _device.DeviceField(d_disp)

@@ -167,6 +167,25 @@ def _bps(velocity, code, m, n, a, b, vsf, what, out, nnf, stream):
         _view(nnf, (1,))[0] = float(np.count_nonzero(~np.isfinite(res)))
 
 
+def _sl_step_batched(velocity, vdt, m, n, members, coefs, vsf, precip, pdt, disp_prev, tdiff, vts, outval, mode,
+                     out, disp_out, nnf, stream):
+    """member by member: the emulated perturbation entry point, then the emulated single-step call"""
+    vt, pt = _NP[vdt], _NP[pdt]
+    ab = _view(coefs, (members, 2))
+    tmp = np.empty((m, n, 2))
+    bad = np.zeros(1)
+    td = np.array([tdiff])
+    N = m * n
+    for j in range(members):
+        _bps(velocity, vdt, m, n, float(ab[j, 0]), float(ab[j, 1]), vsf, 0, tmp.ctypes.data, bad.ctypes.data, stream)
+        if _addr(nnf) is not None:
+            _view(nnf, (members,))[j] = bad[0]
+        dp = None if _addr(disp_prev) is None else _addr(disp_prev) + j * 2 * N * 8
+        _sl_rows(_addr(precip) + j * N * np.dtype(pt).itemsize, tmp.ctypes.data, None, dp, td.ctypes.data, 1, vts, 1,
+                 outval, mode, _lib.F64, _lib.LAYOUT_INTERLEAVED, pdt, m, n, 0, m,
+                 _addr(out) + j * N * np.dtype(pt).itemsize, _addr(disp_out) + j * 2 * N * 8, stream)
+
+
 def _vet_cost(sd, templ, inp, mask, xs, ys, nx, ny, smooth_gain, gradient, out, stream):
     from oracle import vet as ora_vet
     r = ora_vet.cost_function(_view(sd, (2, xs, ys)).copy(), _view(templ, (nx, ny)).copy(),
@@ -423,7 +442,7 @@ _TABLE = {"b200_vet_cost": _vet_cost, "b200_vet_value_and_gradient": _vet_value_
           "b200_gaussian_filter": _gaussian_filter, "b200_proesmans_scale": _proesmans_scale, "b200_proesmans_field": _proesmans_field,
           "b200_sl_trajectories": _sl_trajectories, "b200_spline_prepare": _spline_prepare,
           "b200_spline_sample": _spline_sample, "b200_field_stats": _field_stats, "b200_sl_extrapolate_rows": _sl_rows,
-          "b200_bps_perturb_velocity": _bps}
+          "b200_bps_perturb_velocity": _bps, "b200_sl_step_batched": _sl_step_batched}
 
 
 def _call(name, *args):

@@ -164,3 +164,33 @@ def test_full_size_properties(b200):
     mat = extrap(P, np.asarray(V + gen(pert, 30.0)), [1.0])
     assert_bits_equal(fused, mat, "fused vs materialised")
     assert not np.array_equal(fused, base, equal_nan=True)
+
+
+def test_batched_member_step_equals_member_by_member_calls(env_bps=None):
+    """b200_sl_step_batched through extrapolate_members: every member's field and displacement
+    bit-identical to its own single-step extrapolate call (float32 / float64 fields, 11 members =
+    two batches of the kernel, three lead times with carried displacements, NaN inflow)."""
+    import torch
+    assert torch.cuda.is_available(), "gpu-marked test needs a GPU"
+    import pysteps_b200
+    from pysteps_b200 import _synthetic as syn
+    from pysteps_b200.extrapolation.semilagrangian import extrapolate, extrapolate_members
+    init, gen = pysteps_b200.noise.get_method("bps")
+    for dtype, vkind in ((np.float32, "smooth"), (np.float64, "rotation")):
+        m, n, M = 200, 264, 11
+        V = syn.velocity_field(m, n, 3, vkind) * (4.0 if vkind == "rotation" else 1.0)
+        P = np.stack([syn.rain_field(m, n, 3 + j) for j in range(M)]).astype(dtype)
+        perts = [init(V, 1.0, 5.0, randstate=np.random.RandomState(50 + j)) for j in range(M)]
+        disp_b, disp_s = None, [None] * M
+        for t in range(3):
+            Vm = [V + gen(perts[j], (t + 1) * 5.0) for j in range(M)]
+            out_b, disp_b = extrapolate_members(P, Vm, displacement_prev=disp_b)
+            for j in range(M):
+                o, disp_s[j] = extrapolate(P[j], Vm[j], [1.0], displacement_prev=disp_s[j], return_displacement=True)
+                assert out_b.dtype == o.dtype
+                assert_bits_equal(out_b[j], o[0], f"{dtype.__name__} t={t} member {j}")
+                assert np.array_equal(np.asarray(disp_b)[j], np.asarray(disp_s[j])), (t, j)
+        # device tensors in -> device tensors out
+        dP = torch.from_numpy(P).cuda()
+        o_d, d_d = extrapolate_members(dP, Vm, displacement_prev=None)
+        assert o_d.is_cuda and d_d.is_cuda and tuple(d_d.shape) == (M, 2, m, n)

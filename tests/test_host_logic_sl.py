@@ -11,6 +11,7 @@ import pytest
 import cpu_abi
 from oracle import noise_motion as ora_bps
 from oracle import semilagrangian as ora
+from pysteps_b200 import _synthetic as syn
 
 
 def _reference():
@@ -208,3 +209,35 @@ def test_spline_orders_host_logic_and_kernel_bodies(seed, monkeypatch):
         full = extrap(P, V, 3, interp_order=3, map_coordinates_mode="nearest")
         band = extrap(P, V, 3, interp_order=3, map_coordinates_mode="nearest", b200_rows=(5, 11))
         assert _bits_equal(band, full[:, 5:11])
+
+
+def test_extrapolate_members_equals_member_by_member_calls():
+    """extrapolate_members (one batched launch per lead time) against the loop body of
+    nowcasts/utils.py:440-458 spelled with single-member calls: same bits, float32 and float64
+    precipitation, first lead time and carried displacements."""
+    import pysteps_b200
+    from pysteps_b200.extrapolation.semilagrangian import extrapolate, extrapolate_members
+    init, gen = pysteps_b200.noise.get_method("bps")
+    rng = np.random.default_rng(11)
+    with cpu_abi.emulated():
+        for dtype in (np.float64, np.float32):
+            m, n, M = 40, 52, 3
+            V = 2.0 * syn.velocity_field(m, n, 3)
+            P = np.stack([syn.rain_field(m, n, 3 + j) for j in range(M)]).astype(dtype)
+            perts = [init(V, 1.0, 5.0, randstate=np.random.RandomState(50 + j)) for j in range(M)]
+            disp_b = None
+            disp_s = [None] * M
+            for t in range(3):
+                Vm = [V + gen(perts[j], (t + 1) * 5.0) for j in range(M)]
+                out_b, disp_b = extrapolate_members(P, Vm, displacement_prev=disp_b)
+                for j in range(M):
+                    o, disp_s[j] = extrapolate(P[j], Vm[j], [1.0], displacement_prev=disp_s[j], return_displacement=True)
+                    assert out_b.dtype == o.dtype and np.array_equal(out_b[j], o[0], equal_nan=True), (dtype, t, j)
+                    assert np.array_equal(np.asarray(disp_b)[j], np.asarray(disp_s[j])), (dtype, t, j)
+            with pytest.raises(ValueError, match="same velocity"):
+                V2 = V.copy()
+                other = init(V2, 1.0, 5.0, randstate=np.random.RandomState(1))
+                extrapolate_members(P[:2], [Vm[0], V2 + gen(other, 5.0)])
+            with pytest.raises(TypeError):
+                extrapolate_members(P[:1], [V])
+        _ = rng
