@@ -283,6 +283,10 @@ int b200_detect_outliers(const double *uv, const double *xy, const int *n_dev, i
  * nodes; both device pointers.  Stage entry used by the parity tests of the build. */
 int b200_kdtree_build(const double *xy, const int *n_dev, int n_cap, int *tree_indices,
                       int *node_count, void *stream);
+/* cleansing.py:201-214, the global branch (k is None): Mahalanobis distance of every vector to the
+ * mean of ALL vectors under their sample covariance; out[i] = MD > thr. */
+int b200_detect_outliers_global(const double *uv, const int *n_dev, int n_cap, double thr,
+                                uint8_t *out, void *stream);
 /* rows with drop == 0, order preserved */
 int b200_compact_rows(const double *xy, const double *uv, const uint8_t *drop, const int *n_dev,
                       int n_cap, double *out_xy, double *out_uv, int *out_count, void *stream);
@@ -315,6 +319,11 @@ int b200_idw_fill_ckdtree(const double *xy, const double *vals, const int *npts_
                           int nvar, int k, double power, double dist_offset, double mean_res,
                           const double *xgrid, int nx, const double *ygrid, int ny, double *out,
                           void *stream);
+/* idwinterp2d with k = None (interpolate.py:82-88): every vector contributes to every grid point.
+ * nvar <= 8. */
+int b200_idw_fill_all(const double *xy, const double *vals, const int *npts_dev, int npts_cap, int nvar,
+                      double power, double dist_offset, double mean_res, const double *xgrid, int nx,
+                      const double *ygrid, int ny, double *out, void *stream);
 
 /* ------------------------------------------------------------------------
  * Variational Echo Tracking -- replaces the native extension of the reference,

@@ -81,6 +81,9 @@ _SIGNATURES = {
                                        c_void_p, c_int, c_void_p]),
     "b200_detect_outliers": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_double, c_int, c_void_p,
                                      c_void_p]),
+    "b200_detect_outliers_global": (c_int, [c_void_p, c_void_p, c_int, c_double, c_void_p, c_void_p]),
+    "b200_idw_fill_all": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_double, c_double,
+                                  c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "b200_kdtree_build": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "b200_compact_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                   c_void_p, c_void_p]),

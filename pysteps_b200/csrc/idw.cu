@@ -489,6 +489,42 @@ __global__ void __launch_bounds__(IDW_THREADS, 4) idw32_kernel(const IDWParams p
     p.out[((size_t)1 * p.ny + i) * p.nx + j] = ay * inv;
 }
 
+// ---- k = None: every vector weighs in (interpolate.py:82-88, scipy cdist) ------------------------
+// One thread per grid point, the vectors staged through shared memory in chunks; weights and sums in
+// float64 in index order (NumPy sums the same terms pairwise: relative differences ~1e-14).
+constexpr int IDW_ALL_MAXVAR = 8;
+
+__global__ void __launch_bounds__(256)
+idw_all_kernel(const IDWParams p) {
+    __shared__ double2 spt[1024];
+    const int npts = p.npts_dev ? min(*p.npts_dev, p.npts_cap) : p.npts_cap;
+    const int j = blockIdx.x * 32 + (threadIdx.x & 31), i = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const bool active = j < p.nx && i < p.ny;
+    const double qx = p.gx[min(j, p.nx - 1)], qy = p.gy[min(i, p.ny - 1)];
+    const double2 *__restrict__ pts = reinterpret_cast<const double2 *>(p.xy);
+    double ws = 0.0, acc[IDW_ALL_MAXVAR];
+#pragma unroll
+    for (int v = 0; v < IDW_ALL_MAXVAR; v++) acc[v] = 0.0;
+    for (int base = 0; base < npts; base += 1024) {
+        const int cnt = min(1024, npts - base);
+        __syncthreads();
+        for (int t = threadIdx.x; t < cnt; t += 256) spt[t] = pts[base + t];
+        __syncthreads();
+        if (!active) continue;
+        for (int t = 0; t < cnt; t++) {
+            const double dx = __dsub_rn(spt[t].x, qx), dy = __dsub_rn(spt[t].y, qy);
+            double d = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+            if (p.mean_res != 1.0) d = __ddiv_rn(d, p.mean_res);
+            d = __dadd_rn(d, p.offset);
+            const double w = __ddiv_rn(1.0, (p.power == 0.5) ? sqrt(d) : pow(d, p.power));
+            ws += w;
+            for (int v = 0; v < p.nvar; v++) acc[v] += p.vals[(size_t)(base + t) * p.nvar + v] * w;
+        }
+    }
+    if (!active) return;
+    for (int v = 0; v < p.nvar; v++) p.out[((size_t)v * p.ny + i) * p.nx + j] = acc[v] / ws;
+}
+
 // library-internal side stream of the calling thread's device + fork/join events: the tree build
 // (one CTA, latency bound) overlaps the exhaustive fill, the recomputation of the listed grid
 // points waits for both
@@ -578,4 +614,19 @@ extern "C" int b200_idw_fill(const double *xy, const double *vals, const int *np
     B200_CUDA(cudaStreamWaitEvent(s, ss->join, 0));
     return kdp::idw_fix(xy, vals, nvar, k, power, dist_offset, mean_res, xgrid, nx, ygrid, ny, ts.tb, tie_list,
                         tie_count, out, s);
+}
+
+extern "C" int b200_idw_fill_all(const double *xy, const double *vals, const int *npts_dev, int npts_cap, int nvar,
+                                 double power, double dist_offset, double mean_res, const double *xgrid, int nx,
+                                 const double *ygrid, int ny, double *out, void *stream) {
+    B200_REQUIRE(xy && vals && xgrid && ygrid && out && npts_cap >= 1 && nx >= 1 && ny >= 1, "bad arguments");
+    B200_REQUIRE(nvar >= 1 && nvar <= IDW_ALL_MAXVAR, "at most 8 variables");
+    IDWParams p;
+    memset(&p, 0, sizeof(p));
+    p.xy = xy; p.vals = vals; p.npts_dev = npts_dev; p.npts_cap = npts_cap; p.nvar = nvar; p.k = npts_cap;
+    p.gx = xgrid; p.gy = ygrid; p.nx = nx; p.ny = ny;
+    p.power = power; p.offset = dist_offset; p.mean_res = mean_res; p.out = out;
+    idw_all_kernel<<<dim3(b200::ceil_div(nx, 32), b200::ceil_div(ny, 8)), 256, 0, (cudaStream_t)stream>>>(p);
+    B200_LAUNCH_CHECK();
+    return 0;
 }

@@ -157,7 +157,91 @@ decluster_kernel(const double *__restrict__ xy, const double *__restrict__ uv, c
     }
 }
 
+// ---- global Mahalanobis outlier test (cleansing.py:201-214, k is None) --------------------------
+// MD_i = sqrt(z_i VI z_i^T) with z = uv - mean(uv), V = np.cov(z.T), VI = inv(V); out = MD > thr.
+// One CTA; float64 sums by a fixed tree (NumPy reduces through BLAS here, so the last bits of V are
+// not defined by the reference either: decisions agree unless MD is within ~1e-13 of thr).
+__global__ void __launch_bounds__(256)
+outliers_global_kernel(const double *__restrict__ uv, const int *__restrict__ n_dev, int n_cap, double thr,
+                       uint8_t *__restrict__ out) {
+    __shared__ double red[5][256];
+    __shared__ double s_mu, s_mv, s_vi[4];
+    __shared__ int s_ok;
+    const int n = n_dev ? min(*n_dev, n_cap) : n_cap;
+    const int tid = threadIdx.x;
+    if (n < 2) {  // :177-178
+        for (int i = tid; i < n; i += 256) out[i] = 0;
+        return;
+    }
+    auto reduce = [&](int nv) {
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (tid < o)
+                for (int v = 0; v < nv; v++) red[v][tid] += red[v][tid + o];
+            __syncthreads();
+        }
+    };
+    double a = 0.0, b = 0.0;
+    for (int i = tid; i < n; i += 256) { a += uv[2 * i]; b += uv[2 * i + 1]; }
+    red[0][tid] = a; red[1][tid] = b;
+    reduce(2);
+    if (tid == 0) { s_mu = red[0][0] / (double)n; s_mv = red[1][0] / (double)n; }
+    __syncthreads();
+    const double mu = s_mu, mv = s_mv;
+    // np.cov subtracts the (tiny) mean of the centred data again
+    a = b = 0.0;
+    for (int i = tid; i < n; i += 256) { a += uv[2 * i] - mu; b += uv[2 * i + 1] - mv; }
+    red[0][tid] = a; red[1][tid] = b;
+    reduce(2);
+    const double au = red[0][0] / (double)n, av = red[1][0] / (double)n;
+    __syncthreads();
+    double suu = 0.0, suv = 0.0, svv = 0.0;
+    for (int i = tid; i < n; i += 256) {
+        const double x = (uv[2 * i] - mu) - au, y = (uv[2 * i + 1] - mv) - av;
+        suu += x * x; suv += x * y; svv += y * y;
+    }
+    red[0][tid] = suu; red[1][tid] = suv; red[2][tid] = svv;
+    reduce(3);
+    if (tid == 0) {
+        const double fact = 1.0 / (double)(n - 1);
+        const double va = red[0][0] * fact, vb = red[1][0] * fact, vd = red[2][0] * fact;
+        // np.linalg.inv: LU with partial pivoting; exactly singular -> LinAlgError -> MD = 0
+        const bool swap = fabs(vb) > fabs(va);
+        const double p0 = swap ? vb : va, p1 = swap ? vd : vb, q0 = swap ? va : vb, q1 = swap ? vb : vd;
+        int ok = 0;
+        if (p0 != 0.0 && !isnan(p0)) {
+            const double l = q0 * (1.0 / p0), u22 = q1 - l * p1;
+            if (u22 != 0.0) {
+                const double r00 = swap ? 0.0 : 1.0, r10 = swap ? 1.0 : 0.0, r01 = swap ? 1.0 : 0.0, r11 = swap ? 0.0 : 1.0;
+                const double x10 = (r10 - l * r00) / u22, x11 = (r11 - l * r01) / u22;
+                s_vi[0] = (r00 - p1 * x10) / p0; s_vi[1] = (r01 - p1 * x11) / p0; s_vi[2] = x10; s_vi[3] = x11;
+                ok = 1;
+            }
+        }
+        s_ok = ok;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) {
+        double MD = 0.0;
+        if (s_ok) {
+            const double zu = uv[2 * i] - mu, zv = uv[2 * i + 1] - mv;
+            const double t0 = zu * s_vi[0] + zv * s_vi[2], t1 = zu * s_vi[1] + zv * s_vi[3];
+            MD = sqrt(t0 * zu + t1 * zv);
+        }
+        out[i] = (MD > thr) ? 1 : 0;
+    }
+}
+
 }  // namespace
+
+extern "C" int b200_detect_outliers_global(const double *uv, const int *n_dev, int n_cap, double thr,
+                                           uint8_t *out, void *stream) {
+    B200_REQUIRE(uv && out && n_cap >= 0, "bad arguments");
+    if (n_cap == 0) return 0;
+    outliers_global_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(uv, n_dev, n_cap, thr, out);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int b200_compact_rows(const double *xy, const double *uv, const uint8_t *drop, const int *n_dev,
                                  int n_cap, double *out_xy, double *out_uv, int *out_count, void *stream) {

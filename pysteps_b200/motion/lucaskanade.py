@@ -328,12 +328,15 @@ def dense_lucaskanade(input_images, lk_kwargs=None, fd_method="shitomasi", fd_kw
     kept_xy = torch.empty((pool_cap, 2), dtype=torch.float64, device="cuda")
     kept_uv = torch.empty((pool_cap, 2), dtype=torch.float64, device="cuda")
     if k_outlier is None:
-        raise NotImplementedError("pysteps_b200 LK: k_outlier=None (global outlier test) is not implemented")
-    # equidistant / coincident neighbours in scipy.spatial.cKDTree's own order (csrc/knn.cu): with
-    # integer corner coordinates that order decides outlier tests
-    _call("b200_detect_outliers",
-          pool_uv.data_ptr(), pool_xy.data_ptr(), counts[0:1].data_ptr(),
-          pool_cap, float(nr_std_outlier), int(k_outlier), flags.data_ptr(), _s())
+        # the global test (cleansing.py:201-214): every vector against the mean / covariance of all
+        _call("b200_detect_outliers_global", pool_uv.data_ptr(), counts[0:1].data_ptr(), pool_cap,
+              float(nr_std_outlier), flags.data_ptr(), _s())
+    else:
+        # equidistant / coincident neighbours in scipy.spatial.cKDTree's own order (csrc/knn.cu): with
+        # integer corner coordinates that order decides outlier tests
+        _call("b200_detect_outliers",
+              pool_uv.data_ptr(), pool_xy.data_ptr(), counts[0:1].data_ptr(),
+              pool_cap, float(nr_std_outlier), int(k_outlier), flags.data_ptr(), _s())
     _call("b200_compact_rows", pool_xy.data_ptr(), pool_uv.data_ptr(), flags.data_ptr(),
           counts[0:1].data_ptr(), pool_cap, kept_xy.data_ptr(), kept_uv.data_ptr(),
           counts[1:2].data_ptr(), _s())
@@ -361,8 +364,6 @@ def dense_lucaskanade(input_images, lk_kwargs=None, fd_method="shitomasi", fd_kw
     power = float(interp_kwargs.get("power", 0.5))
     k = interp_kwargs.get("k", 20)
     dist_offset = float(interp_kwargs.get("dist_offset", 0.5))
-    if k is None:
-        raise NotImplementedError("pysteps_b200 LK: idwinterp2d with k=None is not implemented")
     # extension (an unknown interpolator kwarg is ignored by the reference): fill only the grid
     # rows [r0, r1) -- the result is then band shaped (2, r1-r0, n).  The sparse stages are
     # deterministic, so ranks that each fill one band of the same frames agree bit for bit with
@@ -392,9 +393,13 @@ def dense_lucaskanade(input_images, lk_kwargs=None, fd_method="shitomasi", fd_kw
             on_grid = 2  # half-pixel grid (the usual case: medians of integers): 32-bit integer keys
         # exhaustive tile search; grid points whose neighbour set depends on cKDTree's tie order are
         # recomputed from its query (csrc/idw.cu, knn.cu)
-        _call("b200_idw_fill", dec_xy.data_ptr(), dec_uv.data_ptr(), None, n_dec, 2, int(min(int(k), n_dec)),
-              power, dist_offset, 1.0, xgrid.data_ptr(), n, ygrid.data_ptr(), mb, on_grid,
-              out.data_ptr(), _s())
+        if k is None:  # every vector weighs in at every grid point (interpolate.py:82-88)
+            _call("b200_idw_fill_all", dec_xy.data_ptr(), dec_uv.data_ptr(), None, n_dec, 2, power, dist_offset, 1.0,
+                  xgrid.data_ptr(), n, ygrid.data_ptr(), mb, out.data_ptr(), _s())
+        else:
+            _call("b200_idw_fill", dec_xy.data_ptr(), dec_uv.data_ptr(), None, n_dec, 2, int(min(int(k), n_dec)),
+                  power, dist_offset, 1.0, xgrid.data_ptr(), n, ygrid.data_ptr(), mb, on_grid,
+                  out.data_ptr(), _s())
 
     if verbose:
         torch.cuda.current_stream().synchronize()

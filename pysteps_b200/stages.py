@@ -144,8 +144,20 @@ def detect_outliers(input_array, thr, coord=None, k=None, verbose=False):
     input_array = np.copy(input_array)
     if np.any(~np.isfinite(input_array)):
         raise ValueError("input_array contains non-finite values")
-    if input_array.ndim != 2 or input_array.shape[1] != 2 or coord is None or k is None:
-        raise NotImplementedError("pysteps_b200 detect_outliers: (n, 2) vectors with coord and k only")
+    if input_array.ndim != 2 or input_array.shape[1] != 2:
+        raise NotImplementedError("pysteps_b200 detect_outliers: (n, 2) vectors only")
+    if coord is None or k is None:
+        # global test (cleansing.py:201-214)
+        nsamples = input_array.shape[0]
+        if nsamples < 2:
+            return np.zeros(nsamples, dtype=bool)
+        duv = _device.to_device(np.ascontiguousarray(input_array, dtype=np.float64))
+        flags = torch.empty(nsamples, dtype=torch.uint8, device="cuda")
+        _lib.call("b200_detect_outliers_global", duv.data_ptr(), None, nsamples, float(thr), flags.data_ptr(), _s())
+        out = flags.cpu().numpy().astype(bool)
+        if verbose:
+            print(f"--- {np.sum(out)} outliers detected ---")
+        return out
     coord = np.copy(coord)
     if coord.ndim != 2 or coord.shape[1] != 2:
         raise NotImplementedError("pysteps_b200 detect_outliers: (n, 2) coordinates only")
@@ -220,8 +232,6 @@ def idwinterp2d(xy_coord, values, xgrid, ygrid, power=0.5, k=20, dist_offset=0.5
     if v_h.shape[0] != xy_h.shape[0]:
         raise ValueError("the number of samples in argument 'values' does not match the "
                          f"number of coordinates {v_h.shape[0]}!={xy_h.shape[0]}")
-    if k is None:
-        raise NotImplementedError("pysteps_b200 idwinterp2d: k=None is not implemented")
     out = torch.empty((nvar, ny, nx), dtype=torch.float64, device="cuda")
     v2 = v_h.reshape(v_h.shape[0], nvar)
     npts = v2.shape[0]
@@ -254,10 +264,15 @@ def idwinterp2d(xy_coord, values, xgrid, ygrid, power=0.5, k=20, dist_offset=0.5
             on_grid = 2  # half-pixel vectors on an integer grid: 32-bit integer keys (csrc/idw.cu)
         dxy = _device.to_device(np.ascontiguousarray(xy_h))
         dv = _device.to_device(np.ascontiguousarray(v2))
-        kk = int(min(int(k), npts))
+        kk = npts if k is None else int(min(int(k), npts))
 
         def fill(gx, gy, mean_res, dst):
             dgx, dgy = _device.to_device(gx), _device.to_device(gy)
+            if k is None:  # every point weighs in (interpolate.py:82-88)
+                _lib.call("b200_idw_fill_all", dxy.data_ptr(), dv.data_ptr(), None, npts, nvar, float(power),
+                          float(dist_offset), mean_res, dgx.data_ptr(), gx.size, dgy.data_ptr(), gy.size,
+                          dst.data_ptr(), _s())
+                return
             _lib.call("b200_idw_fill", dxy.data_ptr(), dv.data_ptr(), None, npts, nvar, kk, float(power),
                       float(dist_offset), mean_res, dgx.data_ptr(), gx.size, dgy.data_ptr(), gy.size,
                       int(on_grid), dst.data_ptr(), _s())

@@ -378,6 +378,17 @@ def _lk_detect_outliers(uv, xy, n_dev, cap, thr, k, out, stream):
                                    int(k), ctypes.c_void_p(_addr(out)))
 
 
+def _lk_detect_outliers_global(uv, n_dev, cap, thr, out, stream):
+    from oracle import lucaskanade as ora_lk
+    cnt = _count(n_dev, cap)
+    if cnt:
+        _view(out, (cap,), np.uint8)[:cnt] = ora_lk.detect_outliers(_view(uv, (cap, 2))[:cnt].copy(), thr)
+
+
+def _lk_idw_fill_all(xy, vals, n_dev, cap, nvar, power, offset, mean_res, xg, nx, yg, ny, out, stream):
+    _lk_idw_fill(xy, vals, n_dev, cap, nvar, None, power, offset, mean_res, xg, nx, yg, ny, 0, out, stream)
+
+
 def _lk_compact_rows(xy, uv, drop, n_dev, cap, oxy, ouv, ocount, stream):
     cnt = _count(n_dev, cap)
     keep = _view(drop, (cap,), np.uint8)[:cnt] == 0
@@ -433,7 +444,8 @@ _TABLE_LK = {"b200_mask_invalid": _lk_mask_invalid, "b200_morph_opening": _lk_mo
              "b200_masked_minmax": _lk_masked_minmax, "b200_quantise_u8": _lk_quantise,
              "b200_min_eig": _lk_min_eig, "b200_good_features": _lk_good_features,
              "b200_lk_build_pyramid": _lk_build_pyramid, "b200_lk_track": _lk_track,
-             "b200_lk_compact_tracks": _lk_compact_tracks, "b200_lk_frontend": _lk_frontend, "b200_detect_outliers": _lk_detect_outliers,
+             "b200_lk_compact_tracks": _lk_compact_tracks, "b200_lk_frontend": _lk_frontend,
+          "b200_detect_outliers_global": _lk_detect_outliers_global, "b200_idw_fill_all": _lk_idw_fill_all, "b200_detect_outliers": _lk_detect_outliers,
              "b200_compact_rows": _lk_compact_rows, "b200_decluster": _lk_decluster,
              "b200_idw_fill": _lk_idw_fill, "b200_idw_fill_ckdtree": _lk_idw_fill_ckdtree, "b200_fill_f64": _fill_f64}
 

@@ -55,7 +55,7 @@ def _random_call(rng):
     if rng.random() < 0.2:
         kw["decl_scale"] = int(rng.choice([1, 5, 40]))
     if rng.random() < 0.2:
-        kw["k_outlier"] = int(rng.choice([5, 30, 100]))
+        kw["k_outlier"] = [5, 30, 100, None][int(rng.integers(0, 4))]
         kw["nr_std_outlier"] = float(rng.choice([1, 2, 3]))
     inp = fr
     q = rng.random()

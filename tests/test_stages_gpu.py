@@ -88,3 +88,42 @@ def test_cleansing_and_interpolation(stages):
     full = stages.idwinterp2d(dxy, duv, xg, yg)
     band = stages.idwinterp2d(dxy, duv, xg, yg[60:130])
     assert np.array_equal(band, full[:, 60:130])
+
+
+def test_global_outlier_test_and_all_point_weighting(env=None):
+    """The k=None branches: cleansing.py:201-214 (every vector against the mean / covariance of all)
+    and interpolate.py:82-88 (every vector weighs in at every grid point), stand-alone and inside
+    dense_lucaskanade."""
+    import torch
+    assert torch.cuda.is_available(), "gpu-marked test needs a GPU"
+    from oracle import lucaskanade as ora
+    from pysteps_b200 import _synthetic as syn
+    from pysteps_b200 import stages
+    from pysteps_b200.motion import get_method
+    rng = np.random.default_rng(4)
+    for n in (2, 3, 50, 700, 2500):
+        uv = np.stack([2 + 0.4 * rng.standard_normal(n), -1 + 0.3 * rng.standard_normal(n)], 1)
+        uv[::9] += 3.0
+        for thr in (1.0, 2.0, 3.0):
+            got = stages.detect_outliers(uv, thr)
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                want = ora.detect_outliers(uv, thr)
+            assert np.array_equal(got, want), (n, thr)
+    for npts, (ny, nx) in ((3, (20, 30)), (40, (64, 70)), (1500, (90, 100))):
+        xy = rng.uniform(0, 100, (npts, 2))
+        vals = rng.standard_normal((npts, 2))
+        gx, gy = np.arange(nx, dtype=float), np.arange(ny, dtype=float)
+        got = stages.idwinterp2d(xy, vals, gx, gy, k=None)
+        want = ora.idwinterp2d(xy, vals, gx, gy, k=None)
+        assert np.abs(got - want).max() <= 1e-12, npts
+    fr = syn.rain_frames(160, 192, 2, 1)
+    lk = get_method("lk")
+    with ora.knn_mode("ckdtree"):
+        xy, uv = lk(fr, dense=False, k_outlier=None)
+        oxy, ouv = ora.dense_lucaskanade(fr, dense=False, k_outlier=None)
+        assert np.array_equal(xy, oxy) and np.array_equal(uv, ouv)
+        V = lk(fr, interp_kwargs={"k": None})
+        Vo = ora.dense_lucaskanade(fr, interp_kwargs={"k": None})
+        assert np.abs(V - Vo).max() <= 1e-12
