@@ -114,24 +114,63 @@ def make_inputs(w, seed):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """nvidia-smi in loop mode (-lms 200, the profiling recipe's clocks line) from the warm-up to the
-    end of the timed steps.  The first sample (taken before any load) is dropped."""
+    """SM clock and throttle reasons of rank 0's GPU every 200 ms from the warm-up to the end of the
+    timed steps -- the fields of the profiling recipe's nvidia-smi line (clocks.sm, clocks.max.sm,
+    the four clocks_event_reasons), read through NVML in a background thread.  An `nvidia-smi -lms`
+    loop re-enumerates the box on every poll under a driver-wide lock that kernel launches also take:
+    it slowed a launch-heavy step by 40 % on one GPU and by 4x with eight ranks on the box.
+    Falls back to the nvidia-smi loop when pynvml is unavailable."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index=0, enabled=True):
         self.index = index
-        # one sampler per job (rank 0's GPU): nvidia-smi polls serialise on a driver-wide lock
-        # that kernel launches of every process on the box also take
         self.enabled = enabled and not os.environ.get("BENCH_NO_CLOCKS")
-        self.samples = []
+        self.samples = []     # (sm_mhz, max_mhz, reason bitmask)
         self.proc = None
+        self.thread = None
+        self.source = None
+        self._stop = False
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+
+    def _poll(self, nv, h):
+        while not self._stop:
+            try:
+                self.samples.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM),
+                                     nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM),
+                                     int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))))
+            except Exception:
+                pass
+            time.sleep(0.2)
 
     def __enter__(self):
         if not self.enabled:
             return self
         try:
+            import threading
+            nv, h = self._nvml_handle()
+            self.source = "nvml (pynvml), 200 ms"
+            self.thread = threading.Thread(target=self._poll, args=(nv, h), daemon=True)
+            self.thread.start()
+            time.sleep(0.25)
+            return self
+        except Exception:
+            self.thread = None
+        try:
+            self.source = "nvidia-smi -lms 200"
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                  "--format=csv,noheader,nounits", "-lms", "200"],
@@ -142,32 +181,33 @@ class ClockSampler:
         return self
 
     def __exit__(self, *exc):
-        if self.proc is None:
-            return
-        time.sleep(0.05)
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except Exception:
-            self.proc.kill()
-            out = ""
-        for line in (out or "").splitlines():
-            parts = [x.strip() for x in line.split(",")]
-            if len(parts) >= 6:
-                self.samples.append(parts)
+        if self.thread is not None:
+            time.sleep(0.05)
+            self._stop = True
+            self.thread.join(timeout=2)
+        if self.proc is not None:
+            time.sleep(0.05)
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                self.proc.kill()
+                out = ""
+            for line in (out or "").splitlines():
+                parts = [x.strip() for x in line.split(",")]
+                if len(parts) >= 6 and parts[0].isdigit() and parts[1].isdigit():
+                    mask = sum(bit for (nm, bit), v in zip(self.BITS, parts[2:6]) if v.lower() == "active")
+                    self.samples.append((int(parts[0]), int(parts[1]), mask))
         if len(self.samples) >= 3:
-            self.samples = self.samples[1:]
+            self.samples = self.samples[1:]  # the first sample was taken before any load
 
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [nm for k, nm in enumerate(names)
-                   if any(len(s) > 2 + k and s[2 + k].lower() == "active" for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+        sm = sorted(s[0] for s in self.samples)
+        reasons = [nm for nm, bit in self.BITS if any(s[2] & bit for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(s[1] for s in self.samples), "reasons": reasons,
+                "samples": len(self.samples), "source": self.source}
 
 
 def stage_rooflines(trace_ms, steps, m, n, peak_gbs, sl_bytes):

@@ -34,7 +34,18 @@ def require_cuda():
         _initialised = True
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_ptr():
+    """cudaStream_t of torch's current stream on the current device (what every C-ABI call is
+    enqueued on).  The raw accessor is ~1 us; torch.cuda.current_stream() builds a Stream object
+    (~15 us -- three per ensemble member-step add up)."""
+    if _raw_stream is not None:
+        try:
+            return _raw_stream(torch.cuda.current_device())
+        except Exception:  # noqa: BLE001 -- fall back to the public API
+            pass
     return torch.cuda.current_stream().cuda_stream
 
 

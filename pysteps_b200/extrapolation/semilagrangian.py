@@ -14,6 +14,7 @@ Inputs may be NumPy arrays (results are NumPy arrays, one H2D per input and one
 D2H per output) or CUDA ``torch`` tensors (results stay on the device).
 """
 import math
+import threading
 import os
 import time
 import warnings
@@ -70,10 +71,28 @@ def _field_tensor(a):
     return _device.to_device(a, torch.float64)
 
 
+_pinned = threading.local()
+
+
+def _pinned_slot(rows):
+    """A small pinned host buffer from a per-thread ring (allocating pinned memory per call costs
+    more than the copy it receives)."""
+    ring = getattr(_pinned, "ring", None)
+    if ring is None:
+        ring = _pinned.ring = [torch.empty((4, 4), dtype=torch.float64, pin_memory=True) for _ in range(8)]
+        _pinned.next = 0
+    if rows > 4:
+        return torch.empty((rows, 4), dtype=torch.float64, pin_memory=True)
+    _pinned.next = (_pinned.next + 1) % len(ring)
+    return ring[_pinned.next][:rows]
+
+
 class _Stats:
     """[(n_nonfinite, nanmin, nanmax, n_nan), ...] of the given fields, reduced on the device.
-    The kernels are enqueued at construction; `get()` performs the (single, tiny) D2H and is
-    called as late as possible so that the trajectory kernel is already in flight."""
+    The kernels are enqueued at construction.  `post()` -- called once every kernel that writes a
+    row has been enqueued, and BEFORE the trajectory kernel is -- enqueues the tiny D2H into pinned
+    memory and records an event; `get()` waits for that event only, so the host reads the verdict
+    while the trajectory kernel is still running instead of draining the stream."""
 
     def __init__(self, *tensors):
         self.buf = torch.empty((len(tensors), 4), dtype=torch.float64, device="cuda")
@@ -83,10 +102,21 @@ class _Stats:
                 _lib.call("b200_field_stats", t.data_ptr(), _device.dtype_code(t.dtype), t.numel(),
                           self.buf[i].data_ptr(), s)
         self.host = None
+        self._pin = self._event = None
+
+    def post(self):
+        if self._event is None and self.host is None:
+            self._pin = _pinned_slot(self.buf.shape[0])
+            self._pin.copy_(self.buf, non_blocking=True)
+            self._event = torch.cuda.Event()
+            self._event.record()
+        return self
 
     def get(self):
         if self.host is None:
-            self.host = self.buf.cpu().numpy()
+            self.post()
+            self._event.synchronize()
+            self.host = self._pin.numpy().copy()
         return self.host
 
 
@@ -120,9 +150,10 @@ def extrapolate(precip, velocity, timesteps, outval=np.nan, xy_coords=None,
         # the producing kernel counts the non-finite elements of the perturbed field itself
         stats = _Stats(*([None] if d_precip is None else [d_precip, None]))
         d_vel = velocity.device_interleaved(stats.buf[-1, 0:1])
+        stats.post()
     else:
         d_vel = _field_tensor(velocity)
-        stats = _Stats(*([d_vel] if d_precip is None else [d_precip, d_vel]))
+        stats = _Stats(*([d_vel] if d_precip is None else [d_precip, d_vel])).post()
 
     def finiteness_errors():
         st = stats.get()
@@ -366,7 +397,7 @@ def extrapolate_members(precip, perturbed_velocities, displacement_prev=None, ti
         raise ValueError("precip and velocity have incompatible shapes")
     on_device = _device.is_device_tensor(precip)
     d_precip = _field_tensor(precip)
-    stats = _Stats(d_precip)
+    stats = _Stats(d_precip).post()
     coefs = np.ascontiguousarray([[v.pert.a, v.pert.b] for v in perturbed_velocities], dtype=np.float64)
     d_prev = None
     if displacement_prev is not None:

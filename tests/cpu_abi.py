@@ -497,6 +497,9 @@ class _Event:
     def record(self, *a):
         pass
 
+    def synchronize(self):
+        pass
+
 
 @contextlib.contextmanager
 def emulated():
