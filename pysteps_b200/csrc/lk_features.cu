@@ -350,7 +350,11 @@ extern "C" int b200_good_features(const float *eig, const uint8_t *valid, int m,
     B200_LAUNCH_CHECK();
     // every interior pixel can be a candidate on a plateau
     const unsigned cap = (unsigned)N;
-    B200_CUDA(keys.alloc(sizeof(unsigned long long) * ((size_t)cap + SORT_TILE), s));
+    // the bitonic network sorts the next power of two above the candidate count (padding zeroed):
+    // size the buffer for the largest count possible
+    size_t cap_pow2 = SORT_TILE;
+    while (cap_pow2 < (size_t)cap) cap_pow2 <<= 1;
+    B200_CUDA(keys.alloc(sizeof(unsigned long long) * cap_pow2, s));
     candidates_kernel<<<dim3(b200::ceil_div(n, TX), b200::ceil_div(m, TY)), dim3(TX, TY), 0, s>>>(
         eig, valid, m, n, (unsigned *)state.p, (unsigned long long *)keys.p, cap);
     B200_LAUNCH_CHECK();

@@ -40,9 +40,13 @@ def _is_default_grid(xy_coords, m, n):
         return False
     key = id(xy_coords)
     ref = _default_grid_seen.get(key)
-    if ref is not None and ref() is xy_coords:
-        return True
     xy = np.asarray(xy_coords)
+    if ref is not None and ref() is xy_coords:
+        # seen before: a few O(1) probes guard against an in-place edit since (corners and centre of
+        # both planes); anything else falls through to the full comparison
+        if (xy.shape == (2, m, n) and xy[0, 0, 0] == 0 and xy[1, 0, 0] == 0 and xy[0, -1, -1] == n - 1
+                and xy[1, -1, -1] == m - 1 and xy[0, m // 2, n // 2] == n // 2 and xy[1, m // 2, n // 2] == m // 2):
+            return True
     ok = (xy.shape == (2, m, n)
           and np.array_equal(xy[0], np.broadcast_to(np.arange(n), (m, n)))
           and np.array_equal(xy[1], np.broadcast_to(np.arange(m)[:, None], (m, n))))
