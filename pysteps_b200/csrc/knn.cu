@@ -537,7 +537,7 @@ int idw_fix(const double *xy, const double *vals, int nvar, int k, double power,
     const size_t N = (size_t)ny * nx;
     if (k <= NBSMEM) {
         // as many warps as the chip holds (one search each); the list is usually shorter
-        const int blocks = (int)std::max<size_t>(1, std::min<size_t>((N + QW - 1) / QW, (size_t)b200::num_sms() * 12));
+        const int blocks = (int)std::max<size_t>(1, std::min<size_t>((N + QW - 1) / QW, (size_t)b200::num_sms() * 16));  // 16 CTAs of 4 warps fill an SM
         idw_fix_warp_kernel<<<blocks, 32 * QW, 0, s>>>(p);
         B200_LAUNCH_CHECK();
         return 0;

@@ -241,23 +241,47 @@ __device__ __forceinline__ Cov cov_at(const uint8_t *__restrict__ q, int h, int 
     return c;
 }
 
-// per pixel: the three 5-tap row sums of the covariance products, in double, left to right
-__global__ void __launch_bounds__(TX *TY)
+// per pixel: the three 5-tap row sums of the covariance products, in double, left to right.
+// A CTA evaluates the products of its 64 x 8 tile plus two columns either side ONCE into shared
+// memory (already widened to double), then every pixel adds its five neighbours: 9.6 u8 loads and
+// conversions per pixel instead of 45 -- the conversion (XU) pipe bounded the per-pixel version.
+constexpr int CR_W = 64, CR_H = 8, CR_P = CR_W + 4;
+
+__global__ void __launch_bounds__(256)
 cov_rowsum_kernel(const uint8_t *__restrict__ q, int h, int w, double *__restrict__ rs) {
-    const int x = blockIdx.x * TX + threadIdx.x, y = blockIdx.y * TY + threadIdx.y;
-    if (x >= w || y >= h) return;
+    __shared__ double s_xx[CR_H][CR_P], s_xy[CR_H][CR_P], s_yy[CR_H][CR_P];
+    const int x0 = blockIdx.x * CR_W, y0 = blockIdx.y * CR_H;
     const int tail0 = (w / 32) * 32;
-    double sxx = 0.0, sxy = 0.0, syy = 0.0;
-#pragma unroll
-    for (int d = -2; d <= 2; d++) {
-        const Cov c = cov_at(q, h, w, y, reflect101(x + d, w), tail0);
-        if (d == -2) { sxx = (double)c.xx; sxy = (double)c.xy; syy = (double)c.yy; }
-        else { sxx = __dadd_rn(sxx, (double)c.xx); sxy = __dadd_rn(sxy, (double)c.xy); syy = __dadd_rn(syy, (double)c.yy); }
+    for (int i = threadIdx.x; i < CR_H * CR_P; i += 256) {
+        const int r = i / CR_P, c = i - r * CR_P;
+        const int y = y0 + r, xs = x0 - 2 + c;
+        if (y < h && xs <= w + 1) {  // columns past w + 1 feed no pixel of the image
+            const Cov cv = cov_at(q, h, w, y, reflect101(xs, w), tail0);
+            s_xx[r][c] = (double)cv.xx;
+            s_xy[r][c] = (double)cv.xy;
+            s_yy[r][c] = (double)cv.yy;
+        }
     }
-    const size_t N = (size_t)h * w, i = (size_t)y * w + x;
-    rs[i] = sxx;
-    rs[N + i] = sxy;
-    rs[2 * N + i] = syy;
+    __syncthreads();
+    const size_t N = (size_t)h * w;
+    const int r = threadIdx.x >> 5, y = y0 + r;
+    if (y >= h) return;
+#pragma unroll
+    for (int k = 0; k < CR_W / 32; k++) {
+        const int c = (threadIdx.x & 31) + 32 * k, x = x0 + c;
+        if (x >= w) break;
+        double sxx = s_xx[r][c], sxy = s_xy[r][c], syy = s_yy[r][c];
+#pragma unroll
+        for (int d = 1; d < 5; d++) {
+            sxx = __dadd_rn(sxx, s_xx[r][c + d]);
+            sxy = __dadd_rn(sxy, s_xy[r][c + d]);
+            syy = __dadd_rn(syy, s_yy[r][c + d]);
+        }
+        const size_t i = (size_t)y * w + x;
+        rs[i] = sxx;
+        rs[N + i] = sxy;
+        rs[2 * N + i] = syy;
+    }
 }
 
 // per column: OpenCV's running column sum (double) down the rows, then the eigenvalue.
@@ -305,10 +329,42 @@ box_chain_kernel(const double *__restrict__ rs, int h, int w, float *__restrict_
     for (int y = 0; y < BOX_R; y++) issue(y);
     // BOX_U rows per round: ONE wait for the whole group, the BOX_U entering rows read from the ring
     // into registers (independent loads), then the dependent add / subtract chain alone on the
-    // critical path -- the wait and the shared-memory latency are paid once per round, not per row
+    // critical path -- the wait and the shared-memory latency are paid once per round, not per row.
+    // A lone warp issues one instruction every ~4.6 cycles (ncu: issue active 22 %), so the row rate
+    // is set by the INSTRUCTION COUNT of a row: interior rounds (all rows of the round and all rows
+    // they prefetch inside the image) run without the reflection / bounds arithmetic -- ~11
+    // instructions per row instead of 52.
     constexpr int BOX_U = 8;
-    for (int y0 = 0; y0 < h; y0 += BOX_U) {
+    static_assert(BOX_R % BOX_U == 0 && BOX_U % 4 == 0, "ring slots and the delay line are addressed by u");
+    // (lanes past the last column shadow column w - 1: they compute and store the very same values
+    // to the very same addresses, so the stores need no predicate)
+    const bool live = x < w;
+    int y0 = 0;
+    float *__restrict__ o = dst + xc;                                   // output row y0
+    const double *__restrict__ nx = src + (size_t)(BOX_R + 2) * w + xc;  // entering row of step y0 + BOX_R
+    for (; y0 + BOX_R + BOX_U + 2 <= h; y0 += BOX_U) {
         cp_async_wait<BOX_R - BOX_U>();  // rows y0 .. y0 + BOX_U - 1 have landed
+        double(*slot)[32] = ring_s + (y0 % BOX_R);
+        double in[BOX_U];
+#pragma unroll
+        for (int u = 0; u < BOX_U; u++) in[u] = slot[u][lane];
+#pragma unroll
+        for (int u = 0; u < BOX_U; u++) {
+            const double a = __dadd_rn(S, in[u]);
+            S = __dsub_rn(a, delay[u & 3]);
+            delay[u & 3] = in[u];
+            *o = __double2float_rn(a);
+            o += w;
+        }
+#pragma unroll
+        for (int u = 0; u < BOX_U; u++) {  // refill the slots just consumed
+            cp_async8(&slot[u][lane], nx);
+            cp_async_commit();
+            nx += w;
+        }
+    }
+    for (; y0 < h; y0 += BOX_U) {  // the last BOX_R + BOX_U + 2 rows: reflected prefetches, ragged end
+        cp_async_wait<BOX_R - BOX_U>();
         double in[BOX_U];
 #pragma unroll
         for (int u = 0; u < BOX_U; u++) in[u] = ring_s[(y0 + u) % BOX_R][lane];
@@ -319,11 +375,11 @@ box_chain_kernel(const double *__restrict__ rs, int h, int w, float *__restrict_
                 const double a = __dadd_rn(S, in[u]);
                 S = __dsub_rn(a, delay[u & 3]);  // y0 is a multiple of 4
                 delay[u & 3] = in[u];
-                if (x < w) dst[(size_t)y * w + x] = __double2float_rn(a);
+                if (live) dst[(size_t)y * w + x] = __double2float_rn(a);
             }
         }
 #pragma unroll
-        for (int u = 0; u < BOX_U; u++) issue(y0 + u + BOX_R);  // refill the slots just consumed
+        for (int u = 0; u < BOX_U; u++) issue(y0 + u + BOX_R);
     }
 }
 
@@ -421,7 +477,7 @@ extern "C" int b200_min_eig(const uint8_t *q, int m, int n, float *eig, void *st
     const size_t N = (size_t)m * n;
     B200_CUDA(rs.alloc(sizeof(double) * 3 * N, s));
     B200_CUDA(box.alloc(sizeof(float) * 3 * N, s));
-    cov_rowsum_kernel<<<grid2d(m, n), dim3(TX, TY), 0, s>>>(q, m, n, (double *)rs.p);
+    cov_rowsum_kernel<<<dim3(b200::ceil_div(n, CR_W), b200::ceil_div(m, CR_H)), 256, 0, s>>>(q, m, n, (double *)rs.p);
     B200_LAUNCH_CHECK();
     box_chain_kernel<<<dim3(b200::ceil_div(n, 32), 3), 32, 0, s>>>((const double *)rs.p, m, n, (float *)box.p);
     B200_LAUNCH_CHECK();
