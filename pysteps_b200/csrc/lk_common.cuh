@@ -50,7 +50,14 @@ __device__ __forceinline__ MM mm_block(MM v, MM *sm) {
     return v;
 }
 
-// stats layout written by the final kernel: [min, max, count] (+3 per set)
+// stats layout: [min, max, count] (+3 per set)
+__device__ __forceinline__ void mm_write_stats(double *__restrict__ stats, int s, const MM &v) {
+    // numpy's masked min()/max() of an all-masked array is `masked`; report NaN
+    stats[3 * s + 0] = v.cnt ? v.mn : CUDART_NAN;
+    stats[3 * s + 1] = v.cnt ? v.mx : CUDART_NAN;
+    stats[3 * s + 2] = (double)v.cnt;
+}
+
 __global__ void __launch_bounds__(256) mm_final_kernel(const MM *__restrict__ part, int nparts, int nsets,
                                                        double *__restrict__ stats) {
     __shared__ MM sm[32];
@@ -59,12 +66,37 @@ __global__ void __launch_bounds__(256) mm_final_kernel(const MM *__restrict__ pa
         v.mn = CUDART_INF; v.mx = -CUDART_INF; v.cnt = 0;
         for (int i = threadIdx.x; i < nparts; i += blockDim.x) v = mm_merge(v, part[(size_t)s * nparts + i]);
         v = mm_block(v, sm);
-        if (threadIdx.x == 0) {
-            // numpy's masked min()/max() of an all-masked array is `masked`; report NaN
-            stats[3 * s + 0] = v.cnt ? v.mn : CUDART_NAN;
-            stats[3 * s + 1] = v.cnt ? v.mx : CUDART_NAN;
-            stats[3 * s + 2] = (double)v.cnt;
+        if (threadIdx.x == 0) mm_write_stats(stats, s, v);
+        __syncthreads();
+    }
+}
+
+// The same final reduction WITHOUT a second launch: every CTA publishes its partials, takes a
+// ticket, and the CTA that draws the last one reduces them all (`ticket` is zeroed by the caller on
+// the stream before the launch).  Order of the merges: min / max / integer counts are associative,
+// so the statistics are those of mm_final_kernel bit for bit.  Call from ALL threads of the CTA,
+// after thread 0 has stored this CTA's partials (flat thread index `tid`, 1-D or 2-D blocks).
+__device__ __forceinline__ void mm_finish(const MM *part, int nparts, int nsets, double *__restrict__ stats,
+                                          unsigned *ticket, MM *sm, int tid, int nthreads) {
+    __shared__ int s_last;
+    if (tid == 0) {
+        __threadfence();  // the partials before the ticket
+        s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int s = 0; s < nsets; s++) {
+        MM v;
+        v.mn = CUDART_INF; v.mx = -CUDART_INF; v.cnt = 0;
+        for (int i = tid; i < nparts; i += nthreads) {
+            const MM *q = part + (size_t)s * nparts + i;
+            MM t;
+            t.mn = __ldcg(&q->mn); t.mx = __ldcg(&q->mx); t.cnt = __ldcg(&q->cnt);  // other CTAs' stores: from L2
+            v = mm_merge(v, t);
         }
+        v = mm_block(v, sm);
+        if (tid == 0) mm_write_stats(stats, s, v);
         __syncthreads();
     }
 }

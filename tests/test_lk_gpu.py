@@ -66,6 +66,75 @@ class Stages:
                self.st.data_ptr(), self.st.data_ptr(), self.q_det.data_ptr(), self.valid.data_ptr(), s)
 
 
+def _boundary_frame(m, n, seed):
+    """Values whose scaled image (x - min) / (max - min) * 255 sits on, and a few ulps either side of,
+    integer boundaries -- where the fused front end's division-free scaling must defer to the division."""
+    rng = np.random.default_rng(seed)
+    k = rng.integers(0, 256, size=(m, n)).astype(np.float64)
+    a = k / 255.0 * 40.0
+    ulps = rng.integers(-3, 4, size=(m, n))
+    a = np.where(ulps == 0, a, np.nextafter(a, np.where(ulps > 0, np.inf, -np.inf)))
+    a[0, 0], a[0, 1] = 0.0, 40.0
+    a[rng.random((m, n)) < 0.3] = 0.0
+    return a
+
+
+@pytest.mark.parametrize("case", ["plain_160x200", "nan_200x176", "boundary", "nan_boundary", "f32"])
+@pytest.mark.parametrize("buffer_mask,opening", [(5, 3), (0, 3), (3, 0), (4, 3), (1, 3), (2, 0)])
+def test_fused_front_end_equals_stage_kernels(env, case, buffer_mask, opening):
+    """b200_lk_frontend (TMA tiles, bit-row stencils, division-free scaling) against the stand-alone
+    stage kernels, bit for bit: mask, both statistics blocks, both uint8 images, the validity map."""
+    torch, L = env
+    f32 = case == "f32"
+    if case in ("boundary", "nan_boundary"):
+        fr = _boundary_frame(144, 200, 5)
+        if case == "nan_boundary":
+            fr[40:60, 90:130] = np.nan
+            fr[3, 5] = np.nan
+    elif f32:
+        fr = _frames("nan_200x176")[0].astype(np.float32).astype(np.float64)
+    else:
+        fr = _frames(case)[0]
+    m, n = fr.shape
+    s = torch.cuda.current_stream().cuda_stream
+    img = torch.from_numpy(np.ascontiguousarray(fr)).cuda()
+    flag = 2 if f32 else 0  # B200_QUANTISE_F32
+    # stage kernels
+    mask = torch.empty((m, n), dtype=torch.uint8, device="cuda")
+    st0 = torch.empty(3, dtype=torch.float64, device="cuda")
+    L.call("b200_mask_invalid", img.data_ptr(), None, m, n, mask.data_ptr(), st0.data_ptr(), s)
+    opened = img
+    if opening:
+        opened = torch.empty((m, n), dtype=torch.float64, device="cuda")
+        L.call("b200_morph_opening", img.data_ptr(), mask.data_ptr(), m, n, 3, st0.data_ptr(), st0.data_ptr(),
+               opened.data_ptr(), s)
+    st = torch.empty(12, dtype=torch.float64, device="cuda")
+    L.call("b200_masked_minmax", opened.data_ptr(), mask.data_ptr(), m, n, buffer_mask, st0.data_ptr(),
+           st.data_ptr(), s)
+    q_track = torch.empty((m, n), dtype=torch.uint8, device="cuda")
+    L.call("b200_quantise_u8", opened.data_ptr(), mask.data_ptr(), m, n, 0 | flag, 0, st.data_ptr(), st.data_ptr(),
+           q_track.data_ptr(), None, s)
+    q_det = torch.empty((m, n), dtype=torch.uint8, device="cuda")
+    valid = torch.empty((m, n), dtype=torch.uint8, device="cuda")
+    L.call("b200_quantise_u8", opened.data_ptr(), mask.data_ptr(), m, n, 1 | flag, buffer_mask, st.data_ptr(),
+           st.data_ptr(), q_det.data_ptr(), valid.data_ptr(), s)
+    # fused
+    mask2 = torch.zeros((m, n), dtype=torch.uint8, device="cuda")
+    st0b = torch.zeros(3, dtype=torch.float64, device="cuda")
+    stb = torch.zeros(12, dtype=torch.float64, device="cuda")
+    qt2 = torch.zeros((m, n), dtype=torch.uint8, device="cuda")
+    qd2 = torch.zeros((m, n), dtype=torch.uint8, device="cuda")
+    v2 = torch.zeros((m, n), dtype=torch.uint8, device="cuda")
+    L.call("b200_lk_frontend", img.data_ptr(), None, m, n, opening, buffer_mask, flag, mask2.data_ptr(),
+           st0b.data_ptr(), stb.data_ptr(), qt2.data_ptr(), qd2.data_ptr(), v2.data_ptr(), s)
+    assert torch.equal(mask, mask2)
+    assert_bits_equal(st0b.cpu().numpy(), st0.cpu().numpy(), "frame statistics")
+    assert_bits_equal(stb.cpu().numpy(), st.cpu().numpy(), "opened-image statistics")
+    assert torch.equal(q_track, qt2), f"tracking image: {(q_track != qt2).sum().item()} pixels differ"
+    assert torch.equal(q_det, qd2), f"detection image: {(q_det != qd2).sum().item()} pixels differ"
+    assert torch.equal(valid, v2)
+
+
 @pytest.mark.parametrize("name", ["plain_160x200", "nan_200x176", "odd_width_150x203"])
 def test_dense_stages(env, name):
     torch, L = env
