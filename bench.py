@@ -835,6 +835,59 @@ def roofline_of(b, w, blk, peaks):
     return roofline, roofline_fp64, peak, alg_bytes
 
 
+def float32_taps_block(b, w, peaks, reps=10):
+    """The OPT-IN float32-tap trajectory kernel timed beside the exact one on this workload's motion field
+    (device-resident inputs, L2 flushed, CUDA events around each C call).  Its call contains the float64 ->
+    float32 copy of the field and the exact fix-up launch over the uncertified pixels, so `ms_per_call` is
+    what a user pays; the exact path's `interleave` call is listed beside its kernel for the same reason."""
+    import pysteps_b200
+    from pysteps_b200 import _lib
+    torch = b.torch
+    m, n, T = w["m"], w["n"], w["T"]
+    frames, precip, _ = make_inputs(w, 0)
+    P = torch.from_numpy(precip).cuda()
+    V = pysteps_b200.motion.get_method("lk")(torch.from_numpy(frames).cuda())
+    extrap = pysteps_b200.extrapolation.get_method("semilagrangian")
+
+    def timed(names, **kw):
+        for _ in range(3):
+            extrap(P, V, T, **kw)
+        acc = {k: [] for k in names}
+        for _ in range(reps):
+            b.flush.fill_(1)
+            with _lib.Trace(only=names) as tr:
+                extrap(P, V, T, **kw)
+            for k, v in tr.summary().items():
+                acc[k] += v
+        return {k: sum(v) / len(v) for k, v in acc.items() if v}
+
+    ex = timed(("b200_sl_extrapolate_rows", "b200_sl_interleave_velocity"))
+    fa = timed(("b200_sl_extrapolate_rows_f32", "b200_sl_interleave_velocity"), b200_float32_taps=True)
+    exact, dex = extrap(P, V, T, return_displacement=True)
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    fast, dfa = extrap(P, V, T, return_displacement=True, b200_float32_taps=True, b200_fallback_count=cnt)
+    err = torch.nan_to_num((fast.double() - exact.double()).abs(), nan=0.0).max().item()
+    gy, gx = torch.meshgrid(torch.arange(m, device="cuda", dtype=torch.float64),
+                            torch.arange(n, device="cuda", dtype=torch.float64), indexing="ij")
+    same_idx = bool(torch.equal(torch.floor(gx + dfa[0]), torch.floor(gx + dex[0]))
+                    and torch.equal(torch.floor(gy + dfa[1]), torch.floor(gy + dex[1])))
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg = m * n * (8 + 4 + 4 * T)  # float32 field pairs + float32 precip in + T float32 planes out
+    call_ms = fa["b200_sl_extrapolate_rows_f32"]
+    return {"what": "opt-in b200_float32_taps=True: float32 taps, float64 trajectory, tap indices certified equal to "
+                    "the exact kernel's, uncertified pixels recomputed by the exact code (csrc/sl.cu sl_f32_kernel)",
+            "ms_per_call": call_ms, "interleave_ms": fa.get("b200_sl_interleave_velocity"),
+            "exact_ms_per_call": ex["b200_sl_extrapolate_rows"], "exact_interleave_ms": ex.get("b200_sl_interleave_velocity"),
+            "speedup_vs_exact_call": ex["b200_sl_extrapolate_rows"] / call_ms,
+            "recomputed_fraction": cnt.item() / (m * n),
+            "max_value_error_over_max_precip": err / float(P.abs().max()),
+            "max_displacement_error_px": (dfa - dex).abs().max().item(),
+            "tap_indices_equal": same_idx,
+            "nan_pattern_equal": bool(torch.equal(torch.isnan(fast), torch.isnan(exact))),
+            "roofline": {"bound": "hbm", "achieved": alg / (call_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (call_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": alg}}
+
+
 def public(blk):
     return {k: v for k, v in blk.items() if not k.startswith("_")}
 
@@ -887,6 +940,11 @@ def run_ours(args, w):
                      "parity": parity, "cpu_baseline": cpu, "stage_ms_per_step": stage_ms,
                      "stage_rooflines": stages})
         line.update(extras)
+        if not args.no_extras and args.workload == "lk_sl12_2048" and b.world == 1 and b.lk:
+            try:
+                line["sl_float32_taps"] = float32_taps_block(b, w, peaks)
+            except Exception as exc:  # supplementary block only
+                line["sl_float32_taps"] = {"error": repr(exc)}
         print(json.dumps(line))
     else:
         if not args.no_parity:

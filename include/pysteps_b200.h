@@ -91,6 +91,21 @@ int b200_sl_extrapolate_rows(const void *precip, const void *velocity,
                              int row_begin, int row_count, void *out, double *disp_out,
                              void *stream);
 
+/* OPT-IN float32-tap variant of b200_sl_extrapolate_rows (no counterpart in the reference, whose
+ * arithmetic is float64 throughout; the north star allows "a stated float32 tolerance (bit-exact
+ * for the integer displacement indices)"): the trajectory stays float64, the fields are sampled from
+ * float32 copies.  A per-pixel error bound certifies that every sample floors to the same tap indices
+ * as the exact kernel; pixels that cannot be certified (near a cell boundary, the border, outside,
+ * non-finite) are recomputed by the exact code inside the same launch.  Values: within float32
+ * rounding of b200_sl_extrapolate_rows.  Restrictions: n_iter = 1, pixel-grid coordinates, a
+ * precipitation field, T <= 32.  fallback_count (device uint64, optional, accumulated not reset):
+ * number of recomputed pixels. */
+int b200_sl_extrapolate_rows_f32(const void *precip, const void *velocity, const double *disp_prev,
+                                 const double *tdiff, int T, double vel_timestep, double outval, int mode,
+                                 int velocity_dtype, int velocity_layout, int precip_dtype, int m, int n,
+                                 int row_begin, int row_count, void *out, double *disp_out,
+                                 unsigned long long *fallback_count, void *stream);
+
 /* Displacement field after EVERY leadtime, disp_steps (T, 2, row_count, n) float64: the
  * trajectory part of b200_sl_extrapolate_rows alone (semilagrangian.py:201-219), for samplers
  * other than the built-in order-1 warp (interp_order 0 and 2..5 below).  Same arithmetic as the fused

@@ -36,6 +36,9 @@ _SIGNATURES = {
     "b200_sl_extrapolate_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_dp, c_int, c_double,
                                          c_int, c_double, c_int, c_int, c_int, c_int, c_int, c_int,
                                          c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "b200_sl_extrapolate_rows_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_dp, c_int, c_double, c_double, c_int,
+                                             c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                             c_void_p, c_void_p]),
     "b200_sl_interleave_velocity": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "b200_sl_trajectories": (c_int, [c_void_p, c_void_p, c_void_p, c_dp, c_int, c_double, c_int, c_int, c_int,
                                      c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

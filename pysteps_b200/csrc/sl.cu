@@ -119,7 +119,9 @@ __device__ __noinline__ double2 slow_velocity(const double2 *__restrict__ Vi, in
 }
 
 // map_coordinates(precip, order=1, mode, cval) for one pixel (:221-232), generic path
-__device__ __noinline__ double slow_precip(const double *__restrict__ P, int m, int n, double cy,
+// (PT: storage type of the field; the trajectory kernel reads float64, widened once per call)
+template <typename PT>
+__device__ __noinline__ double slow_precip(const PT *__restrict__ P, int m, int n, double cy,
                                            double cx, int mode, double cval) {
     const Axis ay = make_axis(cy, m), ax = make_axis(cx, n);
     int y0 = ay.i0, y1 = ay.i1, x0 = ax.i0, x1 = ax.i1;
@@ -130,10 +132,10 @@ __device__ __noinline__ double slow_precip(const double *__restrict__ P, int m, 
         y1 = (y0 + 1 < m) ? y0 + 1 : (m > 1 ? m - 2 : 0);
         x1 = (x0 + 1 < n) ? x0 + 1 : (n > 1 ? n - 2 : 0);
     }
-    const double *r0 = P + (size_t)y0 * n;
-    const double *r1 = P + (size_t)y1 * n;
-    return bilin(__ldg(r0 + x0), __ldg(r0 + x1), __ldg(r1 + x0), __ldg(r1 + x1), ay.w0, ay.w1,
-                 ax.w0, ax.w1);
+    const PT *r0 = P + (size_t)y0 * n;
+    const PT *r1 = P + (size_t)y1 * n;
+    return bilin((double)__ldg(r0 + x0), (double)__ldg(r0 + x1), (double)__ldg(r1 + x0), (double)__ldg(r1 + x1),
+                 ay.w0, ay.w1, ax.w0, ax.w1);
 }
 
 // ---- fast path: footprint strictly inside the array ------------------------------------
@@ -202,12 +204,11 @@ template <> __device__ __forceinline__ double from_double<double>(double v) { re
 // the inner loop / division branches.
 // VF32: the velocity was float32 at the API (a compile-time fact of the launch: the rounding of
 // the sampled increments costs conversion-pipe slots even when predicated off).
-template <typename F, bool NITER1, int BY, bool VF32, bool BATCH = false>
-__global__ void __launch_bounds__(SL_BX *BY)
-sl_multistep_kernel(const __grid_constant__ SLParams p) {
-    const int x = blockIdx.x * SL_BX + threadIdx.x;
-    const int yl = blockIdx.y * BY + threadIdx.y;  // row inside the band
-    if (x >= p.n || yl >= p.rows) return;
+// One pixel's whole trajectory (all T leadtimes of the launch).  PT: storage type of the
+// precipitation field (float64 in the trajectory kernel; the input type when this runs as the exact
+// fallback of the float32-tap kernel below).
+template <typename F, bool NITER1, bool VF32, bool BATCH, typename PT>
+__device__ __forceinline__ void sl_pixel(const SLParams &p, const int x, const int yl, const size_t z) {
     const int y = p.row0 + yl;
     const int m = p.m, n = p.n;
     const int ymax = m - 2, xmax = n - 2;  // largest interior floor index (negative: none)
@@ -215,9 +216,8 @@ sl_multistep_kernel(const __grid_constant__ SLParams p) {
     const size_t NF = (size_t)m * n;       // plane stride of the full-frame arrays
     const int idx = yl * n + x;            // pixel index inside the band
     const int gidx = y * n + x;            // pixel index inside the full frame
-    const size_t z = BATCH ? blockIdx.z : 0;  // member of a batched launch
     const double2 *__restrict__ Vi = (const double2 *)p.Vi + (BATCH ? z * p.zs_vi : 0);
-    const double *__restrict__ P = (const double *)p.precip + (BATCH ? z * p.zs_precip : 0);
+    const PT *__restrict__ P = (const PT *)p.precip + (BATCH ? z * p.zs_precip : 0);
     F *__restrict__ out = (F *)p.out + (BATCH ? z * p.zs_out : 0) + idx;
     const double *__restrict__ disp_in = p.disp_in + (BATCH ? z * p.zs_disp : 0);
     double *__restrict__ disp_out = p.disp_out ? p.disp_out + (BATCH ? z * p.zs_disp : 0) : nullptr;
@@ -284,9 +284,9 @@ sl_multistep_kernel(const __grid_constant__ SLParams p) {
             if (!have_foot) f = footprint(cy, cx, n, ymax, xmax);
             double v;
             if (f.interior) {
-                const double *q = P + f.base;
-                v = bilin(__ldg(q), __ldg(q + 1), __ldg(q + n), __ldg(q + n + 1), f.wy0, f.wy1,
-                                  f.wx0, f.wx1);
+                const PT *q = P + f.base;
+                v = bilin((double)__ldg(q), (double)__ldg(q + 1), (double)__ldg(q + n), (double)__ldg(q + n + 1),
+                          f.wy0, f.wy1, f.wx0, f.wx1);
             } else {
                 v = slow_precip(P, m, n, cy, cx, mode, cval);
             }
@@ -301,6 +301,180 @@ sl_multistep_kernel(const __grid_constant__ SLParams p) {
         p.vinc_out[idx] = ux;
         p.vinc_out[N + idx] = uy;
     }
+}
+
+template <typename F, bool NITER1, int BY, bool VF32, bool BATCH = false>
+__global__ void __launch_bounds__(SL_BX *BY)
+sl_multistep_kernel(const __grid_constant__ SLParams p) {
+    const int x = blockIdx.x * SL_BX + threadIdx.x;
+    const int yl = blockIdx.y * BY + threadIdx.y;  // row inside the band
+    if (x >= p.n || yl >= p.rows) return;
+    sl_pixel<F, NITER1, VF32, BATCH, double>(p, x, yl, BATCH ? blockIdx.z : 0);  // z: member of a batched launch
+}
+
+// ---- float32-tap variant (opt-in: tolerance on the VALUES, certified INDICES) ----------------------
+// The trajectory stays in float64 (displacement, coordinates, floor, fractional weights), but the
+// fields are sampled from float32 copies with float32 arithmetic: 8 instead of 16 bytes per velocity
+// tap and ~20 instead of ~94 FP64-pipe instructions per pixel and leadtime.  What keeps the integer tap
+// indices identical to the exact kernel's is a running error bound per pixel:
+//   E   >= |displacement here - displacement of the exact kernel|  (max norm, pixels)
+//   Eu  >= |velocity increment here - exact increment|
+// A sample at coordinates c is CERTIFIED when its four taps are inside the array and the fractional
+// parts lie in (e, 1 - e) for the bound e on |c - c_exact|: then both kernels floor to the same cell,
+// and inside a cell the bilinear interpolant is Lipschitz with the slopes G read off the four taps, so
+//   Eu' <= |scale| * (G * e + eps32 * (4.5 |v| + 4 G)),   eps32 = 2^-23, v the sampled velocity
+// (with u = 2^-24 and every tap within G of v: tap rounding u(|v|+G); the two weights G u/2; the three
+// lerps 3u(|v|+G) + 4u G inherited through the differences; the final rounding u|v|; the scale factor and
+// its product 2u|v|; a float32 velocity's increment rounded by the reference, u|v|: u(8|v| + 7.5 G) in all).
+// A pixel with ANY uncertified sample -- near a cell boundary (~1e-4 of the pixels at 12 leadtimes),
+// near the array border, outside it, non-finite -- is recomputed from the start by sl_pixel, the exact
+// kernel's own code, so every mode / outval / NaN rule holds unchanged.  Net contract: floor indices of
+// every sample equal to the exact kernel's; values within float32 rounding of it (tests/test_sl_gpu.py
+// states the tolerance).
+struct SLFastParams {
+    const float2 *Vf;   // (m,n) float32 (vx,vy)
+    const void *Pf;     // (m,n) precipitation in its input type F
+    float scale[SL_MAX_T];
+    float s0;           // tdiff[0] / vel_timestep
+    unsigned *nlist;    // number of listed pixels (zeroed before the launch)
+    int *list;          // band-local pixel indices to recompute exactly (capacity: the band)
+};
+
+constexpr float SLF_EPS = 1.1920929e-07f;  // 2^-23
+constexpr float SLF_INFLATE = 1.001f;      // slack for the float32 evaluation of the bound itself
+
+struct FootF {
+    int base;
+    float tx, ty;
+    bool ok;  // interior and certified
+};
+
+// one velocity sample of the float32 path at (cy, cx) with position error bound e;
+// returns the sampled velocity (vx, vy) and the bound g >= (Gx + Gy) slope + the rounding term's factor
+__device__ __forceinline__ FootF sample_f32(const float2 *__restrict__ Vf, int n, int ymax, int xmax, double cy,
+                                            double cx, float e, float &vx, float &vy, float &err_coef) {
+    FootF f;
+    const double sy = __dadd_rd(cy, SL_MAGIC), sx = __dadd_rd(cx, SL_MAGIC);
+    const int iy = __double2loint(sy), ix = __double2loint(sx);
+    // (unsigned compares: a negative index is a huge unsigned; ymax / xmax < 0 -- no interior -- fail them all)
+    const bool interior = (__double2hiint(sy) == 0x43380000) & (__double2hiint(sx) == 0x43380000) &
+                          ((unsigned)iy <= (unsigned)ymax) & ((unsigned)ix <= (unsigned)xmax) & (ymax >= 0) & (xmax >= 0);
+    f.ty = (float)__dsub_rn(cy, __dsub_rn(sy, SL_MAGIC));
+    f.tx = (float)__dsub_rn(cx, __dsub_rn(sx, SL_MAGIC));
+    // both fractions in (lo, 1 - lo) with lo = e + 2 eps  <=>  max |t - 1/2| < 1/2 - lo
+    f.ok = interior & (fmaxf(fabsf(f.ty - 0.5f), fabsf(f.tx - 0.5f)) < 0.5f - (e + 2.f * SLF_EPS));
+    f.base = iy * n + ix;
+    if (f.ok) {
+        const float2 *q = Vf + f.base;
+        const float2 a00 = __ldg(q), a01 = __ldg(q + 1), a10 = __ldg(q + n), a11 = __ldg(q + n + 1);
+        const float d0x = a01.x - a00.x, d1x = a11.x - a10.x, d0y = a01.y - a00.y, d1y = a11.y - a10.y;
+        const float x0 = __fmaf_rn(f.tx, d0x, a00.x), x1 = __fmaf_rn(f.tx, d1x, a10.x);
+        const float y0 = __fmaf_rn(f.tx, d0y, a00.y), y1 = __fmaf_rn(f.tx, d1y, a10.y);
+        const float wx = x1 - x0, wy = y1 - y0;
+        vx = __fmaf_rn(f.ty, wx, x0);
+        vy = __fmaf_rn(f.ty, wy, y0);
+        // slopes inside the cell: |d/dx| <= max(|d0|,|d1|) <= |d0|+|d1| =: D ; |d/dy| <= |w| + D
+        const float gx = __fmaf_rn(2.f, fabsf(d0x) + fabsf(d1x), fabsf(wx));
+        const float gy = __fmaf_rn(2.f, fabsf(d0y) + fabsf(d1y), fabsf(wy));
+        const float g = fmaxf(gx, gy);
+        const float av = fmaxf(fabsf(vx), fabsf(vy));
+        err_coef = __fmaf_rn(g, e, SLF_EPS * __fmaf_rn(4.f, g, 4.5f * av));
+    }
+    return f;
+}
+
+// n_iter == 1, pixel-grid coordinates, a precipitation field, T <= SL_MAX_T (one launch).
+// Pixels with an uncertified sample stop at once and are LISTED (one atomic per warp); the exact code
+// runs on the compacted list in a second launch -- done inline, every warp holding a single such pixel
+// (most warps, at a few percent of the pixels) would pay for the exact trajectory on top of the fast one.
+template <typename F, bool VF32>
+__global__ void __launch_bounds__(SL_BX *SL_BY)
+sl_f32_kernel(const __grid_constant__ SLParams p, const __grid_constant__ SLFastParams q) {
+    const int x = blockIdx.x * SL_BX + threadIdx.x;
+    const int yl = blockIdx.y * SL_BY + threadIdx.y;
+    const bool inb = x < p.n && yl < p.rows;
+    const int n = p.n;
+    const int idx = yl * n + x;
+    bool good = true;
+    if (inb) {
+        const int y = p.row0 + yl;
+        const int ymax = p.m - 2, xmax = n - 2;
+        const size_t N = (size_t)p.rows * n;
+        const int gidx = y * n + x;
+        const float2 *__restrict__ Vf = q.Vf;
+        const F *__restrict__ Pf = (const F *)q.Pf;
+        F *__restrict__ out = (F *)p.out + idx;
+        const double gx = (double)x, gy = (double)y;
+        const int T = p.T;
+        double dx, dy;
+        float ux, uy, E = 0.f, Eu;
+        if (p.init_mode == SL_INIT_FRESH) {
+            dx = 0.0; dy = 0.0;
+            const float2 v = Vf[gidx];
+            ux = v.x * q.s0; uy = v.y * q.s0;
+            Eu = 2.f * SLF_EPS * fmaxf(fabsf(ux), fabsf(uy));  // V -> float32, the scale factor, the product: 3 * 2^-24
+        } else {  // SL_INIT_PREV
+            dx = p.disp_in[idx]; dy = p.disp_in[N + idx];
+            float vx = 0.f, vy = 0.f, ec = 0.f;
+            const FootF f = sample_f32(Vf, n, ymax, xmax, __dadd_rn(gy, dy), __dadd_rn(gx, dx), 0.f, vx, vy, ec);
+            good = f.ok;
+            const float sf = q.scale[0];
+            ux = vx * sf; uy = vy * sf;
+            Eu = fabsf(sf) * ec * SLF_INFLATE;
+        }
+        for (int ti = 0; ti < T && good; ti++) {
+            const float sf = q.scale[ti], sa = fabsf(sf) * SLF_INFLATE;
+            float vx = 0.f, vy = 0.f, ec = 0.f;
+            // midpoint sample at displacement - increment / 2
+            const double hx = __fma_rn(-0.5, (double)ux, dx), hy = __fma_rn(-0.5, (double)uy, dy);
+            FootF f = sample_f32(Vf, n, ymax, xmax, __dadd_rn(gy, hy), __dadd_rn(gx, hx), __fmaf_rn(0.5f, Eu, E), vx, vy, ec);
+            good = f.ok;
+            ux = vx * sf; uy = vy * sf;
+            dx = __dsub_rn(dx, (double)ux);
+            dy = __dsub_rn(dy, (double)uy);
+            E = (E + sa * ec) * SLF_INFLATE + 1e-12f;
+            // end-point sample: the next increment, and the footprint of the precipitation warp
+            f = sample_f32(Vf, n, ymax, xmax, __dadd_rn(gy, dy), __dadd_rn(gx, dx), E, vx, vy, ec);
+            good &= f.ok;
+            ux = vx * sf; uy = vy * sf;
+            Eu = sa * ec;
+            if (good) {
+                const F *r = Pf + f.base;
+                const float a00 = (float)__ldg(r), a01 = (float)__ldg(r + 1), a10 = (float)__ldg(r + n),
+                            a11 = (float)__ldg(r + n + 1);
+                const float v0 = __fmaf_rn(f.tx, a01 - a00, a00), v1 = __fmaf_rn(f.tx, a11 - a10, a10);
+                out[(size_t)ti * N] = (F)__fmaf_rn(f.ty, v1 - v0, v0);
+            }
+        }
+        if (good && p.disp_out) {
+            p.disp_out[idx] = dx;
+            p.disp_out[N + idx] = dy;
+        }
+    }
+    // list the pixels to recompute: one atomic per warp
+    const unsigned bad = __ballot_sync(0xffffffffu, !good);
+    if (bad) {
+        const int lane = (threadIdx.y * SL_BX + threadIdx.x) & 31;
+        unsigned base = 0;
+        if (lane == __ffs(bad) - 1) base = atomicAdd(q.nlist, __popc(bad));
+        base = __shfl_sync(0xffffffffu, base, __ffs(bad) - 1);
+        if (!good) q.list[base + __popc(bad & ((1u << lane) - 1u))] = idx;
+    }
+}
+
+// the listed pixels, by the exact kernel's own code (rewrites every leadtime and the displacement)
+template <typename F, bool VF32>
+__global__ void __launch_bounds__(128)
+sl_f32_fixup_kernel(const __grid_constant__ SLParams p, const unsigned *__restrict__ nlist,
+                    const int *__restrict__ list, unsigned long long *nfallback) {
+    const unsigned cnt = *nlist;
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += stride) {
+        const int idx = list[i];
+        const int yl = idx / p.n;
+        sl_pixel<F, true, VF32, false, F>(p, idx - yl * p.n, yl, 0);
+    }
+    if (nfallback && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(nfallback, (unsigned long long)cnt);
 }
 
 // (2,m,n) planar or (m,n,2) interleaved velocity of dtype F -> (m,n) double2
@@ -413,6 +587,90 @@ int sl_run(const void *precip, const void *velocity, const double *xy, const dou
     return 0;
 }
 
+// (2,m,n) planar or (m,n,2) interleaved velocity of dtype F -> (m,n) float2 (rounded to nearest)
+template <typename F>
+__global__ void __launch_bounds__(256)
+narrow_velocity_kernel(const F *__restrict__ V, float2 *__restrict__ Vf, size_t N, int interleaved) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+        float2 v;
+        if (interleaved) {
+            v.x = (float)__ldg(V + 2 * i);
+            v.y = (float)__ldg(V + 2 * i + 1);
+        } else {
+            v.x = (float)__ldg(V + i);
+            v.y = (float)__ldg(V + N + i);
+        }
+        Vf[i] = v;
+    }
+}
+
+// the float32-tap kernel with its exact fallback; restrictions checked by the caller
+template <typename FV, typename F>
+int sl_run_f32(const void *precip, const void *velocity, const double *disp_prev, const double *tdiff, int T,
+               double vts, double outval, int mode, int layout, int m, int n, int row0, int rows, void *out,
+               double *disp_out, unsigned long long *nfallback, cudaStream_t stream) {
+    const size_t N = (size_t)m * n;
+    b200::Scratch vi, vf;
+    const int sblocks = (int)std::min<size_t>((N + 255) / 256, (size_t)b200::num_sms() * 16);
+    const void *vi_ptr = velocity;  // exact float64 pairs, for the pixels that fall back
+    if (!(sizeof(FV) == 8 && layout == B200_LAYOUT_INTERLEAVED)) {
+        B200_CUDA(vi.alloc(N * sizeof(double2), stream));
+        vi_ptr = vi.p;
+        widen_velocity_kernel<FV><<<sblocks, 256, 0, stream>>>((const FV *)velocity, (double2 *)vi.p, N,
+                                                               layout == B200_LAYOUT_INTERLEAVED);
+        B200_LAUNCH_CHECK();
+    }
+    const void *vf_ptr = velocity;
+    if (!(sizeof(FV) == 4 && layout == B200_LAYOUT_INTERLEAVED)) {
+        B200_CUDA(vf.alloc(N * sizeof(float2), stream));
+        vf_ptr = vf.p;
+        narrow_velocity_kernel<FV><<<sblocks, 256, 0, stream>>>((const FV *)velocity, (float2 *)vf.p, N,
+                                                                layout == B200_LAYOUT_INTERLEAVED);
+        B200_LAUNCH_CHECK();
+    }
+    SLParams p;
+    memset(&p, 0, sizeof(p));
+    p.Vi = vi_ptr;
+    p.precip = precip;  // in its input type: sl_pixel<..., PT = F>
+    p.m = m; p.n = n;
+    p.row0 = row0; p.rows = rows;
+    p.n_iter = 1;
+    p.mode = mode;
+    p.vts = vts;
+    p.td0 = tdiff[0];
+    p.cval = outval;
+    p.has_prev = disp_prev != nullptr;
+    p.vel_f32 = sizeof(FV) == 4;
+    p.T = T;
+    SLFastParams q;
+    memset(&q, 0, sizeof(q));
+    for (int i = 0; i < T; i++) {
+        p.scale[i] = tdiff[i] / vts;
+        q.scale[i] = (float)p.scale[i];
+    }
+    q.s0 = (float)(tdiff[0] / vts);
+    q.Vf = (const float2 *)vf_ptr;
+    q.Pf = precip;
+    p.init_mode = disp_prev ? SL_INIT_PREV : SL_INIT_FRESH;
+    p.disp_in = disp_prev;
+    p.disp_out = disp_out;
+    p.out = out;
+    dim3 block(SL_BX, SL_BY);
+    dim3 grid(b200::ceil_div(n, SL_BX), b200::ceil_div(rows, SL_BY));
+    b200::Scratch lst;
+    const size_t NB = (size_t)rows * n;
+    B200_CUDA(lst.alloc(sizeof(int) * (NB + 4), stream));
+    q.nlist = (unsigned *)lst.p;
+    q.list = (int *)lst.p + 4;
+    B200_CUDA(cudaMemsetAsync(q.nlist, 0, sizeof(unsigned), stream));
+    sl_f32_kernel<F, sizeof(FV) == 4><<<grid, block, 0, stream>>>(p, q);
+    B200_LAUNCH_CHECK();
+    sl_f32_fixup_kernel<F, sizeof(FV) == 4><<<b200::num_sms() * 8, 128, 0, stream>>>(p, q.nlist, q.list, nfallback);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
 // Displacement field after EVERY leadtime (for samplers other than the built-in order-1 warp):
 // the trajectory kernel run one leadtime per launch through the same resume mechanism that
 // chunks long sequences, so the arithmetic is that of the fused loop.
@@ -514,6 +772,39 @@ extern "C" int b200_sl_extrapolate_rows(const void *precip, const void *velocity
 #define SL_DISPATCH(FV, FP)                                                                  \
     return sl_run<FV, FP>(precip, velocity, xy_coords, disp_prev, tdiff, T, vel_timestep, n_iter, \
                           outval, mode, velocity_layout, m, n, row_begin, row_count, out, disp_out, s)
+    if (velocity_dtype == B200_F32 && precip_dtype == B200_F32) SL_DISPATCH(float, float);
+    if (velocity_dtype == B200_F32 && precip_dtype == B200_F64) SL_DISPATCH(float, double);
+    if (velocity_dtype == B200_F64 && precip_dtype == B200_F32) SL_DISPATCH(double, float);
+    if (velocity_dtype == B200_F64 && precip_dtype == B200_F64) SL_DISPATCH(double, double);
+#undef SL_DISPATCH
+    b200::set_error("unknown field dtypes %d / %d", velocity_dtype, precip_dtype);
+    return B200_EINVAL;
+}
+
+// Opt-in float32-tap variant of b200_sl_extrapolate_rows (see sl_f32_kernel): n_iter = 1, pixel-grid
+// coordinates, a precipitation field, at most 32 timesteps.  Tap indices are certified equal to the
+// exact kernel's (uncertified pixels are recomputed by the exact code); values carry float32 rounding.
+// `fallback_count` (device, optional, NOT reset here) receives the number of recomputed pixels.
+extern "C" int b200_sl_extrapolate_rows_f32(const void *precip, const void *velocity, const double *disp_prev,
+                                            const double *tdiff, int T, double vel_timestep, double outval,
+                                            int mode, int velocity_dtype, int velocity_layout, int precip_dtype,
+                                            int m, int n, int row_begin, int row_count, void *out,
+                                            double *disp_out, unsigned long long *fallback_count, void *stream) {
+    B200_REQUIRE(row_begin >= 0 && row_count >= 1 && row_begin + row_count <= m, "row band out of range");
+    B200_REQUIRE(velocity_layout == B200_LAYOUT_PLANAR || velocity_layout == B200_LAYOUT_INTERLEAVED,
+                 "unknown velocity layout");
+    B200_REQUIRE(velocity != nullptr && precip != nullptr && out != nullptr, "precip, velocity and out are required");
+    B200_REQUIRE(tdiff != nullptr && T >= 1, "need at least one timestep");
+    B200_REQUIRE(m >= 1 && n >= 1 && (int64_t)m * n < ((int64_t)1 << 30), "grid must have 1 .. 2^30 pixels");
+    B200_REQUIRE(mode == B200_MODE_CONSTANT || mode == B200_MODE_NEAREST, "unsupported mode");
+    if (T > SL_MAX_T) {
+        b200::set_error("the float32-tap kernel takes at most %d timesteps per call", SL_MAX_T);
+        return B200_ENOTSUP;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+#define SL_DISPATCH(FV, FP)                                                                            \
+    return sl_run_f32<FV, FP>(precip, velocity, disp_prev, tdiff, T, vel_timestep, outval, mode, velocity_layout, \
+                              m, n, row_begin, row_count, out, disp_out, fallback_count, s)
     if (velocity_dtype == B200_F32 && precip_dtype == B200_F32) SL_DISPATCH(float, float);
     if (velocity_dtype == B200_F32 && precip_dtype == B200_F64) SL_DISPATCH(float, double);
     if (velocity_dtype == B200_F64 && precip_dtype == B200_F32) SL_DISPATCH(double, float);

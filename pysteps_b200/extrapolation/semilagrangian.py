@@ -220,6 +220,9 @@ def _extrapolate_checked(precip, velocity, d_precip, d_vel, stats, on_device, ti
     # [r0, r1) -- results and displacement arrays are then band shaped (tile partitioning of
     # one composite over GPUs; inputs stay full frames)
     rows = kwargs.get("b200_rows", None)
+    # extension: sample the fields from float32 copies (values within float32 rounding of the exact
+    # path, tap indices certified identical); off by default
+    f32_taps = bool(kwargs.get("b200_float32_taps", False))
 
     if precip is None and not return_displacement:
         raise ValueError("precip is None but return_displacement is False")
@@ -302,7 +305,20 @@ def _extrapolate_checked(precip, velocity, d_precip, d_vel, stats, on_device, ti
         _lib.call("b200_sl_interleave_velocity", d_vel.data_ptr(), _device.dtype_code(d_vel.dtype),
                   m, n, d_v.data_ptr(), _device.stream_ptr())
         layout = _lib.LAYOUT_INTERLEAVED
-    if d_precip is None or interp_order == 1:
+    if f32_taps:
+        # opt-in: float32 taps, tap indices certified equal to the exact kernel's (csrc/sl.cu sl_f32_kernel)
+        if d_precip is None or interp_order != 1 or n_iter != 1 or d_xy is not None or T > 32:
+            raise NotImplementedError(
+                "pysteps_b200 semilagrangian: b200_float32_taps needs a precipitation field, interp_order=1, "
+                "n_iter=1, the default pixel grid and at most 32 timesteps")
+        cnt = kwargs.get("b200_fallback_count", None)  # optional uint64 device tensor, accumulates
+        _lib.call("b200_sl_extrapolate_rows_f32",
+                  d_precip.data_ptr(), d_v.data_ptr(), _device.ptr(d_prev),
+                  timestep_diff.ctypes.data_as(_lib.c_dp), T, float(vel_timestep), float(outval),
+                  _MODES[map_coordinates_mode], _device.dtype_code(d_vel.dtype), layout,
+                  _device.dtype_code(d_precip.dtype), m, n, r0, mb, d_out.data_ptr(), _device.ptr(d_disp),
+                  _device.ptr(cnt), _device.stream_ptr())
+    elif d_precip is None or interp_order == 1:
         _lib.call("b200_sl_extrapolate_rows",
                   _device.ptr(d_precip), d_v.data_ptr(), _device.ptr(d_xy), _device.ptr(d_prev),
                   timestep_diff.ctypes.data_as(_lib.c_dp), T, float(vel_timestep),

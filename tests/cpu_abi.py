@@ -51,6 +51,13 @@ def _field_stats(ptr, code, numel, out, stream):
     o[3] = float(np.count_nonzero(np.isnan(a)))
 
 
+def _sl_rows_f32(precip, velocity, disp_prev, tdiff, T, vts, outval, mode, vdt, layout, pdt, m, n, r0, rows, out,
+                 disp_out, fallback_count, stream):
+    """the float32-tap entry: the emulation runs the exact loop (inside the documented tolerance)"""
+    _sl_rows(precip, velocity, None, disp_prev, tdiff, T, vts, 1, outval, mode, vdt, layout, pdt, m, n, r0, rows,
+             out, disp_out, stream)
+
+
 def _sl_rows(precip, velocity, xy, disp_prev, tdiff, T, vts, n_iter, outval, mode, vdt, layout, pdt,
              m, n, r0, rows, out, disp_out, stream):
     vt, pt = _NP[vdt], _NP[pdt]
@@ -453,7 +460,7 @@ _TABLE = {"b200_vet_cost": _vet_cost, "b200_vet_value_and_gradient": _vet_value_
           "b200_vet_level_images": _vet_level_images, "b200_vet_warp": _vet_warp, "b200_zoom_bilinear": _zoom,
           "b200_gaussian_filter": _gaussian_filter, "b200_proesmans_scale": _proesmans_scale, "b200_proesmans_field": _proesmans_field,
           "b200_sl_trajectories": _sl_trajectories, "b200_spline_prepare": _spline_prepare,
-          "b200_spline_sample": _spline_sample, "b200_field_stats": _field_stats, "b200_sl_extrapolate_rows": _sl_rows,
+          "b200_spline_sample": _spline_sample, "b200_field_stats": _field_stats, "b200_sl_extrapolate_rows": _sl_rows, "b200_sl_extrapolate_rows_f32": _sl_rows_f32,
           "b200_bps_perturb_velocity": _bps, "b200_sl_step_batched": _sl_step_batched}
 
 

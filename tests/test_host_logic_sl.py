@@ -241,3 +241,39 @@ def test_extrapolate_members_equals_member_by_member_calls():
             with pytest.raises(TypeError):
                 extrapolate_members(P[:1], [V])
         _ = rng
+
+
+def test_float32_taps_host_logic():
+    """b200_float32_taps: routed to its own C entry (emulated here by the exact loop), same return
+    structure / dtypes / band shapes as the default path, and refused -- not silently recomputed some
+    other way -- for what the variant does not cover."""
+    from pysteps_b200.extrapolation.semilagrangian import extrapolate
+    with cpu_abi.emulated():
+        m, n = 30, 41
+        V = 2.0 * syn.velocity_field(m, n, 3)
+        for dtype in (np.float64, np.float32):
+            P = syn.rain_field(m, n, 3).astype(dtype)
+            want, dwant = extrapolate(P, V, 4, return_displacement=True)
+            got, dgot = extrapolate(P, V, 4, return_displacement=True, b200_float32_taps=True)
+            assert got.dtype == dtype and _bits_equal(got, want) and _bits_equal(dgot, dwant)
+            band = extrapolate(P, V, 4, b200_float32_taps=True, b200_rows=(7, 19))
+            assert _bits_equal(band, want[:, 7:19])
+            o, d = extrapolate(P, V, [1.0], displacement_prev=dwant, return_displacement=True, b200_float32_taps=True)
+            o2, d2 = extrapolate(P, V, [1.0], displacement_prev=dwant, return_displacement=True)
+            assert _bits_equal(o, o2) and _bits_equal(d, d2)
+        P = syn.rain_field(m, n, 3)
+        x, y = np.meshgrid(np.arange(n, dtype=float), np.arange(m, dtype=float))
+        # the default pixel grid given explicitly is still the default grid
+        assert _bits_equal(extrapolate(P, V, 2, xy_coords=np.stack([x, y]), b200_float32_taps=True),
+                           extrapolate(P, V, 2))
+        for bad in (dict(n_iter=2), dict(n_iter=0), dict(interp_order=0), dict(interp_order=3),
+                    dict(xy_coords=np.stack([x + 0.25, y]))):
+            with pytest.raises(NotImplementedError, match="b200_float32_taps"):
+                extrapolate(P, V, 2, b200_float32_taps=True, **bad)
+        with pytest.raises(NotImplementedError, match="b200_float32_taps"):
+            extrapolate(None, V, 2, return_displacement=True, b200_float32_taps=True)
+        with pytest.raises(NotImplementedError, match="b200_float32_taps"):
+            extrapolate(P, V, 40, b200_float32_taps=True)
+        # the reference's own errors keep their precedence
+        with pytest.raises(ValueError):
+            extrapolate(P[0], V, 2, b200_float32_taps=True)

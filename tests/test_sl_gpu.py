@@ -287,3 +287,107 @@ def test_randomised_differential_vs_oracle(sl):
         got = sl.extrapolate(P, V, ts, outval, **kw)
         want = ora.extrapolate(P, V, ts, outval, **kw)
         _compare(got, want, f"trial {trial}: {(m, n)} {pdt.__name__}/{vdt.__name__} ts={ts} {sorted(kw)}")
+
+
+# ---------------------------------------------------------------------------------------------
+# opt-in float32-tap kernel (b200_float32_taps=True): tolerance on values, certified tap indices
+F32_VALUE_TOL = 2e-5     # |out - exact| <= F32_VALUE_TOL * max|precip| (finite pixels)
+F32_DISP_TOL = 1e-4      # |displacement - exact| in pixels (measured: 2e-6 smooth field, 3e-5 at |V| ~ 50 px/step)
+
+
+@pytest.mark.parametrize("kind,scale,pdtype", [("smooth", 1.0, np.float32), ("rotation", 4.0, np.float64),
+                                               ("smooth", 0.0, np.float32), ("rotation", 12.0, np.float32)])
+def test_float32_taps_indices_and_tolerance(sl, kind, scale, pdtype):
+    """Every leadtime's end-point coordinates floor to the SAME tap indices as the exact kernel (the
+    displacement after k leadtimes is the k-th end-point sample), values and displacements inside the
+    stated float32 tolerance, NaN pattern identical."""
+    import torch
+    from pysteps_b200 import _synthetic as syn
+    m, n = 384, 448
+    P = syn.rain_field(m, n, 3).astype(pdtype)
+    V = syn.velocity_field(m, n, 3, kind) * scale
+    yy, xx = np.meshgrid(np.arange(m, dtype=np.float64), np.arange(n, dtype=np.float64), indexing="ij")
+    pmax = float(np.abs(P).max())
+    for T in (1, 2, 5, 12):
+        exact, dex = sl.extrapolate(P, V, T, return_displacement=True)
+        cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+        fast, dfa = sl.extrapolate(P, V, T, return_displacement=True, b200_float32_taps=True,
+                                   b200_fallback_count=cnt)
+        assert fast.dtype == exact.dtype and fast.shape == exact.shape
+        assert np.array_equal(np.isnan(fast), np.isnan(exact)), "NaN pattern"
+        ok = ~np.isnan(exact)
+        err = np.abs(fast[ok].astype(np.float64) - exact[ok].astype(np.float64)).max() if ok.any() else 0.0
+        assert err <= F32_VALUE_TOL * pmax, f"T={T}: value error {err:.3e} (max|P| {pmax:.3g})"
+        assert np.abs(dfa - dex).max() <= F32_DISP_TOL, f"T={T}: displacement error {np.abs(dfa - dex).max():.3e}"
+        # integer tap indices of the last end-point sample: identical at EVERY pixel
+        assert np.array_equal(np.floor(xx + dfa[0]), np.floor(xx + dex[0])), f"T={T}: column indices"
+        assert np.array_equal(np.floor(yy + dfa[1]), np.floor(yy + dex[1])), f"T={T}: row indices"
+        frac = int(cnt.item()) / (m * n)
+        if scale > 0 and kind == "smooth":
+            assert frac < 0.2, f"T={T}: {frac:.3f} of the pixels fell back to the exact code"
+    # zero motion: every sample sits ON a cell boundary -> all pixels take the exact path -> identity
+    if scale == 0.0:
+        assert_bits_equal(fast, exact, "zero motion")
+
+
+def test_float32_taps_modes_nonfinite_bands_and_carry(sl):
+    """mode / outval / NaN rules are the exact kernel's (uncertified pixels ARE the exact kernel); the
+    STEPS call shape (single steps with carried displacement) and row bands work as in the exact path."""
+    from pysteps_b200 import _shard, _synthetic as syn
+    m, n = 200, 240
+    P = syn.nan_disc(syn.rain_field(m, n, 4))
+    V = syn.velocity_field(m, n, 4, "rotation") * 5.0
+    pmax = float(np.nanmax(np.abs(P)))
+    for kw in (dict(allow_nonfinite_values=True), dict(allow_nonfinite_values=True, outval=0.0),
+               dict(allow_nonfinite_values=True, map_coordinates_mode="nearest")):
+        exact, dex = sl.extrapolate(P, V, 6, return_displacement=True, **kw)
+        fast, dfa = sl.extrapolate(P, V, 6, return_displacement=True, b200_float32_taps=True, **kw)
+        assert np.array_equal(np.isnan(fast), np.isnan(exact)), f"NaN pattern {kw}"
+        ok = ~np.isnan(exact)
+        assert np.abs(fast[ok] - exact[ok]).max() <= F32_VALUE_TOL * pmax
+        assert np.abs(dfa - dex).max() <= F32_DISP_TOL
+    # carried single steps
+    kw = dict(allow_nonfinite_values=True, return_displacement=True)
+    full, dfull = sl.extrapolate(P, V, 4, **kw)
+    d = None
+    for t in range(4):
+        o, d = sl.extrapolate(P, V, [1.0], displacement_prev=d, b200_float32_taps=True, **kw)
+        ok = ~np.isnan(full[t])
+        assert np.array_equal(np.isnan(o[0]), np.isnan(full[t]))
+        assert np.abs(o[0][ok] - full[t][ok]).max() <= F32_VALUE_TOL * pmax
+    assert np.abs(d - dfull).max() <= F32_DISP_TOL
+    # a band alone == the rows of the full float32-tap frame, bitwise (same kernel, same pixels)
+    fast, dfa = sl.extrapolate(P, V, 3, b200_float32_taps=True, **kw)
+    r0, r1 = _shard.row_band(m, 3, 1)
+    band, dband = sl.extrapolate(P, V, 3, b200_float32_taps=True, b200_rows=(r0, r1), **kw)
+    assert_bits_equal(band, fast[:, r0:r1], "band")
+    assert_bits_equal(dband, dfa[:, r0:r1], "band displacement")
+    # what the variant does not cover is refused, not silently computed otherwise
+    with pytest.raises(NotImplementedError):
+        sl.extrapolate(P, V, 2, allow_nonfinite_values=True, b200_float32_taps=True, n_iter=3)
+    with pytest.raises(NotImplementedError):
+        sl.extrapolate(P, V, 2, allow_nonfinite_values=True, b200_float32_taps=True, interp_order=3)
+
+
+def test_float32_taps_full_size(sl):
+    """BASELINE size: tolerance, indices and the share of recomputed pixels on the LK-like smooth field."""
+    import torch
+    from pysteps_b200 import _synthetic as syn
+    m = n = 2048
+    P = torch.from_numpy(syn.rain_field(m, n, 0).astype(np.float32)).cuda()
+    V = torch.from_numpy(syn.velocity_field(m, n, 0, "smooth")).cuda()
+    exact, dex = sl.extrapolate(P, V, 12, return_displacement=True)
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    fast, dfa = sl.extrapolate(P, V, 12, return_displacement=True, b200_float32_taps=True, b200_fallback_count=cnt)
+    assert torch.equal(torch.isnan(fast), torch.isnan(exact))
+    err = torch.nan_to_num((fast.double() - exact.double()).abs(), nan=0.0).max().item()
+    assert err <= F32_VALUE_TOL * float(P.abs().max()), f"value error {err:.3e}"
+    assert (dfa - dex).abs().max().item() <= F32_DISP_TOL
+    gy, gx = torch.meshgrid(torch.arange(m, device="cuda", dtype=torch.float64),
+                            torch.arange(n, device="cuda", dtype=torch.float64), indexing="ij")
+    assert torch.equal(torch.floor(gx + dfa[0]), torch.floor(gx + dex[0]))
+    assert torch.equal(torch.floor(gy + dfa[1]), torch.floor(gy + dex[1]))
+    frac = cnt.item() / (m * n)
+    print(f"float32 taps 2048^2 T=12: max value error {err:.3e}, max displacement error "
+          f"{(dfa - dex).abs().max().item():.3e}, {100 * frac:.3f} % of the pixels recomputed exactly")
+    assert frac < 0.05

@@ -1,0 +1,5 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_sl_gpu.py -m gpu -x -q -s 2>&1 | tail -12 | tee gpurun_out/r2c23_tests.log
+timeout 600 python tools/sl_f32_timing.py > gpurun_out/r2c23_sl_f32.json 2> gpurun_out/r2c23_sl_f32.err; cat gpurun_out/r2c23_sl_f32.json; tail -3 gpurun_out/r2c23_sl_f32.err
