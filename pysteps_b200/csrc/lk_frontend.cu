@@ -121,8 +121,10 @@ struct Scale {
 };
 
 // PASS = 1: statistics of the opened image.  PASS = 2: uint8 images.
+// (4 CTAs per SM: the launch is 4 persistent CTAs per SM, all of which must be resident -- at 76
+// registers only 3 were, and the 4th ran as a second wave)
 template <int PASS>
-__global__ void __launch_bounds__(FTHREADS)
+__global__ void __launch_bounds__(FTHREADS, 4)
 front_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FrontParams p) {
     __shared__ __align__(128) double s_img[2][BH * BW];
     __shared__ unsigned s_fg[BH][4], s_nz[BH][4], s_mk[BH][4];

@@ -86,6 +86,12 @@ __global__ void __launch_bounds__(LK_THREADS) lk_track_kernel(const LKParams p) 
                 inv_ntail = ntail > 0 ? 1.0f / (float)ntail : 0.f;
     const float half_x = (ww - 1) * 0.5f, half_y = (wh - 1) * 0.5f;
     const float FLT_SCALE = 1.f / (float)(1 << 20);
+    // The ordered float32 sums are sequential chains run by ONE warp of the CTA while the others wait at
+    // the barrier.  Warps go to the SM's four schedulers by warp index, so with warp 0 doing the chains in
+    // every CTA the ~7 resident CTAs of an SM queued all their chain work on ONE scheduler (ncu: 43 % of
+    // the stall samples at the barrier after the tensor chains, issue slots 38 % busy).  The chain warp is
+    // therefore picked by CTA index: ct = this thread's lane in it, negative / >= 32 elsewhere.
+    const int ct = tid - 32 * (blockIdx.x & (LK_THREADS / 32 - 1));
     float nx_out = 0.f, ny_out = 0.f;      // nextPts[ptidx] as carried between levels
     bool status = true;
 
@@ -143,27 +149,24 @@ __global__ void __launch_bounds__(LK_THREADS) lk_track_kernel(const LKParams p) 
         __syncthreads();
 
         // ---- structure tensor: 12 lane chains + 3 tail chains, OpenCV's float32 order ------
-        if (tid < 15) {
-            const int acc = tid < 12 ? tid >> 2 : tid - 12;  // 0: A11, 1: A12, 2: A22
+        // (ct: lane of this CTA's chain warp -- see below; each chain reads only the two derivative
+        // arrays of ITS product through pointers picked once, with running indices)
+        if (ct >= 0 && ct < 15) {
+            const int acc = ct < 12 ? ct >> 2 : ct - 12;  // 0: A11 = sum Ix Ix, 1: A12 = sum Ix Iy, 2: A22 = sum Iy Iy
+            const short *pa = acc == 2 ? Dy : Dx, *pb = acc == 0 ? Dx : Dy;
             float q = 0.f;
-            if (tid < 12) {
-                const int l = tid & 3;
-                for (int y = 0; y < wh; y++)
+            if (ct < 12) {
+                const int l = ct & 3;
+                for (int y = 0; y < wh; y++) {
+                    const short *ra = pa + y * ww, *rb = pb + y * ww;
 #pragma unroll 4
-                    for (int x = l; x < simd_w; x += 4) {
-                        const float fx = (float)Dx[y * ww + x], fy = (float)Dy[y * ww + x];
-                        const float pr = acc == 0 ? fx * fx : (acc == 1 ? fx * fy : fy * fy);
-                        q = pr + q;
-                    }
+                    for (int x = l; x < simd_w; x += 4) q = __fmul_rn((float)ra[x], (float)rb[x]) + q;
+                }
             } else {
                 for (int y = 0; y < wh; y++)
-                    for (int x = simd_w; x < ww; x++) {
-                        const int gx = Dx[y * ww + x], gy = Dy[y * ww + x];
-                        const int pr = acc == 0 ? gx * gx : (acc == 1 ? gx * gy : gy * gy);
-                        q += (float)pr;
-                    }
+                    for (int x = simd_w; x < ww; x++) q += (float)((int)pa[y * ww + x] * (int)pb[y * ww + x]);
             }
-            red[tid] = q;
+            red[ct] = q;
         }
         __syncthreads();
         float A[3];
@@ -222,24 +225,24 @@ __global__ void __launch_bounds__(LK_THREADS) lk_track_kernel(const LKParams p) 
             }
             __syncthreads();
             // ---- mismatch vector: 8 lane chains over pixel pairs (q, q+4) + 2 tail chains --
-            if (tid < 10) {
+            if (ct >= 0 && ct < 10) {
                 float q = 0.f;
-                if (tid < 8) {
+                if (ct < 8) {
                     // qb0 = [x(0,4) y(0,4) x(1,5) y(1,5)], qb1 = [x(2,6) y(2,6) x(3,7) y(3,7)]
-                    const int pair = (tid >> 2) * 2 + ((tid & 3) >> 1);
-                    const float *P = (tid & 1) ? PY : PX;
+                    const int pair = (ct >> 2) * 2 + ((ct & 3) >> 1);
+                    const float *P = (ct & 1) ? PY : PX;
                     const int nsteps = wh * nchunk;
 #pragma unroll 8
                     for (int s = 0; s < nsteps; s++) q += P[4 * s + pair];
                 } else {
-                    const float *P = (tid == 9) ? TYp : TXp;
+                    const float *P = (ct == 9) ? TYp : TXp;
 #pragma unroll 4
                     for (int s = 0; s < ntl; s++) q += P[s];
                 }
-                red[tid] = q;
+                red[ct] = q;
             }
             __syncthreads();
-            if (tid == 0) {
+            if (ct == 0) {
                 // (qb0 + qb1) -> [X0 Y0 X1 Y1]; reduce_sum of [X0 X1 0 0] is (X0+0)+(X1+0)
                 const float X0 = red[0] + red[4], Y0 = red[1] + red[5];
                 const float X1 = red[2] + red[6], Y1 = red[3] + red[7];
