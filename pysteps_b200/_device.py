@@ -139,9 +139,13 @@ def _sample_fingerprint(a):
     return (a.shape, a.dtype.str, a.__array_interface__["data"][0], flat[::step].tobytes())
 
 
-def remember_result(host_array, tensor):
-    """Associate the NumPy result `host_array` with the device tensor it was copied from."""
+def remember_result(host_array, tensor, finite=False):
+    """Associate the NumPy result `host_array` with the device tensor it was copied from.
+    finite=True: every element of `tensor` is finite by construction (a weighted mean of finite vectors);
+    the private device copy is marked so that a consumer need not scan it again."""
     key = id(host_array)
+    if finite:
+        tensor._b200_finite = True  # the kept tensor is private to this module's table: nobody can edit it
 
     def _drop(_ref, key=key, d=_recent, lock=_recent_lock):  # globals are gone at interpreter exit
         with lock:

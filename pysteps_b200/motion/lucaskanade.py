@@ -23,6 +23,7 @@ counts (to size the next launch / take the reference's early-outs).
 """
 import ctypes
 import os
+import threading
 import time
 
 import numpy as np
@@ -112,6 +113,17 @@ def _track_image(f, m, n, buffer_mask):
 
 _side_streams = {}
 _grids = {}
+_readback = threading.local()
+
+
+def _readback_buffers(cap):
+    """Pinned host buffers (counts, xy, uv) of the sparse stage's read-back, one set per host thread."""
+    got = getattr(_readback, "bufs", None)
+    if got is None or got[1].shape[0] < cap:
+        got = _readback.bufs = (torch.empty(4, dtype=torch.int32, pin_memory=True),
+                                torch.empty((cap, 2), dtype=torch.float64, pin_memory=True),
+                                torch.empty((cap, 2), dtype=torch.float64, pin_memory=True))
+    return got[0], got[1][:cap], got[2][:cap]
 
 
 def _pixel_grid(a, b):
@@ -129,7 +141,6 @@ def _pixel_grid(a, b):
 
 def _side_stream():
     """One auxiliary stream per (device, host thread)."""
-    import threading
     key = (torch.cuda.current_device(), threading.get_ident())
     if key not in _side_streams:
         _side_streams[key] = torch.cuda.Stream()
@@ -365,7 +376,16 @@ def dense_lucaskanade(input_images, lk_kwargs=None, fd_method="shitomasi", fd_kw
               float(decl_scale), 1, dec_xy.data_ptr(), dec_uv.data_ptr(), counts[2:3].data_ptr(), _s())
     else:
         counts[2:3].copy_(counts[1:2])
-    n_pool, n_kept, n_dec, _ = counts.cpu().tolist()  # the one host read-back of the sparse stage
+    # the one host read-back of the sparse stage: the counts AND (dense case) the declustered vectors the
+    # interpolator's host-side checks look at, in one round trip -- three separate .cpu() calls were three
+    # waits with the GPU idle in between
+    pin = _readback_buffers(pool_cap)
+    pin[0].copy_(counts, non_blocking=True)
+    if dense:
+        pin[1].copy_(dec_xy, non_blocking=True)
+        pin[2].copy_(dec_uv, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    n_pool, n_kept, n_dec, _ = pin[0].tolist()
 
     if n_pool == 0:  # :245-249
         return zeros_or_empty()
@@ -386,8 +406,8 @@ def dense_lucaskanade(input_images, lk_kwargs=None, fd_method="shitomasi", fd_kw
     # deterministic, so ranks that each fill one band of the same frames agree bit for bit with
     # the rows of the full field (tile partitioning of one composite over GPUs).
     out = torch.empty((2, mb, n), dtype=torch.float64, device="cuda")
-    xy_h = dec_xy[:n_dec].cpu().numpy()
-    uv_h = dec_uv[:n_dec].cpu().numpy()
+    xy_h = pin[1][:n_dec].numpy().copy()
+    uv_h = pin[2][:n_dec].numpy().copy()
     if np.any(~np.isfinite(uv_h)):
         raise ValueError("argument 'values' contains non-finite values")
     if np.any(~np.isfinite(xy_h)):
@@ -421,4 +441,13 @@ def dense_lucaskanade(input_images, lk_kwargs=None, fd_method="shitomasi", fd_kw
     if verbose:
         torch.cuda.current_stream().synchronize()
         print("--- total time: %.2f seconds ---" % (time.time() - t0))
-    return out if on_device else _device.remember_result(_device.to_host(out), out)
+    # a weighted mean of finite vectors with weights (d + dist_offset)^-power, d >= 0: finite whenever
+    # the offset is positive (the default 0.5); the consumer then skips its finiteness scan of the copy
+    finite = bool(dense and dist_offset > 0.0 and 0.0 <= power <= 8.0)
+    if on_device:
+        if finite:
+            # a device result the caller may edit: the certificate holds for THIS version of the tensor only
+            # (torch bumps ._version on every in-place write, through views too)
+            out._b200_finite_version = out._version
+        return out
+    return _device.remember_result(_device.to_host(out), out, finite=finite)

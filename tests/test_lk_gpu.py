@@ -526,3 +526,34 @@ def test_float32_frames_vs_oracle(env):
         assert np.array_equal(xy, oxy) and np.array_equal(uv, ouv), it
         V, Vo = lk(fr), ora.dense_lucaskanade(fr)
         assert V.dtype == np.float64 and np.abs(V - Vo).max() <= 1e-12, it
+
+
+def test_finiteness_certificate_dies_with_a_write(env):
+    """The dense LK field is finite by construction, so the extrapolator skips its finiteness scan of it --
+    but only while the field is the one LK produced: any in-place write (device tensor: version counter;
+    NumPy result: content fingerprint) brings the scan, and the reference's ValueError, back."""
+    torch, _ = env
+    import pysteps_b200
+    from pysteps_b200 import _synthetic as syn
+    from pysteps_b200.extrapolation import semilagrangian as slmod
+    lk = pysteps_b200.motion.get_method("lk")
+    extrap = pysteps_b200.extrapolation.get_method("semilagrangian")
+    frames = syn.rain_frames(192, 224, 2, 1)
+    P = frames[-1]
+    # device tensors
+    V = lk(torch.from_numpy(frames).cuda())
+    assert slmod._known_finite(V)
+    ref = extrap(torch.from_numpy(P).cuda(), V, 2)
+    assert torch.equal(torch.nan_to_num(extrap(torch.from_numpy(P).cuda(), V.clone(), 2), nan=-1.0),
+                       torch.nan_to_num(ref, nan=-1.0)), "certified and scanned calls agree"
+    V[1, 5, 7] = float("nan")
+    assert not slmod._known_finite(V)
+    with pytest.raises(ValueError, match="velocity contains non-finite"):
+        extrap(torch.from_numpy(P).cuda(), V, 2)
+    # NumPy arrays
+    Vh = lk(frames)
+    assert np.isfinite(Vh).all()
+    extrap(P, Vh, 2)
+    Vh[0, 0, 0] = np.inf
+    with pytest.raises(ValueError, match="velocity contains non-finite"):
+        extrap(P, Vh, 2)

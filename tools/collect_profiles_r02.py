@@ -51,7 +51,12 @@ def main():
              "ncu launch list: dense_lucaskanade, 2 frames of 2048^2 (tools/lk_once.py)")
     launches(f"{G}/{T}_launches_sl.csv", f"profiles/{T}_launches_sl.md",
              "ncu launch list: LK field + extrapolate(P, V, 12) at 2048^2 (tools/sl_once.py)")
+    if os.path.exists(f"{G}/{T}_launches_sl_f32.csv"):
+        launches(f"{G}/{T}_launches_sl_f32.csv", f"profiles/{T}_launches_sl_f32.md",
+                 "ncu launch list: one exact and one float32-tap extrapolate(P, V, 12) at 2048^2 (tools/sl_f32_once.py)",
+                 reps=2)
     for rep, out, sub in ((f"{G}/{T}_sl.ncu-rep", f"profiles/{T}_sl_final", "sl_multistep"),
+                          (f"{G}/{T}_sl_f32.ncu-rep", f"profiles/{T}_sl_f32", "sl_f32_kernel"),
                           (f"{G}/{T}_lk.ncu-rep", f"profiles/{T}_lk_kernels", ""),
                           (f"{G}/{T}_vet.ncu-rep", f"profiles/{T}_vet_eval", "vet_eval")):
         if os.path.exists(rep):
@@ -59,7 +64,7 @@ def main():
                                   stdout=subprocess.DEVNULL)
     if os.path.exists(f"profiles/{T}_sl_final_traffic.json"):
         json.dump(json.load(open(f"profiles/{T}_sl_final_traffic.json")), open("profiles/sl_traffic.json", "w"), indent=1)
-    for name in (f"{T}_sl_timing.json", f"{T}_lk_timing.log", f"{T}_vet_time.log", f"{T}_gputests.log", f"{T}_smoke.log"):
+    for name in (f"{T}_sl_f32_timing.json", f"{T}_sl_timing.json", f"{T}_lk_timing.log", f"{T}_vet_time.log", f"{T}_gputests.log", f"{T}_smoke.log"):
         if os.path.exists(f"{G}/{name}"):
             open(f"profiles/{name}", "w").write(open(f"{G}/{name}").read())
     print("value", d["value"], "ms/step", d["ms_per_step"], "e2e", d["e2e"], "frac", d["roofline"]["frac"])
