@@ -33,6 +33,7 @@ parity : before the line is printed, one step's results are compared with the CP
 cpu_baseline: the CPU oracle (port of the reference path) on the same workload.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -440,6 +441,16 @@ def have_lk_oracle():
 
 
 # ----------------------------------------------------------------------------- GPU arm
+def settle_gc():
+    """Before a timed region: collect, then move everything alive to CPython's permanent generation
+    (gc.freeze).  A generation-2 collection of a process that has imported torch walks millions of objects
+    -- 50-60 ms, more than twenty 2.4 ms steps -- and fires wherever the allocation counter happens to
+    trip, e.g. inside a torch.empty of step 13.  It is a property of the interpreter's heap, not of the
+    path measured here; every line says `gc: frozen` so that the choice is visible."""
+    gc.collect()
+    gc.freeze()
+
+
 class Bench:
     def __init__(self):
         import torch
@@ -498,6 +509,7 @@ class Bench:
             if self.all_agree(n_w >= warmup and (n_w >= 400 or time.perf_counter() - t_w >= min_warm_s)):
                 break
         self.barrier()
+        settle_gc()
         launches0 = self.lib.load().b200_launch_count()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         phase = []
@@ -514,7 +526,8 @@ class Bench:
                     phase.append(list(marks))
             self.barrier()
         launches = self.lib.load().b200_launch_count() - launches0
-        dev_ms = self.shard.max_over_ranks(sum(s.elapsed_time(e) for s, e in ev), device="cuda")
+        self.each_ms = [s.elapsed_time(e) for s, e in ev]  # this rank's steps, one by one
+        dev_ms = self.shard.max_over_ranks(sum(self.each_ms), device="cuda")
         # per-stage table: two more, untimed, fully traced steps
         with self.lib.Trace() as stage_trace:
             for _ in range(2):
@@ -542,6 +555,7 @@ class Bench:
         for _ in range(max(4, warmup)):
             out = step()
         self.barrier()
+        settle_gc()
         t0 = time.perf_counter()
         for _ in range(steps):
             out = step()
@@ -760,6 +774,7 @@ def measure(b, w, steps, warmup, clocks=None, solo=False):
     if clocks is not None:
         clocks.__enter__()
     dev_ms, tr, launches, phases = b.time_device(step_device, steps, warmup, 0.5 if clocks is not None else 0.0, marks)
+    each_ms = list(b.each_ms)
     if clocks is not None:
         clocks.__exit__(None, None, None)
     nfields = info["nfields"]
@@ -786,7 +801,8 @@ def measure(b, w, steps, warmup, clocks=None, solo=False):
            "fields_per_gpu": 1 if w["scaling"] == "weak" else round(1.0 / world, 4),
            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(info["h2d"]),
                    "d2h_bytes_per_step": int(info["d2h"]), "ms_per_step": 1e3 * e2e_s / steps},
-           "gpu_launches": int(launches), "_trace": tr, "_info": info,
+           "gpu_launches": int(launches), "ms_each_step_rank0": [round(x, 3) for x in each_ms], "gc": "frozen",
+           "_trace": tr, "_info": info,
            "_stage_trace": stage_trace, "_stage_steps": stage_steps}
     if phases is not None and len(phases) == 2:
         blk["motion_and_broadcast_ms"] = phases[0]
