@@ -111,6 +111,7 @@ def _track_image(f, m, n, buffer_mask):
     return f.q_track
 
 
+_DECLUSTER_MAX = 16384  # csrc/sparse.cu DC_MAX (vectors held in one CTA's shared memory)
 _side_streams = {}
 _grids = {}
 _readback = threading.local()
@@ -372,7 +373,16 @@ def dense_lucaskanade(input_images, lk_kwargs=None, fd_method="shitomasi", fd_kw
     if dense and decl_scale > 1:
         dec_xy = torch.empty((pool_cap, 2), dtype=torch.float64, device="cuda")
         dec_uv = torch.empty((pool_cap, 2), dtype=torch.float64, device="cuda")
-        _call("b200_decluster", kept_xy.data_ptr(), kept_uv.data_ptr(), counts[1:2].data_ptr(), pool_cap,
+        dc_cap = pool_cap
+        if pool_cap > _DECLUSTER_MAX:
+            # the kernel's capacity is about the vectors that exist, not the pool they could fill (many
+            # frames x max_corners): one extra read-back on this rare shape instead of a refusal
+            dc_cap = int(counts[1].item())
+            if dc_cap > _DECLUSTER_MAX:
+                raise NotImplementedError(
+                    f"pysteps_b200 LK: declustering more than {_DECLUSTER_MAX} sparse vectors is not implemented "
+                    f"({dc_cap} survived the outlier test)")
+        _call("b200_decluster", kept_xy.data_ptr(), kept_uv.data_ptr(), counts[1:2].data_ptr(), max(dc_cap, 1),
               float(decl_scale), 1, dec_xy.data_ptr(), dec_uv.data_ptr(), counts[2:3].data_ptr(), _s())
     else:
         counts[2:3].copy_(counts[1:2])

@@ -214,3 +214,19 @@ def test_float32_frames_are_scaled_in_float32_like_the_reference():
             if live is not None:
                 ref = live(inp.copy(), dense=False)
                 assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]), it
+
+
+def test_many_frames_pool_larger_than_the_decluster_kernel(monkeypatch):
+    """The sparse pool holds max_corners vectors per frame pair; the decluster kernel's capacity is about
+    the vectors that EXIST.  A long stack (pool > capacity) must work off the real count -- the reference
+    has no limit -- and only a real excess is refused, by name."""
+    from pysteps_b200.motion import lucaskanade as lkmod
+    fr = syn.rain_frames(96, 112, 5, 3, dx=2, dy=-1)
+    with cpu_abi.emulated():
+        want = lkmod.dense_lucaskanade(fr)
+        monkeypatch.setattr(lkmod, "_DECLUSTER_MAX", 2000)  # 4 pairs x 1000 corners = 4000 > 2000
+        got = lkmod.dense_lucaskanade(fr)
+        assert np.array_equal(got, want)
+        monkeypatch.setattr(lkmod, "_DECLUSTER_MAX", 3)
+        with pytest.raises(NotImplementedError, match="declustering more than 3"):
+            lkmod.dense_lucaskanade(fr)
