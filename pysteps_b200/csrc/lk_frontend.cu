@@ -88,36 +88,9 @@ __device__ __forceinline__ Row load_row(const unsigned (*a)[4], int r) {
     return (Row)a[r][0] | ((Row)a[r][1] << 32) | ((Row)a[r][2] << 64);
 }
 
-// exact (x - im_min) / (im_max - im_min) * 255 -> astype(uint8) of a float64 frame, mostly
-// without the division: the product with a precomputed 255 / range is within 1.2e-13 of the
-// reference's two-rounding result, so its truncation is the reference's unless it lies within 1e-9
-// of an integer -- only then (and for values outside (0, 256)) the division is evaluated.
-struct Scale {
-    double im_min, im_max, range, r255;
-    bool wide;  // range > 1e-8
-    __device__ __forceinline__ void init(const double *st, int set) {
-        im_min = st[3 * set + 0];
-        im_max = st[3 * set + 1];
-        range = __dsub_rn(im_max, im_min);
-        wide = range > 1e-8;
-        r255 = 255.0 / range;
-    }
-    __device__ __forceinline__ uint8_t exact(double val) const {
-        const double q = wide ? __dmul_rn(__ddiv_rn(__dsub_rn(val, im_min), range), 255.0) : __dsub_rn(val, im_min);
-        return cast_u8(q);
-    }
-    __device__ __forceinline__ uint8_t operator()(double val) const {
-        const double num = __dsub_rn(val, im_min);
-        if (num == 0.0) return 0;  // 0 / range * 255, or 0 itself
-        if (wide) {
-            const double qa = __dmul_rn(num, r255);
-            constexpr double MAGIC = 6755399441055744.0;  // 2^52 + 2^51: nearest integer in the low word
-            const double t = __dadd_rn(qa, MAGIC);
-            const double d = __dsub_rn(qa, __dsub_rn(t, MAGIC));  // qa - nearest, in [-0.5, 0.5]
-            if (qa > 0.0 && qa < 255.5 && fabs(d) > 1e-9) return (uint8_t)(__double2loint(t) - (d < 0.0 ? 1 : 0));
-        }
-        return exact(val);
-    }
+// uint8 scaling of float64 frames: qz::ScaleF64 (quantise_body.cuh, also compiled and tested on the host)
+struct Scale : qz::ScaleF64 {
+    __device__ __forceinline__ void init(const double *st, int set) { qz::ScaleF64::init(st[3 * set + 0], st[3 * set + 1]); }
 };
 
 // PASS = 1: statistics of the opened image.  PASS = 2: uint8 images.

@@ -140,7 +140,7 @@ __device__ __noinline__ double slow_precip(const PT *__restrict__ P, int m, int 
 
 // ---- fast path: footprint strictly inside the array ------------------------------------
 // floor via a round-DOWN add of 2^52+2^51: the sum's low word IS (int)floor(c) and its high
-// word is 0x43380000 exactly when 0 <= floor(c) < 2^31, so validity, floor and the integer
+// word is 0x43380000 exactly when 0 <= floor(c) < 2^32, so validity, floor and the integer
 // index cost two FP64-pipe adds and integer compares -- no FRND/F2I/I2F (XU pipe).
 struct Foot {
     int base;  // y0 * n + x0
@@ -152,8 +152,10 @@ __device__ __forceinline__ Foot footprint(double cy, double cx, int n, int ymax,
     Foot f;
     const double sy = __dadd_rd(cy, SL_MAGIC), sx = __dadd_rd(cx, SL_MAGIC);
     const int iy = __double2loint(sy), ix = __double2loint(sx);
+    // (unsigned compares against ymax + 1 = m - 1 >= 0: the high-word test admits 0 <= floor < 2^32, an index
+    // of 2^31 or more reads as a negative int and must fail like every other index beyond the last row)
     f.interior = (__double2hiint(sy) == 0x43380000) & (__double2hiint(sx) == 0x43380000) &
-                 (iy <= ymax) & (ix <= xmax) & (iy >= 0) & (ix >= 0);
+                 ((unsigned)iy < (unsigned)(ymax + 1)) & ((unsigned)ix < (unsigned)(xmax + 1));
     const double ty = __dsub_rn(cy, __dsub_rn(sy, SL_MAGIC));
     const double tx = __dsub_rn(cx, __dsub_rn(sx, SL_MAGIC));
     f.wy0 = __dsub_rn(1.0, ty); f.wy1 = __dsub_rn(1.0, f.wy0);
@@ -356,9 +358,9 @@ __device__ __forceinline__ FootF sample_f32(const float2 *__restrict__ Vf, int n
     FootF f;
     const double sy = __dadd_rd(cy, SL_MAGIC), sx = __dadd_rd(cx, SL_MAGIC);
     const int iy = __double2loint(sy), ix = __double2loint(sx);
-    // (unsigned compares: a negative index is a huge unsigned; ymax / xmax < 0 -- no interior -- fail them all)
+    // (unsigned compares against ymax + 1 = m - 1 >= 0, see footprint())
     const bool interior = (__double2hiint(sy) == 0x43380000) & (__double2hiint(sx) == 0x43380000) &
-                          ((unsigned)iy <= (unsigned)ymax) & ((unsigned)ix <= (unsigned)xmax) & (ymax >= 0) & (xmax >= 0);
+                          ((unsigned)iy < (unsigned)(ymax + 1)) & ((unsigned)ix < (unsigned)(xmax + 1));
     f.ty = (float)__dsub_rn(cy, __dsub_rn(sy, SL_MAGIC));
     f.tx = (float)__dsub_rn(cx, __dsub_rn(sx, SL_MAGIC));
     // both fractions in (lo, 1 - lo) with lo = e + 2 eps  <=>  max |t - 1/2| < 1/2 - lo

@@ -94,4 +94,21 @@ void host_scale_f32(const double *v, int64_t count, double im_min, double im_max
     for (int64_t i = 0; i < count; i++) out[i] = qz::scale_f32(v[i], im_min, im_max);
 }
 
+// float64 scaling to uint8 of the fused front end: the division-free path and the division itself
+void host_scale_f64(const double *v, int64_t count, double im_min, double im_max, unsigned char *out_fast,
+                    unsigned char *out_exact, int64_t *n_fallback) {
+    qz::ScaleF64 sc;
+    sc.init(im_min, im_max);
+    int64_t nf = 0;
+    for (int64_t i = 0; i < count; i++) {
+        out_fast[i] = sc(v[i]);
+        out_exact[i] = sc.exact(v[i]);
+        // (how often the fast path defers to the division: reported, not asserted)
+        const double num = v[i] - im_min, qa = num * sc.r255;
+        const double t = qa + 6755399441055744.0, d = qa - (t - 6755399441055744.0);
+        if (!(num == 0.0) && !(sc.wide && qa > 0.0 && qa < 255.5 && (d > 1e-9 || d < -1e-9))) nf++;
+    }
+    *n_fallback = nf;
+}
+
 }  // extern "C"

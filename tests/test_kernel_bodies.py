@@ -333,3 +333,43 @@ def test_float32_quantise_body_matches_numpy():
                          ctypes.c_double(float(mx)), _p(got))
         assert_bits_equal(got.astype(np.float32), want, f"range {lo}..{hi}")
         assert np.array_equal(got, want.astype(np.float64))
+
+
+def test_float64_quantise_body_matches_numpy_at_and_around_integer_boundaries():
+    """The fused LK front end scales float64 frames to uint8 with a precomputed 255 / range and evaluates the
+    reference's division only near integer results (csrc/quantise_body.cuh ScaleF64).  Against NumPy's
+    `((x - min) / (max - min) * 255).astype('uint8')` on random values AND on values whose scaled image
+    sits exactly on, and a few ulps either side of, every integer 0..255."""
+    L = host_kernels.lib()
+    L.host_scale_f64.restype = None
+    rng = np.random.default_rng(17)
+    u8p = ctypes.POINTER(ctypes.c_uint8)
+    total_fb = 0
+    for lo, hi in ((0.0, 40.0), (-15.0, 43.7), (0.0, 255.0), (1.25, 1.25 + 1e-6), (-3.0e5, 7.7e6), (0.1, 0.3),
+                   (0.0, 1e-9), (2.5, 2.5), (0.0, float(np.float32(37.123)))):
+        rngw = hi - lo
+        x = rng.uniform(lo, hi if hi > lo else lo + 1.0, 200000)
+        if rngw > 1e-8:
+            k = np.arange(256, dtype=np.float64)
+            onb = lo + k / 255.0 * rngw                     # lands on / next to integers after scaling
+            near = [onb]
+            for _ in range(6):
+                near.append(np.nextafter(near[-1], np.inf))
+            dn = onb
+            for _ in range(6):
+                dn = np.nextafter(dn, -np.inf)
+                near.append(dn)
+            x = np.concatenate([x] + near + [np.array([lo, hi, lo - 0.37 * rngw, hi + 0.41 * rngw, np.nan, np.inf])])
+        x = np.ascontiguousarray(x)
+        with np.errstate(invalid="ignore", divide="ignore", over="ignore"):
+            q = ((x - lo) / (hi - lo) * 255) if hi - lo > 1e-8 else (x - lo)
+            want = np.trunc(np.where(np.isfinite(q) & (np.abs(q) < 2147483648.0), q, 0.0)).astype(np.int64).astype(np.uint8)
+        fast = np.empty(x.size, np.uint8)
+        exact = np.empty(x.size, np.uint8)
+        nfb = ctypes.c_int64(0)
+        L.host_scale_f64(_p(x), ctypes.c_int64(x.size), ctypes.c_double(lo), ctypes.c_double(hi),
+                         fast.ctypes.data_as(u8p), exact.ctypes.data_as(u8p), ctypes.byref(nfb))
+        assert np.array_equal(exact, want), f"division path, range {lo}..{hi}"
+        assert np.array_equal(fast, want), f"division-free path, range {lo}..{hi}: {(fast != want).sum()} differ"
+        total_fb += nfb.value
+    assert total_fb > 0  # the boundary values did exercise the fallback

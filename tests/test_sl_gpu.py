@@ -391,3 +391,20 @@ def test_float32_taps_full_size(sl):
     print(f"float32 taps 2048^2 T=12: max value error {err:.3e}, max displacement error "
           f"{(dfa - dex).abs().max().item():.3e}, {100 * frac:.3f} % of the pixels recomputed exactly")
     assert frac < 0.05
+
+
+@pytest.mark.parametrize("mag", [3.0e9, 5.0e9, 1.0e19, 2147483648.5])
+def test_absurd_displacements_follow_the_reference(sl, mag):
+    """Coordinates of 2^31 pixels and beyond: the interior test reads the floor from the low word of a
+    magic-constant sum, so an index >= 2^31 must not pass as a small negative one.  (The reference goes
+    through `(npy_intp)floor(c)`; the oracle reproduces it, incl. the INT64_MIN of out-of-range values.)"""
+    from pysteps_b200 import _synthetic as syn
+    m, n = 40, 56
+    P = syn.rain_field(m, n, 8) + 1.0
+    V = np.zeros((2, m, n))
+    V[0, :, ::2] = -mag      # backward trajectory: coordinates x + mag (columns), rows untouched
+    V[1, ::3, :] = mag       # coordinates y - mag
+    V[0, 5:9, 5:9] = 1.5     # and ordinary pixels among them
+    for kw in (dict(), dict(map_coordinates_mode="nearest"), dict(outval=-1.0, n_iter=2)):
+        got, want = _run_both(sl, (P, V, 2), dict(return_displacement=True, **kw))
+        _compare(got, want, f"|V| = {mag:g} {kw}")
