@@ -134,6 +134,8 @@ class ClockSampler:
         self.thread = None
         self.source = None
         self._stop = False
+        self.paused = False   # True inside a timed region: the background thread does not touch NVML there
+        self._nv = None
 
     def _nvml_handle(self):
         import pynvml
@@ -147,15 +149,27 @@ class ClockSampler:
             phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
             return pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
 
+    def _sample(self, nv, h):
+        try:
+            self.samples.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM),
+                                 nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM),
+                                 int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))))
+        except Exception:
+            pass
+
     def _poll(self, nv, h):
         while not self._stop:
-            try:
-                self.samples.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM),
-                                     nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM),
-                                     int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))))
-            except Exception:
-                pass
+            if not self.paused:
+                self._sample(nv, h)
             time.sleep(0.2)
+
+    def sample_now(self):
+        """One sample from the CALLING thread.  Used at step boundaries inside the timed region, outside the
+        CUDA-event brackets: an NVML query can hold the driver's launch path for tens of ms (one 52 ms step
+        in twenty 2.4 ms ones when the background thread's poll fell into the 60 ms timed region); taken
+        between two steps it delays nothing that is timed."""
+        if self._nv is not None:
+            self._sample(*self._nv)
 
     def __enter__(self):
         if not self.enabled:
@@ -163,7 +177,9 @@ class ClockSampler:
         try:
             import threading
             nv, h = self._nvml_handle()
-            self.source = "nvml (pynvml), 200 ms"
+            self._nv = (nv, h)
+            self.source = ("nvml (pynvml): every 200 ms during the warm-up load, at step boundaries inside the "
+                           "timed region (outside the event brackets)")
             self.thread = threading.Thread(target=self._poll, args=(nv, h), daemon=True)
             self.thread.start()
             time.sleep(0.25)
@@ -495,7 +511,7 @@ class Bench:
         self.dist.broadcast(t, src=0)
         return bool(t.item())
 
-    def time_device(self, step, steps, warmup, min_warm_s=0.0, marks=None):
+    def time_device(self, step, steps, warmup, min_warm_s=0.0, marks=None, sampler=None):
         """W >= 3 untimed steps (stretched to min_warm_s of the same load for the clock sampler),
         then `steps` steps, each bracketed by barrier + synchronize and CUDA events, L2 flushed in
         between (outside the events).  Returns (ms summed over steps [max over ranks], trace,
@@ -510,13 +526,20 @@ class Bench:
                 break
         self.barrier()
         settle_gc()
+        step()  # one more untimed step: whatever the collection left to be re-established is paid here
+        torch.cuda.synchronize()
+        self.barrier()
         launches0 = self.lib.load().b200_launch_count()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         phase = []
         # inside the timed region only the rated kernel's call carries CUDA events (two events per
         # traced call cost ~15 us of host time: 14 ms of an ensemble step when every call is traced)
+        if sampler is not None:
+            sampler.paused = True
         with self.lib.Trace(only=("b200_sl_extrapolate_rows", "b200_sl_extrapolate")) as trace:
-            for s, e in ev:
+            for i, (s, e) in enumerate(ev):
+                if sampler is not None and i in (1, steps // 2, steps - 1):
+                    sampler.sample_now()  # the previous step is still executing: a sample under load
                 self.flush.fill_(1)
                 self.barrier()
                 s.record()
@@ -524,7 +547,11 @@ class Bench:
                 e.record()
                 if marks is not None:
                     phase.append(list(marks))
+            if sampler is not None:
+                sampler.sample_now()
             self.barrier()
+        if sampler is not None:
+            sampler.paused = False
         launches = self.lib.load().b200_launch_count() - launches0
         self.each_ms = [s.elapsed_time(e) for s, e in ev]  # this rank's steps, one by one
         dev_ms = self.shard.max_over_ranks(sum(self.each_ms), device="cuda")
@@ -773,7 +800,8 @@ def measure(b, w, steps, warmup, clocks=None, solo=False):
     marks = info.get("marks")
     if clocks is not None:
         clocks.__enter__()
-    dev_ms, tr, launches, phases = b.time_device(step_device, steps, warmup, 0.5 if clocks is not None else 0.0, marks)
+    dev_ms, tr, launches, phases = b.time_device(step_device, steps, warmup, 0.5 if clocks is not None else 0.0, marks,
+                                                 sampler=clocks)
     each_ms = list(b.each_ms)
     if clocks is not None:
         clocks.__exit__(None, None, None)
