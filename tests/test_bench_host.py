@@ -51,3 +51,57 @@ def test_reference_arm_runs_with_all_host_threads_under_a_launcher(monkeypatch, 
     assert line["cpu_baseline"]["cores"] in (ncpu, max(ncpu // 2, 1)) and line["cpu_baseline"]["cores"] > 1
     assert line["n_gpus"] == 4 and line["cpu_baseline"]["kind"] in ("reference", "port")
     assert line["value"] > 0 and line["e2e"]["value"] == line["value"]
+
+
+def test_clock_sampler_is_silent_inside_a_timed_region():
+    """bench.py's NVML sampler: the background thread polls only while not paused; inside a timed region the
+    main thread samples at step boundaries (a background query there stalled one timed step by 50 ms)."""
+    import time
+
+    import bench
+
+    class FakeNvml:
+        NVML_CLOCK_SM = 0
+        calls = 0
+
+        def nvmlDeviceGetClockInfo(self, h, k):
+            FakeNvml.calls += 1
+            return 1965
+
+        def nvmlDeviceGetMaxClockInfo(self, h, k):
+            return 1965
+
+        def nvmlDeviceGetCurrentClocksEventReasons(self, h):
+            return 0x4  # sw_power_cap: kept and noted
+
+    c = bench.ClockSampler(0, enabled=True)
+    c._nvml_handle = lambda: (FakeNvml(), object())
+    c.__enter__()
+    time.sleep(0.3)
+    c.paused = True
+    time.sleep(0.25)
+    n = FakeNvml.calls
+    time.sleep(0.45)
+    assert FakeNvml.calls == n, "the background thread touched NVML while paused"
+    c.sample_now()
+    c.sample_now()
+    assert FakeNvml.calls == n + 2
+    c.paused = False
+    c.__exit__(None, None, None)
+    s = c.summary()
+    assert s["sm_mhz"] == 1965 and s["reasons"] == ["sw_power_cap"] and s["samples"] >= 3
+    off = bench.ClockSampler(0, enabled=False)
+    off.sample_now()  # no handle: a no-op on the ranks that do not sample
+    assert off.summary()["reasons"] == ["unsampled"]
+
+
+def test_settle_gc_freezes_the_heap():
+    import gc
+
+    import bench
+    junk = [[i] for i in range(1000)]
+    before = gc.get_freeze_count()
+    bench.settle_gc()
+    assert gc.get_freeze_count() > before
+    del junk
+    gc.unfreeze()
